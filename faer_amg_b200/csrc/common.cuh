@@ -1,0 +1,186 @@
+// common.cuh -- internal types of libfamg (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/famg.h"
+
+namespace famg {
+
+// ---------------------------------------------------------------- error plumbing
+void set_error(const char *fmt, ...);
+const char *get_error();
+
+#define FAMG_FAIL(code, ...)          \
+    do {                              \
+        ::famg::set_error(__VA_ARGS__); \
+        return (code);                \
+    } while (0)
+
+#define CUDA_TRY(expr)                                                                     \
+    do {                                                                                   \
+        cudaError_t e__ = (expr);                                                          \
+        if (e__ != cudaSuccess) {                                                          \
+            ::famg::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr,           \
+                              cudaGetErrorString(e__));                                    \
+            return FAMG_ERR_CUDA;                                                          \
+        }                                                                                  \
+    } while (0)
+
+#define FAMG_TRY(expr)                 \
+    do {                               \
+        famg_status s__ = (expr);      \
+        if (s__ != FAMG_OK) return s__; \
+    } while (0)
+
+#define KERNEL_CHECK()  CUDA_TRY(cudaGetLastError())
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace famg
+
+// ---------------------------------------------------------------- handles
+struct famg_ctx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t comm_stream = nullptr;  // halo exchange overlaps interior rows on this stream
+    std::atomic<int64_t> launches{0};
+    // small persistent scratch: scalars for dots / norms, pinned host mirror
+    double *d_scalars = nullptr;  // 64 doubles
+    double *h_scalars = nullptr;  // pinned, 64 doubles
+    double *d_partials = nullptr; // per-block partial sums
+    int64_t partials_cap = 0;
+    double *pcg_ws = nullptr;     // PCG work vectors (r, p, z, q), kept so the V-cycle graph is reused
+    int64_t pcg_ws_cap = 0;
+    std::mutex mu;
+};
+
+struct famg_csr {
+    famg_ctx *ctx = nullptr;
+    std::atomic<int> refs{1};
+    int64_t nrows = 0, ncols = 0, nnz = 0;
+    int *row_ptr = nullptr;  // nrows+1 (+pad)
+    int *col = nullptr;      // nnz (+16 pad, zero filled)
+    double *val = nullptr;   // nnz (+16 pad)
+    // SpMV plan from row-length statistics
+    int tpr = 1;             // threads per row (power of two, 1..32)
+    int max_row_nnz = 0;
+    double avg_row_nnz = 0.0;
+};
+
+struct famg_vec {
+    famg_ctx *ctx = nullptr;
+    int64_t nrows = 0, ncols = 0, ld = 0;
+    double *p = nullptr;
+    bool owns = true;
+};
+
+enum SmootherKind { SM_DIAG = 0, SM_DENSE_INV = 1, SM_SPARSE_INV = 2 };
+
+struct famg_smoother {
+    famg_ctx *ctx = nullptr;
+    std::atomic<int> refs{1};
+    int kind = SM_DIAG;
+    int64_t n = 0;
+    double *d = nullptr;      // SM_DIAG: n
+    double *inv = nullptr;    // SM_DENSE_INV: n x n column-major explicit inverse
+    famg_csr *minv = nullptr; // SM_SPARSE_INV: block-diagonal M^-1 as CSR
+};
+
+namespace famg {
+
+// ---------------------------------------------------------------- allocation helpers
+template <typename T>
+famg_status dev_alloc(T **p, int64_t count) {
+    *p = nullptr;
+    size_t bytes = sizeof(T) * (size_t)(count > 0 ? count : 1);
+    cudaError_t e = cudaMalloc((void **)p, bytes);
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        return e == cudaErrorMemoryAllocation ? FAMG_ERR_ALLOC : FAMG_ERR_CUDA;
+    }
+    return FAMG_OK;
+}
+
+constexpr int CSR_PAD = 16;  // elements of slack after col/val so aligned 128-bit reads may overrun
+
+famg_status csr_alloc(famg_ctx *ctx, int64_t nrows, int64_t ncols, int64_t nnz, famg_csr **out);
+famg_status csr_finalize_plan(famg_csr *a);  // row statistics -> threads-per-row
+void csr_release(famg_csr *a);
+void smoother_release(famg_smoother *s);
+famg_status vec_wrap(famg_ctx *ctx, double *p, int64_t nrows, int64_t ncols, int64_t ld, famg_vec *out);
+
+famg_status ensure_partials(famg_ctx *ctx, int64_t count);
+
+inline void count_launch(famg_ctx *ctx, int n = 1) { ctx->launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---------------------------------------------------------------- device primitives (scan.cu)
+// exclusive scan of n ints; out[n] = total (out has n+1 entries). in may alias out.
+famg_status exclusive_scan_i32(famg_ctx *ctx, const int *in, int *out, int64_t n);
+
+// ---------------------------------------------------------------- SpMV family (spmv.cu)
+enum Epi { EPI_SPMV = 0, EPI_RESID = 1, EPI_SMOOTH = 2, EPI_ADD = 3, EPI_SI = 4 };
+struct SpmvArgs {
+    const famg_csr *a = nullptr;
+    int epi = EPI_SPMV;
+    const double *x = nullptr; int64_t ldx = 0;  // gather source (ncols rows)
+    double *y = nullptr;       int64_t ldy = 0;  // output (nrows rows)
+    const double *b = nullptr; int64_t ldb = 0;  // rhs (RESID, SMOOTH)
+    const double *d = nullptr;                   // diagonal (SMOOTH, SI)
+    int k = 1;
+    double *dot_partials = nullptr;              // k == 1: per-CTA partial of sum_i x[i]*(A x)[i]
+    int row_begin = 0, row_end = -1;             // row range (distributed interior/boundary split)
+    cudaStream_t stream = nullptr;               // default: ctx stream
+};
+famg_status spmv_launch(const SpmvArgs &args, int *num_ctas = nullptr);
+
+// ---------------------------------------------------------------- vector ops (vecops.cu)
+famg_status vec_scale_rows(famg_ctx *ctx, const double *d, const double *in, int64_t ldi, double *out,
+                           int64_t ldo, int64_t n, int k, cudaStream_t st = nullptr);  // out = d .* in
+famg_status vec_fill(famg_ctx *ctx, double *p, int64_t ld, int64_t n, int k, double v);
+famg_status vec_copy(famg_ctx *ctx, double *dst, int64_t ldd, const double *src, int64_t lds, int64_t n, int k);
+// deterministic reductions: result(s) left in ctx->d_scalars[slot]
+famg_status vec_dot(famg_ctx *ctx, const double *x, const double *y, int64_t n, int slot, cudaStream_t st = nullptr);
+famg_status reduce_partials(famg_ctx *ctx, const double *partials, int64_t count, int slot, cudaStream_t st = nullptr);
+// PCG fused updates (k = 1); scalars live on the device
+// x += alpha p; r -= alpha q; partial ||r||^2 -> slot_rr   with alpha = s[num]/s[den]
+famg_status pcg_update_xr(famg_ctx *ctx, double *x, double *r, const double *p, const double *q, int64_t n,
+                          int slot_num, int slot_den, int slot_rr);
+// p = z + beta p with beta = s[num]/s[den]
+famg_status pcg_update_p(famg_ctx *ctx, double *p, const double *z, int64_t n, int slot_num, int slot_den);
+famg_status vec_axpby_sub(famg_ctx *ctx, double *out, const double *a, const double *b, int64_t n);  // out = a - b
+famg_status vec_add_inplace(famg_ctx *ctx, double *x, const double *y, int64_t n);  // x += y
+famg_status read_scalars(famg_ctx *ctx, int first, int count, double *host);  // sync D2H
+
+// ---------------------------------------------------------------- dense coarse solve (coarse.cu)
+famg_status dense_inverse_from_csr(const famg_csr *a, double **d_inv);  // host Cholesky + inverse, uploaded
+famg_status dense_gemv(famg_ctx *ctx, const double *inv, int64_t n, const double *x, int64_t ldx, double *y,
+                       int64_t ldy, int k, cudaStream_t st = nullptr);
+
+// ---------------------------------------------------------------- smoother apply (smoothers.cu)
+famg_status smoother_apply_dev(const famg_smoother *s, const double *in, int64_t ldi, double *out, int64_t ldo,
+                               int k, cudaStream_t st = nullptr);
+
+// host copies of a device CSR (setup-time helpers)
+struct HostCsr {
+    int64_t nrows = 0, ncols = 0;
+    std::vector<int> row_ptr, col;
+    std::vector<double> val;
+};
+famg_status csr_to_host(const famg_csr *a, HostCsr *h);
+famg_status csr_from_host_i32(famg_ctx *ctx, int64_t nrows, int64_t ncols, const int *row_ptr, const int *col,
+                              const double *val, famg_csr **out);
+
+}  // namespace famg

@@ -1,0 +1,676 @@
+// dist.cu -- row-partitioned multigrid + PCG across GPUs (one process per GPU, NCCL over NVLink).
+//
+// The reference has no distributed path at all; its row-block parallelism
+// (par_spmm.rs:100-110: independent 8192-row tasks reading a shared x) is the decomposition kept
+// here, with x no longer shared:
+//   * every level l < L_rep is split into contiguous row slabs (one per rank); vectors are split
+//     conformally.  A slab's column indices are renumbered to [owned | ghost]; each operator
+//     (A_l, R_l, P_l) owns a halo plan: per-peer receive ranges in the ghost tail and per-peer
+//     pack lists, both derived at setup from the replicated global matrix (no setup collective).
+//   * an apply packs the boundary entries, posts grouped ncclSend/ncclRecv on the comm stream,
+//     runs the ghost-free interior rows on the compute stream meanwhile, then the boundary rows.
+//   * levels with fewer than `replicate_below` rows per rank (and always the coarsest) are run
+//     replicated on the global operators after one gather of the restricted residual; every rank
+//     then already holds the full coarse correction, so nothing is scattered back.
+//   * PCG dot products are local deterministic reductions + one ncclAllReduce of a single double.
+// NCCL is resolved with dlopen at first use so that single-GPU users never need it and the copy
+// already loaded by the host process (e.g. torch's) is shared.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cmath>
+
+#include "mg_internal.cuh"
+
+namespace famg {
+
+struct NcclApi {
+    void *handle = nullptr;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclSend) Send = nullptr;
+    decltype(&ncclRecv) Recv = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclBroadcast) Broadcast = nullptr;
+};
+static NcclApi g_nccl;
+static std::mutex g_nccl_mu;
+
+static famg_status nccl_load() {
+    std::lock_guard<std::mutex> lk(g_nccl_mu);
+    if (g_nccl.handle) return FAMG_OK;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) FAMG_FAIL(FAMG_ERR_COMM, "cannot load libnccl.so.2: %s", dlerror());
+#define LOAD(name)                                                                   \
+    g_nccl.name = (decltype(g_nccl.name))dlsym(h, "nccl" #name);                     \
+    if (!g_nccl.name) { dlclose(h); FAMG_FAIL(FAMG_ERR_COMM, "libnccl lacks nccl" #name); }
+    LOAD(GetUniqueId) LOAD(CommInitRank) LOAD(CommDestroy) LOAD(GetErrorString) LOAD(GroupStart) LOAD(GroupEnd)
+    LOAD(Send) LOAD(Recv) LOAD(AllReduce) LOAD(Broadcast)
+#undef LOAD
+    g_nccl.handle = h;
+    return FAMG_OK;
+}
+
+#define NCCL_TRY(expr)                                                                              \
+    do {                                                                                            \
+        ncclResult_t r__ = (expr);                                                                  \
+        if (r__ != ncclSuccess) FAMG_FAIL(FAMG_ERR_COMM, "%s failed: %s", #expr, g_nccl.GetErrorString(r__)); \
+    } while (0)
+
+}  // namespace famg
+
+struct famg_comm {
+    famg_ctx *ctx = nullptr;
+    int nranks = 1, rank = 0;
+    ncclComm_t comm = nullptr;
+    cudaEvent_t ev_packed = nullptr, ev_halo = nullptr;
+};
+
+namespace famg {
+
+// ---------------------------------------------------------------- halo plans
+struct HaloPlan {
+    int nloc = 0, nghost = 0;
+    std::vector<int> recv_cnt, recv_off, send_cnt, send_off;
+    int total_send = 0;
+    int *d_send_idx = nullptr;
+    double *d_sendbuf = nullptr;
+    bool any = false;
+};
+
+struct DistOp {
+    famg_csr *local = nullptr;  // slab, columns renumbered to [owned | ghost]
+    HaloPlan halo;
+    int ib = 0, ie = 0;         // rows [ib, ie) reference no ghost column
+};
+
+struct DistLevel {
+    int64_t r0 = 0, r1 = 0;  // owned rows of this level
+    DistOp A, R, P;          // R: rows of level l+1 (owned), cols level l.  P: rows level l, cols level l+1
+    bool has_R = false, has_P = false;
+    double *d = nullptr;     // owned slice of the Diag smoother
+    double *x = nullptr, *b = nullptr, *t = nullptr;  // work vectors with ghost tails
+    int64_t ld = 0;
+};
+
+}  // namespace famg
+
+struct famg_dist_mg {
+    famg_comm *comm = nullptr;
+    famg_mg *global = nullptr;
+    int lrep = 0;  // first replicated level
+    std::vector<famg::DistLevel> lv;
+    std::vector<std::vector<int64_t>> splits;  // per level, nranks+1
+    // transition buffers: gathered rhs / replicated solution of level lrep, and this rank's piece
+    // of the restricted residual before the gather
+    double *g_f = nullptr, *g_v = nullptr, *fc_loc = nullptr;
+    // PCG work vectors (with ghost tail for p)
+    double *pcg = nullptr; int64_t pcg_ld = 0;
+};
+
+namespace famg {
+
+__global__ void mark_ghost_kernel(const int *__restrict__ rp, const int *__restrict__ col, int row0, int row1, int c0, int c1,
+                                  int *__restrict__ flags, int invert) {
+    // invert == 0: flag columns outside [c0,c1) (global index).  invert == 1: flag columns inside
+    // [c0,c1), stored relative to c0 (what the slab [row0,row1) needs from the owner of [c0,c1)).
+    const int i = row0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= row1) return;
+    for (int q = rp[i]; q < rp[i + 1]; ++q) {
+        const int c = col[q];
+        const bool inside = c >= c0 && c < c1;
+        if (!invert) { if (!inside) flags[c] = 1; }
+        else if (inside) flags[c - c0] = 1;
+    }
+}
+__global__ void compact_kernel(const int *__restrict__ flags, const int *__restrict__ pos, int n, int *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flags[i]) out[pos[i]] = i;
+}
+__global__ void gather_int_kernel(const int *__restrict__ src, const int *__restrict__ idx, int n, int *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = src[idx[i]];
+}
+__global__ void renumber_kernel(int *__restrict__ col, int nnz, int c0, int c1, const int *__restrict__ ghost_pos) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nnz) return;
+    const int c = col[q];
+    col[q] = (c >= c0 && c < c1) ? c - c0 : (c1 - c0) + ghost_pos[c];
+}
+__global__ void interior_range_kernel(const int *__restrict__ rp, const int *__restrict__ col, int nrows, int nloc_cols,
+                                      int *__restrict__ lo_hi) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrows) return;
+    bool ghost = false;
+    for (int q = rp[i]; q < rp[i + 1]; ++q) ghost |= col[q] >= nloc_cols;
+    if (!ghost) return;
+    const int mid = nrows / 2;
+    if (i < mid) atomicMax(&lo_hi[0], i + 1); else atomicMin(&lo_hi[1], i);
+}
+__global__ void pack_kernel(const double *__restrict__ x, const int *__restrict__ idx, int n, double *__restrict__ buf) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) buf[i] = x[idx[i]];
+}
+
+static void halo_free(HaloPlan &h) { cudaFree(h.d_send_idx); cudaFree(h.d_sendbuf); h.d_send_idx = nullptr; h.d_sendbuf = nullptr; }
+static void distop_free(DistOp &o) { if (o.local) csr_release(o.local); o.local = nullptr; halo_free(o.halo); }
+
+// Build the slab of `m` owned by `rank` (rows rs[rank]..rs[rank+1]) with columns split by cs.
+static famg_status distop_build(famg_comm *cm, const famg_csr *m, const std::vector<int64_t> &rs, const std::vector<int64_t> &cs,
+                                bool replicated_cols, DistOp *op) {
+    famg_ctx *ctx = cm->ctx;
+    const int nr = cm->nranks, me = cm->rank;
+    const int row0 = (int)rs[me], row1 = (int)rs[me + 1];
+    FAMG_TRY(famg_csr_row_slab(m, row0, row1, &op->local));
+    HaloPlan &h = op->halo;
+    h.recv_cnt.assign(nr, 0); h.recv_off.assign(nr, 0); h.send_cnt.assign(nr, 0); h.send_off.assign(nr, 0);
+    op->ib = 0; op->ie = row1 - row0;
+    if (replicated_cols) {  // the consumer vector is replicated: global column indices, no halo
+        h.nloc = (int)m->ncols; h.nghost = 0; h.any = false;
+        return FAMG_OK;
+    }
+    const int c0 = (int)cs[me], c1 = (int)cs[me + 1], ncols = (int)m->ncols;
+    h.nloc = c1 - c0;
+    int *flags = nullptr, *pos = nullptr, *small = nullptr;
+    famg_status st = dev_alloc(&flags, ncols + 1);
+    if (st == FAMG_OK) st = dev_alloc(&pos, ncols + 2);
+    if (st == FAMG_OK) st = dev_alloc(&small, 4 * nr + 8);
+    auto done = [&](famg_status s) { cudaStreamSynchronize(ctx->stream); cudaFree(flags); cudaFree(pos); cudaFree(small); return s; };
+    if (st != FAMG_OK) return done(st);
+    // 1. my ghost columns (ascending => grouped by owner rank)
+    cudaMemsetAsync(flags, 0, sizeof(int) * (ncols + 1), ctx->stream);
+    if (row1 > row0) {
+        mark_ghost_kernel<<<(unsigned)ceil_div(row1 - row0, 256), 256, 0, ctx->stream>>>(m->row_ptr, m->col, row0, row1, c0, c1, flags, 0);
+        count_launch(ctx);
+    }
+    st = exclusive_scan_i32(ctx, flags, pos, ncols);
+    if (st != FAMG_OK) return done(st);
+    {
+        std::vector<int> hs(nr + 1), hp(nr + 1);
+        for (int p = 0; p <= nr; ++p) hs[p] = (int)cs[p];
+        cudaMemcpy(small, hs.data(), sizeof(int) * (nr + 1), cudaMemcpyHostToDevice);
+        gather_int_kernel<<<1, 256, 0, ctx->stream>>>(pos, small, nr + 1, small + nr + 1);
+        count_launch(ctx);
+        cudaStreamSynchronize(ctx->stream);
+        cudaMemcpy(hp.data(), small + nr + 1, sizeof(int) * (nr + 1), cudaMemcpyDeviceToHost);
+        if (nr + 1 > 256) return done((set_error("too many ranks"), FAMG_ERR_UNSUPPORTED));
+        for (int p = 0; p < nr; ++p) { h.recv_cnt[p] = hp[p + 1] - hp[p]; h.recv_off[p] = hp[p]; }
+        h.nghost = hp[nr];
+        if (h.recv_cnt[me] != 0) return done((set_error("internal: own columns flagged as ghosts"), FAMG_ERR_INVALID));
+    }
+    // 2. renumber the slab's columns
+    if (op->local->nnz) {
+        renumber_kernel<<<(unsigned)ceil_div(op->local->nnz, 256), 256, 0, ctx->stream>>>(op->local->col, (int)op->local->nnz, c0, c1, pos);
+        count_launch(ctx);
+    }
+    op->local->ncols = h.nloc + h.nghost;
+    // 3. what every peer needs from me (ascending local index => same order as the peer's ghost list)
+    std::vector<std::vector<int>> send_lists(nr);
+    for (int p = 0; p < nr; ++p) {
+        if (p == me || h.nloc == 0 || rs[p + 1] == rs[p]) continue;
+        cudaMemsetAsync(flags, 0, sizeof(int) * (h.nloc + 1), ctx->stream);
+        mark_ghost_kernel<<<(unsigned)ceil_div(rs[p + 1] - rs[p], 256), 256, 0, ctx->stream>>>(m->row_ptr, m->col, (int)rs[p], (int)rs[p + 1],
+                                                                                                c0, c1, flags, 1);
+        count_launch(ctx);
+        st = exclusive_scan_i32(ctx, flags, pos, h.nloc);
+        if (st != FAMG_OK) return done(st);
+        int cnt = 0;
+        cudaMemcpy(&cnt, pos + h.nloc, sizeof(int), cudaMemcpyDeviceToHost);
+        h.send_cnt[p] = cnt;
+        if (cnt) {
+            int *tmp = nullptr;
+            st = dev_alloc(&tmp, cnt);
+            if (st != FAMG_OK) return done(st);
+            compact_kernel<<<(unsigned)ceil_div(h.nloc, 256), 256, 0, ctx->stream>>>(flags, pos, h.nloc, tmp);
+            count_launch(ctx);
+            send_lists[p].resize(cnt);
+            cudaStreamSynchronize(ctx->stream);
+            cudaMemcpy(send_lists[p].data(), tmp, sizeof(int) * cnt, cudaMemcpyDeviceToHost);
+            cudaFree(tmp);
+        }
+    }
+    h.total_send = 0;
+    for (int p = 0; p < nr; ++p) { h.send_off[p] = h.total_send; h.total_send += h.send_cnt[p]; }
+    if (h.total_send) {
+        std::vector<int> all; all.reserve(h.total_send);
+        for (int p = 0; p < nr; ++p) all.insert(all.end(), send_lists[p].begin(), send_lists[p].end());
+        st = dev_alloc(&h.d_send_idx, h.total_send);
+        if (st == FAMG_OK) st = dev_alloc(&h.d_sendbuf, h.total_send);
+        if (st != FAMG_OK) return done(st);
+        cudaMemcpy(h.d_send_idx, all.data(), sizeof(int) * h.total_send, cudaMemcpyHostToDevice);
+    }
+    h.any = h.total_send > 0 || h.nghost > 0;
+    // 4. interior row range
+    {
+        const int nrows = row1 - row0;
+        int init[2] = {0, nrows};
+        cudaMemcpy(small, init, sizeof(init), cudaMemcpyHostToDevice);
+        if (nrows > 0 && h.nghost > 0) {
+            interior_range_kernel<<<(unsigned)ceil_div(nrows, 256), 256, 0, ctx->stream>>>(op->local->row_ptr, op->local->col, nrows, h.nloc, small);
+            count_launch(ctx);
+        }
+        cudaStreamSynchronize(ctx->stream);
+        cudaMemcpy(init, small, sizeof(init), cudaMemcpyDeviceToHost);
+        op->ib = init[0]; op->ie = std::max(init[0], init[1]);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return done((set_error("dist setup: %s", cudaGetErrorString(e)), FAMG_ERR_CUDA));
+    return done(FAMG_OK);
+}
+
+// start the halo exchange of x_ext ([owned | ghost tail]) for `op`; compute stream keeps going
+static famg_status halo_begin(famg_comm *cm, const HaloPlan &h, double *x_ext) {
+    if (!h.any || cm->nranks == 1) return FAMG_OK;
+    famg_ctx *ctx = cm->ctx;
+    if (h.total_send) {
+        pack_kernel<<<(unsigned)ceil_div(h.total_send, 256), 256, 0, ctx->stream>>>(x_ext, h.d_send_idx, h.total_send, h.d_sendbuf);
+        count_launch(ctx);
+    }
+    CUDA_TRY(cudaEventRecord(cm->ev_packed, ctx->stream));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->comm_stream, cm->ev_packed, 0));
+    NCCL_TRY(g_nccl.GroupStart());
+    for (int p = 0; p < cm->nranks; ++p) {
+        if (h.send_cnt[p]) NCCL_TRY(g_nccl.Send(h.d_sendbuf + h.send_off[p], (size_t)h.send_cnt[p], ncclDouble, p, cm->comm, ctx->comm_stream));
+        if (h.recv_cnt[p]) NCCL_TRY(g_nccl.Recv(x_ext + h.nloc + h.recv_off[p], (size_t)h.recv_cnt[p], ncclDouble, p, cm->comm, ctx->comm_stream));
+    }
+    NCCL_TRY(g_nccl.GroupEnd());
+    CUDA_TRY(cudaEventRecord(cm->ev_halo, ctx->comm_stream));
+    return FAMG_OK;
+}
+static famg_status halo_end(famg_comm *cm, const HaloPlan &h) {
+    if (!h.any || cm->nranks == 1) return FAMG_OK;
+    CUDA_TRY(cudaStreamWaitEvent(cm->ctx->stream, cm->ev_halo, 0));
+    return FAMG_OK;
+}
+
+// y = epi(A_local x_ext ...) with the exchange overlapped by the interior rows.
+static famg_status dist_apply(famg_comm *cm, const DistOp &op, int epi, double *x_ext, double *y, const double *b, const double *d,
+                              double *dot_partials, int *num_partials) {
+    SpmvArgs g; g.a = op.local; g.epi = epi; g.x = x_ext; g.ldx = 0; g.y = y; g.ldy = 0; g.b = b; g.ldb = 0; g.d = d; g.k = 1;
+    const int nrows = (int)op.local->nrows;
+    int total = 0, n = 0;
+    if (num_partials) *num_partials = 0;
+    if (!op.halo.any || cm->nranks == 1) {
+        g.dot_partials = dot_partials;
+        FAMG_TRY(spmv_launch(g, &n));
+        if (num_partials) *num_partials = n;
+        return FAMG_OK;
+    }
+    FAMG_TRY(halo_begin(cm, op.halo, x_ext));
+    if (op.ie > op.ib) {
+        g.row_begin = op.ib; g.row_end = op.ie; g.dot_partials = dot_partials ? dot_partials + total : nullptr;
+        FAMG_TRY(spmv_launch(g, &n)); total += n;
+    }
+    FAMG_TRY(halo_end(cm, op.halo));
+    if (op.ib > 0) {
+        g.row_begin = 0; g.row_end = op.ib; g.dot_partials = dot_partials ? dot_partials + total : nullptr;
+        FAMG_TRY(spmv_launch(g, &n)); total += n;
+    }
+    if (op.ie < nrows) {
+        g.row_begin = op.ie; g.row_end = nrows; g.dot_partials = dot_partials ? dot_partials + total : nullptr;
+        FAMG_TRY(spmv_launch(g, &n)); total += n;
+    }
+    if (num_partials) *num_partials = total;
+    return FAMG_OK;
+}
+
+static famg_status allreduce_slots(famg_comm *cm, int first, int count) {
+    if (cm->nranks == 1) return FAMG_OK;
+    double *p = cm->ctx->d_scalars + first;
+    NCCL_TRY(g_nccl.AllReduce(p, p, (size_t)count, ncclDouble, ncclSum, cm->comm, cm->ctx->stream));
+    return FAMG_OK;
+}
+
+// gather the owned pieces of a level vector into a replicated one
+static famg_status allgather_rows(famg_dist_mg *dm, int level, const double *local, double *global) {
+    famg_comm *cm = dm->comm;
+    const auto &sp = dm->splits[level];
+    if (cm->nranks == 1) {
+        CUDA_TRY(cudaMemcpyAsync(global, local, sizeof(double) * (sp[1] - sp[0]), cudaMemcpyDeviceToDevice, cm->ctx->stream));
+        return FAMG_OK;
+    }
+    NCCL_TRY(g_nccl.GroupStart());
+    for (int p = 0; p < cm->nranks; ++p) {
+        const size_t cnt = (size_t)(sp[p + 1] - sp[p]);
+        if (!cnt) continue;
+        NCCL_TRY(g_nccl.Broadcast(p == cm->rank ? local : global + sp[p], global + sp[p], cnt, ncclDouble, p, cm->comm, cm->ctx->stream));
+    }
+    NCCL_TRY(g_nccl.GroupEnd());
+    return FAMG_OK;
+}
+
+// one visit of a distributed level; result in va (owned rows, ghost tail follows)
+static famg_status dist_cycle(famg_dist_mg *dm, int level, double *va, const double *f, bool zero_guess) {
+    famg_comm *cm = dm->comm;
+    famg_ctx *ctx = cm->ctx;
+    famg_mg *gm = dm->global;
+    if (level == dm->lrep) {
+        // replicated tail: gather f, run the global cycle from this level, keep the owned slice
+        MgLevel &G = gm->lv[level];
+        const int64_t n = G.a->nrows;
+        const auto &sp = dm->splits[level];
+        FAMG_TRY(allgather_rows(dm, level, f, dm->g_f));
+        if (!zero_guess) FAMG_TRY(allgather_rows(dm, level, va, dm->g_v));
+        FAMG_TRY(mg_cycle(gm, (size_t)level, dm->g_v, (n + 1) & ~(int64_t)1, dm->g_f, (n + 1) & ~(int64_t)1, 1, zero_guess));
+        CUDA_TRY(cudaMemcpyAsync(va, dm->g_v + sp[cm->rank], sizeof(double) * (sp[cm->rank + 1] - sp[cm->rank]), cudaMemcpyDeviceToDevice,
+                                 ctx->stream));
+        return FAMG_OK;
+    }
+    DistLevel &L = dm->lv[level];
+    const int64_t nloc = L.r1 - L.r0;
+    double *cur = va, *oth = L.t;
+    const int nu = gm->nu, mu = gm->mu;
+    auto sweep = [&]() -> famg_status {
+        FAMG_TRY(dist_apply(cm, L.A, EPI_SMOOTH, cur, oth, f, L.d, nullptr, nullptr));
+        std::swap(cur, oth);
+        return FAMG_OK;
+    };
+    int pre = nu;
+    if (zero_guess) {
+        if (((nu - 1) + nu) & 1) std::swap(cur, oth);
+        FAMG_TRY(vec_scale_rows(ctx, L.d, f, 0, cur, 0, nloc, 1));
+        pre -= 1;
+    }
+    for (int i = 0; i < pre; ++i) FAMG_TRY(sweep());
+    FAMG_TRY(dist_apply(cm, L.A, EPI_RESID, cur, oth, f, nullptr, nullptr, nullptr));
+    const bool coarse_rep = level + 1 == dm->lrep;
+    // restriction into the owned rows of level+1
+    double *fc, *vc;
+    if (coarse_rep) { fc = dm->fc_loc; vc = dm->g_v; }
+    else { fc = dm->lv[level + 1].b; vc = dm->lv[level + 1].x; }
+    FAMG_TRY(dist_apply(cm, L.R, EPI_SPMV, oth, fc, nullptr, nullptr, nullptr, nullptr));
+    if (coarse_rep) {
+        MgLevel &G = gm->lv[level + 1];
+        const int64_t ldg = (G.a->nrows + 1) & ~(int64_t)1;
+        FAMG_TRY(allgather_rows(dm, level + 1, fc, dm->g_f));
+        for (int m = 0; m < mu; ++m) FAMG_TRY(mg_cycle(gm, (size_t)level + 1, dm->g_v, ldg, dm->g_f, ldg, 1, m == 0));
+    } else {
+        for (int m = 0; m < mu; ++m) FAMG_TRY(dist_cycle(dm, level + 1, vc, fc, m == 0));
+    }
+    FAMG_TRY(dist_apply(cm, L.P, EPI_ADD, vc, cur, nullptr, nullptr, nullptr, nullptr));
+    for (int i = 0; i < nu; ++i) FAMG_TRY(sweep());
+    if (cur != va) FAMG_FAIL(FAMG_ERR_INVALID, "internal: distributed ping-pong parity broken");
+    return FAMG_OK;
+}
+
+static void dist_free(famg_dist_mg *d) {
+    for (auto &l : d->lv) {
+        distop_free(l.A); distop_free(l.R); distop_free(l.P);
+        cudaFree(l.d); cudaFree(l.x); cudaFree(l.b); cudaFree(l.t);
+    }
+    cudaFree(d->g_f); cudaFree(d->g_v); cudaFree(d->fc_loc); cudaFree(d->pcg);
+    delete d;
+}
+
+}  // namespace famg
+
+using namespace famg;
+
+extern "C" {
+
+famg_status famg_comm_unique_id(void *id_bytes) {
+    if (!id_bytes) FAMG_FAIL(FAMG_ERR_INVALID, "null argument");
+    FAMG_TRY(nccl_load());
+    static_assert(sizeof(ncclUniqueId) == FAMG_UNIQUE_ID_BYTES, "ncclUniqueId size");
+    ncclUniqueId id;
+    NCCL_TRY(g_nccl.GetUniqueId(&id));
+    memcpy(id_bytes, &id, sizeof(id));
+    return FAMG_OK;
+}
+
+famg_status famg_comm_create(famg_ctx *ctx, int nranks, int rank, const void *id_bytes, famg_comm **out) {
+    if (!ctx || !out || nranks < 1 || rank < 0 || rank >= nranks) FAMG_FAIL(FAMG_ERR_INVALID, "bad argument");
+    *out = nullptr;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    famg_comm *c = new famg_comm();
+    c->ctx = ctx; c->nranks = nranks; c->rank = rank;
+    if (nranks > 1) {
+        if (!id_bytes) { delete c; FAMG_FAIL(FAMG_ERR_INVALID, "null unique id"); }
+        famg_status st = nccl_load();
+        if (st != FAMG_OK) { delete c; return st; }
+        ncclUniqueId id;
+        memcpy(&id, id_bytes, sizeof(id));
+        ncclResult_t r = g_nccl.CommInitRank(&c->comm, nranks, id, rank);
+        if (r != ncclSuccess) { delete c; FAMG_FAIL(FAMG_ERR_COMM, "ncclCommInitRank failed: %s", g_nccl.GetErrorString(r)); }
+    }
+    cudaEventCreateWithFlags(&c->ev_packed, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming);
+    *out = c;
+    return FAMG_OK;
+}
+
+famg_status famg_comm_destroy(famg_comm *c) {
+    if (!c) return FAMG_OK;
+    cudaSetDevice(c->ctx->device);
+    cudaStreamSynchronize(c->ctx->stream); cudaStreamSynchronize(c->ctx->comm_stream);
+    if (c->comm) g_nccl.CommDestroy(c->comm);
+    cudaEventDestroy(c->ev_packed); cudaEventDestroy(c->ev_halo);
+    delete c;
+    return FAMG_OK;
+}
+
+famg_status famg_comm_allreduce_sum(famg_comm *c, double *vals, int n) {
+    if (!c || !vals || n < 0 || n > 32) FAMG_FAIL(FAMG_ERR_INVALID, "bad argument (n <= 32)");
+    famg_ctx *ctx = c->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_scalars + 32, vals, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    FAMG_TRY(allreduce_slots(c, 32, n));
+    CUDA_TRY(cudaMemcpyAsync(vals, ctx->d_scalars + 32, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return FAMG_OK;
+}
+
+famg_status famg_dist_mg_create(famg_comm *c, famg_mg *gm, const int64_t *const *row_splits, int64_t replicate_below,
+                                famg_dist_mg **out) {
+    if (!c || !gm || !row_splits || !out) FAMG_FAIL(FAMG_ERR_INVALID, "null argument");
+    *out = nullptr;
+    famg_ctx *ctx = c->ctx;
+    if (gm->ctx != ctx) FAMG_FAIL(FAMG_ERR_INVALID, "multigrid and communicator live on different contexts");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const int nl = (int)gm->lv.size(), nr = c->nranks;
+    famg_dist_mg *d = new famg_dist_mg();
+    d->comm = c; d->global = gm;
+    d->splits.resize(nl);
+    for (int l = 0; l < nl; ++l) {
+        d->splits[l].assign(row_splits[l], row_splits[l] + nr + 1);
+        const auto &sp = d->splits[l];
+        bool ok = sp[0] == 0 && sp[nr] == gm->lv[l].a->nrows;
+        for (int p = 0; p < nr; ++p) ok = ok && sp[p] <= sp[p + 1];
+        if (!ok) { dist_free(d); FAMG_FAIL(FAMG_ERR_INVALID, "row_splits of level %d do not partition its rows", l); }
+    }
+    // first replicated level: too few rows per rank, a non-Diag smoother, or the coarsest level
+    int lrep = nl - 1;
+    for (int l = 0; l < nl - 1; ++l)
+        if (gm->lv[l].a->nrows / nr < replicate_below || gm->lv[l].s->kind != SM_DIAG) { lrep = l; break; }
+    d->lrep = lrep;
+    FAMG_TRY(mg_ensure_workspace(gm, 1));
+    d->lv.resize(lrep);
+    famg_status st = FAMG_OK;
+    for (int l = 0; l < lrep && st == FAMG_OK; ++l) {
+        DistLevel &L = d->lv[l];
+        MgLevel &G = gm->lv[l];
+        L.r0 = d->splits[l][c->rank]; L.r1 = d->splits[l][c->rank + 1];
+        st = distop_build(c, G.a, d->splits[l], d->splits[l], false, &L.A);
+        MgLevel &C = gm->lv[l + 1];
+        const bool coarse_rep = l + 1 == lrep;
+        if (st == FAMG_OK) { st = distop_build(c, C.r, d->splits[l + 1], d->splits[l], false, &L.R); L.has_R = true; }
+        if (st == FAMG_OK) { st = distop_build(c, C.p, d->splits[l], d->splits[l + 1], coarse_rep, &L.P); L.has_P = true; }
+        if (st != FAMG_OK) break;
+        const int64_t nloc = L.r1 - L.r0;
+        st = dev_alloc(&L.d, nloc);
+        if (st == FAMG_OK && nloc)
+            cudaMemcpyAsync(L.d, G.s->d + L.r0, sizeof(double) * nloc, cudaMemcpyDeviceToDevice, ctx->stream);
+    }
+    // vector tails: a level-l vector is consumed by A_l and R_l (level l columns) and by P_{l-1}
+    for (int l = 0; l < lrep && st == FAMG_OK; ++l) {
+        DistLevel &L = d->lv[l];
+        int64_t ghost = std::max(L.A.halo.nghost, L.R.halo.nghost);
+        if (l > 0) ghost = std::max<int64_t>(ghost, d->lv[l - 1].P.halo.nghost);
+        L.ld = (L.r1 - L.r0) + ghost + 2;
+        st = dev_alloc(&L.x, L.ld);
+        if (st == FAMG_OK) st = dev_alloc(&L.b, L.ld);
+        if (st == FAMG_OK) st = dev_alloc(&L.t, L.ld);
+        if (st == FAMG_OK) {
+            cudaMemsetAsync(L.x, 0, sizeof(double) * L.ld, ctx->stream);
+            cudaMemsetAsync(L.b, 0, sizeof(double) * L.ld, ctx->stream);
+            cudaMemsetAsync(L.t, 0, sizeof(double) * L.ld, ctx->stream);
+        }
+    }
+    if (st == FAMG_OK) {
+        const int64_t n = gm->lv[lrep].a->nrows;
+        st = dev_alloc(&d->g_f, n + 2);
+        if (st == FAMG_OK) st = dev_alloc(&d->g_v, n + 2);
+        if (st == FAMG_OK) st = dev_alloc(&d->fc_loc, d->splits[lrep][c->rank + 1] - d->splits[lrep][c->rank] + 2);
+    }
+    if (st == FAMG_OK) {
+        // PCG vectors r, z, q, x-scratch, and p with the ghost tail of A_0
+        const int64_t nloc = d->splits[0][c->rank + 1] - d->splits[0][c->rank];
+        const int64_t ghost = lrep > 0 ? d->lv[0].ld : nloc + 2;
+        d->pcg_ld = (std::max(nloc + 2, ghost) + 1) & ~(int64_t)1;
+        st = dev_alloc(&d->pcg, 6 * d->pcg_ld);
+        if (st == FAMG_OK) cudaMemsetAsync(d->pcg, 0, sizeof(double) * 6 * d->pcg_ld, ctx->stream);
+    }
+    cudaStreamSynchronize(ctx->stream);
+    if (st != FAMG_OK) { dist_free(d); return st; }
+    *out = d;
+    return FAMG_OK;
+}
+
+famg_status famg_dist_mg_destroy(famg_dist_mg *d) {
+    if (!d) return FAMG_OK;
+    cudaSetDevice(d->comm->ctx->device);
+    cudaStreamSynchronize(d->comm->ctx->stream); cudaStreamSynchronize(d->comm->ctx->comm_stream);
+    dist_free(d);
+    return FAMG_OK;
+}
+
+static famg_status dist_check_local(const famg_dist_mg *d, const famg_vec *v) {
+    const int64_t nloc = d->splits[0][d->comm->rank + 1] - d->splits[0][d->comm->rank];
+    if (!v || v->nrows != nloc || v->ncols != 1) FAMG_FAIL(FAMG_ERR_INVALID, "distributed vectors must hold this rank's %lld rows (1 column)", (long long)nloc);
+    return FAMG_OK;
+}
+
+// out_local = B rhs_local: one distributed mu-cycle from a zero guess. (buffers: pcg slot 4/5)
+static famg_status dist_precond(famg_dist_mg *d, double *out_ext, const double *rhs) {
+    return dist_cycle(d, 0, out_ext, rhs, true);
+}
+
+famg_status famg_dist_mg_apply_dev(famg_dist_mg *d, famg_vec *out_local, const famg_vec *rhs_local) {
+    if (!d) FAMG_FAIL(FAMG_ERR_INVALID, "null argument");
+    FAMG_TRY(dist_check_local(d, out_local));
+    FAMG_TRY(dist_check_local(d, rhs_local));
+    famg_ctx *ctx = d->comm->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    double *z = d->pcg + 4 * d->pcg_ld;
+    FAMG_TRY(dist_precond(d, z, rhs_local->p));
+    return vec_copy(ctx, out_local->p, out_local->ld, z, d->pcg_ld, out_local->nrows, 1);
+}
+
+famg_status famg_dist_spmv_dev(famg_dist_mg *d, famg_vec *y_local, const famg_vec *x_local) {
+    if (!d) FAMG_FAIL(FAMG_ERR_INVALID, "null argument");
+    FAMG_TRY(dist_check_local(d, y_local));
+    FAMG_TRY(dist_check_local(d, x_local));
+    famg_ctx *ctx = d->comm->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (d->lrep == 0) FAMG_FAIL(FAMG_ERR_UNSUPPORTED, "level 0 is replicated on this configuration");
+    double *xe = d->pcg + 5 * d->pcg_ld;
+    FAMG_TRY(vec_copy(ctx, xe, d->pcg_ld, x_local->p, x_local->ld, x_local->nrows, 1));
+    return dist_apply(d->comm, d->lv[0].A, EPI_SPMV, xe, y_local->p, nullptr, nullptr, nullptr, nullptr);
+}
+
+famg_status famg_dist_pcg_solve_dev(famg_dist_mg *d, famg_vec *x, const famg_vec *b, double rel_tol, double abs_tol,
+                                    int64_t max_iters, int zero_guess, famg_cg_info *info) {
+    if (!d || !info) FAMG_FAIL(FAMG_ERR_INVALID, "null argument");
+    FAMG_TRY(dist_check_local(d, x));
+    FAMG_TRY(dist_check_local(d, b));
+    famg_comm *cm = d->comm;
+    famg_ctx *ctx = cm->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (d->lrep == 0) FAMG_FAIL(FAMG_ERR_UNSUPPORTED, "problem too small to partition: use famg_pcg_solve on one GPU");
+    const int64_t n = x->nrows, ld = d->pcg_ld;
+    info->iter_count = 0; info->abs_residual = 0; info->rel_residual = 0;
+    double *r = d->pcg, *p = d->pcg + ld, *z = d->pcg + 2 * ld, *q = d->pcg + 3 * ld, *xe = d->pcg + 5 * ld;
+    DistOp &A = d->lv[0].A;
+    enum { S_BB = 0, S_RR = 1, S_PTQ = 2, S_RTZ_A = 3, S_RTZ_B = 4 };
+    double h[8];
+    FAMG_TRY(vec_dot(ctx, b->p, b->p, n, S_BB));
+    FAMG_TRY(allreduce_slots(cm, S_BB, 1));
+    FAMG_TRY(read_scalars(ctx, S_BB, 1, h));
+    const double b_norm = sqrt(h[0]);
+    if (b_norm == 0.0) return famg_vec_fill(x, 0.0);
+    const double thr = std::max(abs_tol, rel_tol * b_norm);
+    if (zero_guess) {
+        FAMG_TRY(famg_vec_fill(x, 0.0));
+        FAMG_TRY(vec_copy(ctx, r, ld, b->p, b->ld, n, 1));
+    } else {
+        FAMG_TRY(vec_copy(ctx, xe, ld, x->p, x->ld, n, 1));
+        FAMG_TRY(dist_apply(cm, A, EPI_RESID, xe, r, b->p, nullptr, nullptr, nullptr));
+    }
+    FAMG_TRY(vec_dot(ctx, r, r, n, S_RR));
+    FAMG_TRY(allreduce_slots(cm, S_RR, 1));
+    FAMG_TRY(read_scalars(ctx, S_RR, 1, h));
+    double rn = sqrt(h[0]);
+    bool converged = rn < thr;
+    int slot_rtz = S_RTZ_A, slot_rtz_new = S_RTZ_B;
+    if (!converged) {
+        FAMG_TRY(dist_precond(d, z, r));
+        FAMG_TRY(vec_copy(ctx, p, ld, z, ld, n, 1));
+        FAMG_TRY(vec_dot(ctx, r, z, n, slot_rtz));
+        FAMG_TRY(allreduce_slots(cm, slot_rtz, 1));
+        for (int64_t it = 0; it < max_iters; ++it) {
+            FAMG_TRY(ensure_partials(ctx, ceil_div(n, 256 / A.local->tpr) + 8));
+            int np = 0;
+            FAMG_TRY(dist_apply(cm, A, EPI_SPMV, p, q, nullptr, nullptr, ctx->d_partials, &np));
+            FAMG_TRY(reduce_partials(ctx, ctx->d_partials, np, S_PTQ));
+            FAMG_TRY(allreduce_slots(cm, S_PTQ, 1));
+            FAMG_TRY(pcg_update_xr(ctx, x->p, r, p, q, n, slot_rtz, S_PTQ, S_RR));
+            FAMG_TRY(allreduce_slots(cm, S_RR, 1));
+            FAMG_TRY(read_scalars(ctx, S_RR, 4, h));
+            const double ptq = h[S_PTQ - S_RR], rtz = h[slot_rtz - S_RR];
+            if (!(ptq > 0.0) || !(rtz > 0.0))
+                FAMG_FAIL(FAMG_ERR_NOT_SPD, "pcg: operator or preconditioner is not positive definite (p.Ap=%g, r.z=%g)", ptq, rtz);
+            rn = sqrt(h[0]);
+            info->iter_count = it + 1;
+            if (rn < thr) { converged = true; break; }
+            FAMG_TRY(dist_precond(d, z, r));
+            FAMG_TRY(vec_dot(ctx, r, z, n, slot_rtz_new));
+            FAMG_TRY(allreduce_slots(cm, slot_rtz_new, 1));
+            FAMG_TRY(pcg_update_p(ctx, p, z, n, slot_rtz_new, slot_rtz));
+            std::swap(slot_rtz, slot_rtz_new);
+        }
+    }
+    info->abs_residual = rn; info->rel_residual = rn / b_norm;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (!converged) FAMG_FAIL(FAMG_ERR_NO_CONVERGENCE, "pcg: no convergence in %lld iterations (abs %.3e, rel %.3e)", (long long)max_iters, rn, rn / b_norm);
+    return FAMG_OK;
+}
+
+famg_status famg_dist_pcg_solve(famg_dist_mg *d, double *x_local, const double *b_local, double rel_tol, double abs_tol,
+                                int64_t max_iters, int zero_guess, famg_cg_info *info) {
+    if (!d || !x_local || !b_local || !info) FAMG_FAIL(FAMG_ERR_INVALID, "null argument");
+    famg_ctx *ctx = d->comm->ctx;
+    const int64_t n = d->splits[0][d->comm->rank + 1] - d->splits[0][d->comm->rank];
+    famg_vec *dx = nullptr, *db = nullptr;
+    FAMG_TRY(famg_vec_create(ctx, n, 1, &dx));
+    famg_status st = famg_vec_create(ctx, n, 1, &db);
+    if (st == FAMG_OK) st = famg_vec_upload(db, b_local, n);
+    if (st == FAMG_OK && !zero_guess) st = famg_vec_upload(dx, x_local, n);
+    famg_status solve = FAMG_OK;
+    if (st == FAMG_OK) {
+        solve = famg_dist_pcg_solve_dev(d, dx, db, rel_tol, abs_tol, max_iters, zero_guess, info);
+        if (solve == FAMG_OK || solve == FAMG_ERR_NO_CONVERGENCE) {
+            std::string keep = get_error();
+            st = famg_vec_download(dx, x_local, n);
+            if (solve != FAMG_OK) set_error("%s", keep.c_str());
+        }
+    }
+    famg_vec_destroy(dx); famg_vec_destroy(db);
+    return st != FAMG_OK ? st : solve;
+}
+
+}  // extern "C"

@@ -1,0 +1,256 @@
+// gallery.cu -- synthetic operators generated on the device, and the small host-side dense pieces
+// of hierarchy construction (tentative prolongator, thin Q).
+//
+// The reference ships no 3-D generator: G7 / G27 are the benchmark inputs defined in
+// SURVEY 8(d).  The value formulas are evaluated in a fixed left-to-right order (and the library
+// is compiled with -fmad=false) so they are bit-identical to the oracle's generators.
+#include <cmath>
+
+#include "common.cuh"
+
+namespace famg {
+
+__global__ void g7_count_kernel(int nx, int ny, int nz, int *__restrict__ cnt) {
+    const long long n = (long long)nx * ny * nz;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int x = (int)(i % nx), y = (int)((i / nx) % ny), z = (int)(i / ((long long)nx * ny));
+    cnt[i] = 1 + (x > 0) + (x + 1 < nx) + (y > 0) + (y + 1 < ny) + (z > 0) + (z + 1 < nz);
+}
+__global__ void g7_fill_kernel(int nx, int ny, int nz, const int *__restrict__ rp, int *__restrict__ col, double *__restrict__ val) {
+    const long long n = (long long)nx * ny * nz;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int x = (int)(i % nx), y = (int)((i / nx) % ny), z = (int)(i / ((long long)nx * ny));
+    int q = rp[i];
+    const int ii = (int)i, sxy = nx * ny;
+    if (z > 0) { col[q] = ii - sxy; val[q++] = -1.0; }
+    if (y > 0) { col[q] = ii - nx; val[q++] = -1.0; }
+    if (x > 0) { col[q] = ii - 1; val[q++] = -1.0; }
+    col[q] = ii; val[q++] = 6.0;
+    if (x + 1 < nx) { col[q] = ii + 1; val[q++] = -1.0; }
+    if (y + 1 < ny) { col[q] = ii + nx; val[q++] = -1.0; }
+    if (z + 1 < nz) { col[q] = ii + sxy; val[q++] = -1.0; }
+}
+
+__global__ void g27_count_kernel(int nx, int ny, int nz, int *__restrict__ cnt) {
+    const long long n = (long long)nx * ny * nz;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int x = (int)(i % nx), y = (int)((i / nx) % ny), z = (int)(i / ((long long)nx * ny));
+    const int cx = 1 + (x > 0) + (x + 1 < nx), cy = 1 + (y > 0) + (y + 1 < ny), cz = 1 + (z > 0) + (z + 1 < nz);
+    cnt[i] = cx * cy * cz;
+}
+__device__ __forceinline__ double g27_k(int d) { return d == 0 ? 2.0 : -1.0; }
+__device__ __forceinline__ double g27_m(int d) { return d == 0 ? 4.0 / 6.0 : 1.0 / 6.0; }
+__global__ void g27_fill_kernel(int nx, int ny, int nz, double ey, double ez, const int *__restrict__ rp, int *__restrict__ col,
+                                double *__restrict__ val) {
+    const long long n = (long long)nx * ny * nz;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int x = (int)(i % nx), y = (int)((i / nx) % ny), z = (int)(i / ((long long)nx * ny));
+    int q = rp[i];
+    for (int dz = -1; dz <= 1; ++dz) {
+        if (z + dz < 0 || z + dz >= nz) continue;
+        for (int dy = -1; dy <= 1; ++dy) {
+            if (y + dy < 0 || y + dy >= ny) continue;
+            for (int dx = -1; dx <= 1; ++dx) {
+                if (x + dx < 0 || x + dx >= nx) continue;
+                const double t0 = g27_k(dx) * g27_m(dy) * g27_m(dz);
+                const double t1 = ey * g27_m(dx) * g27_k(dy) * g27_m(dz);
+                const double t2 = ez * g27_m(dx) * g27_m(dy) * g27_k(dz);
+                col[q] = (int)i + dx + nx * (dy + ny * dz);
+                val[q++] = t0 + t1 + t2;
+            }
+        }
+    }
+}
+
+static famg_status gallery_build(famg_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, int stencil, double ey, double ez, famg_csr **out) {
+    *out = nullptr;
+    if (nx <= 0 || ny <= 0 || nz <= 0) FAMG_FAIL(FAMG_ERR_INVALID, "grid dimensions must be positive");
+    const int64_t n = nx * ny * nz;
+    if (n >= INT32_MAX) FAMG_FAIL(FAMG_ERR_UNSUPPORTED, "grid too large for 32-bit indices");
+    int *cnt = nullptr, *rp = nullptr;
+    FAMG_TRY(dev_alloc(&cnt, n + 1));
+    famg_status st = dev_alloc(&rp, n + 1);
+    const unsigned grid = (unsigned)ceil_div(n, 256);
+    if (st == FAMG_OK) {
+        if (stencil == 7) g7_count_kernel<<<grid, 256, 0, ctx->stream>>>((int)nx, (int)ny, (int)nz, cnt);
+        else g27_count_kernel<<<grid, 256, 0, ctx->stream>>>((int)nx, (int)ny, (int)nz, cnt);
+        count_launch(ctx);
+        st = exclusive_scan_i32(ctx, cnt, rp, n);
+    }
+    int total = 0;
+    if (st == FAMG_OK) {
+        cudaError_t e = cudaMemcpy(&total, rp + n, sizeof(int), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { set_error("gallery: %s", cudaGetErrorString(e)); st = FAMG_ERR_CUDA; }
+        else if (total < 0) { set_error("gallery: more than 2^31 non-zeros"); st = FAMG_ERR_UNSUPPORTED; }
+    }
+    famg_csr *a = nullptr;
+    if (st == FAMG_OK) st = csr_alloc(ctx, n, n, total, &a);
+    if (st == FAMG_OK) {
+        cudaMemcpyAsync(a->row_ptr, rp, sizeof(int) * (n + 1), cudaMemcpyDeviceToDevice, ctx->stream);
+        if (stencil == 7) g7_fill_kernel<<<grid, 256, 0, ctx->stream>>>((int)nx, (int)ny, (int)nz, a->row_ptr, a->col, a->val);
+        else g27_fill_kernel<<<grid, 256, 0, ctx->stream>>>((int)nx, (int)ny, (int)nz, ey, ez, a->row_ptr, a->col, a->val);
+        count_launch(ctx);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { set_error("gallery: %s", cudaGetErrorString(e)); st = FAMG_ERR_CUDA; }
+    }
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(cnt); cudaFree(rp);
+    if (st == FAMG_OK) st = csr_finalize_plan(a);
+    if (st != FAMG_OK) { if (a) csr_release(a); return st; }
+    *out = a;
+    return FAMG_OK;
+}
+
+// ---- host dense helpers -------------------------------------------------------------------
+// One-sided Jacobi thin SVD of an m x k column-major block (k is the near-null width: tiny).
+// Stands in for faer thin_svd (interpolation/mod.rs:770), whose column signs are not knowable
+// here; convention: singular values descending, largest-magnitude entry of each v_j positive.
+static void host_thin_svd(int64_t m, int64_t k, std::vector<double> &u, std::vector<double> &s, std::vector<double> &v) {
+    v.assign((size_t)(k * k), 0.0);
+    s.assign((size_t)k, 0.0);
+    for (int64_t i = 0; i < k; ++i) v[(size_t)(i + i * k)] = 1.0;
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0.0;
+        for (int64_t p = 0; p + 1 < k; ++p)
+            for (int64_t q = p + 1; q < k; ++q) {
+                double alpha = 0, beta = 0, gamma = 0;
+                for (int64_t i = 0; i < m; ++i) {
+                    const double up = u[(size_t)(i + p * m)], uq = u[(size_t)(i + q * m)];
+                    alpha += up * up; beta += uq * uq; gamma += up * uq;
+                }
+                if (gamma == 0.0) continue;
+                const double lim = sqrt(alpha * beta);
+                if (fabs(gamma) <= 1e-300 || fabs(gamma) <= 1e-16 * lim) continue;
+                off = std::max(off, fabs(gamma) / (lim > 0 ? lim : 1.0));
+                const double zeta = (beta - alpha) / (2.0 * gamma);
+                const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+                for (int64_t i = 0; i < m; ++i) {
+                    const double up = u[(size_t)(i + p * m)], uq = u[(size_t)(i + q * m)];
+                    u[(size_t)(i + p * m)] = c * up - sn * uq;
+                    u[(size_t)(i + q * m)] = sn * up + c * uq;
+                }
+                for (int64_t i = 0; i < k; ++i) {
+                    const double vp = v[(size_t)(i + p * k)], vq = v[(size_t)(i + q * k)];
+                    v[(size_t)(i + p * k)] = c * vp - sn * vq;
+                    v[(size_t)(i + q * k)] = sn * vp + c * vq;
+                }
+            }
+        if (off < 1e-15) break;
+    }
+    for (int64_t j = 0; j < k; ++j) {
+        double nn = 0;
+        for (int64_t i = 0; i < m; ++i) nn += u[(size_t)(i + j * m)] * u[(size_t)(i + j * m)];
+        s[(size_t)j] = sqrt(nn);
+    }
+    for (int64_t j = 0; j < k; ++j) {
+        int64_t best = j;
+        for (int64_t l = j + 1; l < k; ++l) if (s[(size_t)l] > s[(size_t)best]) best = l;
+        if (best != j) {
+            std::swap(s[(size_t)j], s[(size_t)best]);
+            for (int64_t i = 0; i < m; ++i) std::swap(u[(size_t)(i + j * m)], u[(size_t)(i + best * m)]);
+            for (int64_t i = 0; i < k; ++i) std::swap(v[(size_t)(i + j * k)], v[(size_t)(i + best * k)]);
+        }
+    }
+    for (int64_t j = 0; j < k; ++j) {
+        if (s[(size_t)j] > 0) for (int64_t i = 0; i < m; ++i) u[(size_t)(i + j * m)] /= s[(size_t)j];
+        else for (int64_t i = 0; i < m; ++i) u[(size_t)(i + j * m)] = 0.0;
+        int64_t big = 0;
+        for (int64_t i = 1; i < k; ++i) if (fabs(v[(size_t)(i + j * k)]) > fabs(v[(size_t)(big + j * k)])) big = i;
+        if (v[(size_t)(big + j * k)] < 0) {
+            for (int64_t i = 0; i < k; ++i) v[(size_t)(i + j * k)] = -v[(size_t)(i + j * k)];
+            for (int64_t i = 0; i < m; ++i) u[(size_t)(i + j * m)] = -u[(size_t)(i + j * m)];
+        }
+    }
+}
+
+}  // namespace famg
+
+using namespace famg;
+
+extern "C" {
+
+famg_status famg_gallery_g7(famg_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, famg_csr **out) {
+    if (!ctx || !out) FAMG_FAIL(FAMG_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return gallery_build(ctx, nx, ny, nz, 7, 0.0, 0.0, out);
+}
+
+famg_status famg_gallery_g27(famg_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, double eps_y, double eps_z, famg_csr **out) {
+    if (!ctx || !out) FAMG_FAIL(FAMG_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return gallery_build(ctx, nx, ny, nz, 27, eps_y, eps_z, out);
+}
+
+famg_status famg_tentative_p(famg_ctx *ctx, int64_t n_fine, int64_t block_size, int64_t k, int64_t cand, const double *near_null,
+                             int64_t ld_nn, int64_t n_aggs, const uint64_t *agg_ptr, const uint64_t *agg_nodes, famg_csr **p,
+                             double *coarse_nn) {
+    if (!ctx || !near_null || !agg_ptr || !agg_nodes || !p || !coarse_nn) FAMG_FAIL(FAMG_ERR_INVALID, "null argument");
+    *p = nullptr;
+    if (block_size <= 0 || k <= 0 || cand <= 0 || cand > k || n_fine % block_size != 0 || ld_nn < n_fine)
+        FAMG_FAIL(FAMG_ERR_INVALID, "tentative_p: bad dimensions");
+    if ((int64_t)agg_ptr[n_aggs] * block_size != n_fine) FAMG_FAIL(FAMG_ERR_INVALID, "partition does not cover the fine grid");  // interpolation/mod.rs:745
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const int64_t nc = n_aggs * cand;
+    // row i of P has exactly `cand` entries (columns ci*cand .. ci*cand+cand-1) => direct CSR
+    std::vector<int> rp((size_t)n_fine + 1), ci((size_t)(n_fine * cand));
+    std::vector<double> cv((size_t)(n_fine * cand), 0.0);
+    std::vector<char> seen((size_t)(n_fine / block_size), 0);
+    for (int64_t i = 0; i <= n_fine; ++i) rp[(size_t)i] = (int)(i * cand);
+    std::vector<double> u, s, v;
+    for (int64_t g = 0; g < n_aggs; ++g) {
+        const int64_t na = (int64_t)(agg_ptr[g + 1] - agg_ptr[g]);
+        const int64_t m = na * block_size;
+        if (m < cand)  // interpolation/mod.rs:757-762
+            FAMG_FAIL(FAMG_ERR_INVALID, "Agg size of %lld cannot support near-null dimension of %lld", (long long)m, (long long)cand);
+        u.assign((size_t)(m * k), 0.0);
+        for (int64_t lj = 0; lj < na; ++lj) {
+            const uint64_t node = agg_nodes[agg_ptr[g] + lj];
+            if (node >= (uint64_t)(n_fine / block_size) || seen[(size_t)node]) FAMG_FAIL(FAMG_ERR_INVALID, "invalid partition");
+            seen[(size_t)node] = 1;
+            for (int64_t o = 0; o < block_size; ++o)
+                for (int64_t c = 0; c < k; ++c)
+                    u[(size_t)(lj * block_size + o + c * m)] = near_null[(int64_t)node * block_size + o + c * ld_nn];
+        }
+        host_thin_svd(m, k, u, s, v);
+        for (int64_t r = 0; r < cand; ++r)
+            for (int64_t c = 0; c < k; ++c) coarse_nn[g * cand + r + c * nc] = s[(size_t)r] * v[(size_t)(c + r * k)];
+        for (int64_t li = 0; li < na; ++li) {
+            const int64_t fi = (int64_t)agg_nodes[agg_ptr[g] + li];
+            for (int64_t oi = 0; oi < block_size; ++oi)
+                for (int64_t oj = 0; oj < cand; ++oj) {
+                    const int64_t row = fi * block_size + oi;
+                    ci[(size_t)(row * cand + oj)] = (int)(g * cand + oj);
+                    cv[(size_t)(row * cand + oj)] = u[(size_t)(li * block_size + oi + oj * m)];
+                }
+        }
+    }
+    return csr_from_host_i32(ctx, n_fine, nc, rp.data(), ci.data(), cv.data(), p);
+}
+
+famg_status famg_thin_q(int64_t n, int64_t k, double *a, int64_t lda) {
+    if (!a || n < 0 || k < 0 || lda < n) FAMG_FAIL(FAMG_ERR_INVALID, "bad argument");
+    // modified Gram-Schmidt, applied twice per column; R has a positive diagonal
+    for (int64_t j = 0; j < k; ++j) {
+        double *aj = a + j * lda;
+        for (int pass = 0; pass < 2; ++pass)
+            for (int64_t l = 0; l < j; ++l) {
+                const double *al = a + l * lda;
+                double d = 0;
+                for (int64_t i = 0; i < n; ++i) d += al[i] * aj[i];
+                for (int64_t i = 0; i < n; ++i) aj[i] -= d * al[i];
+            }
+        double nn = 0;
+        for (int64_t i = 0; i < n; ++i) nn += aj[i] * aj[i];
+        nn = sqrt(nn);
+        if (!(nn > 0)) FAMG_FAIL(FAMG_ERR_NUMERIC, "thin_q: column %lld is linearly dependent", (long long)j);
+        for (int64_t i = 0; i < n; ++i) aj[i] /= nn;
+    }
+    return FAMG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,370 @@
+// smoothers.cu -- level smoothers: Diag (L1 / L2 / Jacobi), exact coarse solve, block smoother.
+// Reference: src/preconditioners/smoothers.rs:43-86, coarse_solvers.rs:173-206,
+// block_smoothers.rs:88-146,293-324, and smooth() in multigrid.rs:407-424.
+#include <cmath>
+
+#include "common.cuh"
+
+namespace famg {
+
+// ---------------------------------------------------------------- Diag setup (one pass over A)
+// Thread per row, entries visited in ascending column order == triplet_iter order, so the sums
+// round exactly like the reference's sequential loops.
+__global__ void diag_l1_kernel(const int *__restrict__ row_ptr, const double *__restrict__ val, int n, double *__restrict__ d) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = 0.0;
+    for (int q = row_ptr[i]; q < row_ptr[i + 1]; ++q) s += fabs(val[q]);
+    d[i] = 1.0 / s;  // d.recip()  (smoothers.rs:72-75)
+}
+
+// extracts a_ii (binary search like mat.get(i,i)); flags missing diagonals
+__global__ void diag_extract_kernel(const int *__restrict__ row_ptr, const int *__restrict__ col, const double *__restrict__ val,
+                                    int n, double *__restrict__ diag, int *__restrict__ missing) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int lo = row_ptr[i], hi = row_ptr[i + 1];
+    const int end = hi;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (col[mid] < i) lo = mid + 1; else hi = mid;
+    }
+    if (lo < end && col[lo] == i) diag[i] = val[lo];
+    else { diag[i] = 0.0; atomicAdd(missing, 1); }
+}
+
+__global__ void diag_sqrt_kernel(double *__restrict__ v, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = sqrt(v[i]);
+}
+
+__global__ void diag_l2_kernel(const int *__restrict__ row_ptr, const int *__restrict__ col, const double *__restrict__ val, int n,
+                               const double *__restrict__ dsqrt, double *__restrict__ d) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = 0.0;
+    const double di = dsqrt[i];
+    for (int q = row_ptr[i]; q < row_ptr[i + 1]; ++q) {
+        const double scale = di / dsqrt[col[q]];
+        s += fabs(val[q]) * scale;
+    }
+    d[i] = 1.0 / s;
+}
+
+__global__ void diag_jacobi_kernel(const double *__restrict__ diag, int n, double omega, double *__restrict__ d) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) d[i] = omega / diag[i];
+}
+
+void smoother_release(famg_smoother *s) {
+    if (!s) return;
+    if (s->refs.fetch_sub(1) == 1) {
+        cudaFree(s->d); cudaFree(s->inv);
+        if (s->minv) csr_release(s->minv);
+        delete s;
+    }
+}
+
+famg_status smoother_apply_dev(const famg_smoother *s, const double *in, int64_t ldi, double *out, int64_t ldo, int k,
+                               cudaStream_t st) {
+    famg_ctx *ctx = s->ctx;
+    if (s->kind == SM_DIAG) return vec_scale_rows(ctx, s->d, in, ldi, out, ldo, s->n, k, st);
+    if (s->kind == SM_DENSE_INV) return dense_gemv(ctx, s->inv, s->n, in, ldi, out, ldo, k, st);
+    if (in == out) FAMG_FAIL(FAMG_ERR_INVALID, "block smoother apply cannot run in place");
+    SpmvArgs a; a.a = s->minv; a.epi = EPI_SPMV; a.x = in; a.ldx = ldi; a.y = out; a.ldy = ldo; a.k = k; a.stream = st;
+    return spmv_launch(a);
+}
+
+}  // namespace famg
+
+using namespace famg;
+
+extern "C" {
+
+famg_status famg_smoother_diag(const famg_csr *a, int kind, double omega, famg_smoother **out) {
+    if (!a || !out) FAMG_FAIL(FAMG_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (a->nrows != a->ncols) FAMG_FAIL(FAMG_ERR_INVALID, "diagonal smoother needs a square matrix");
+    famg_ctx *ctx = a->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const int n = (int)a->nrows;
+    famg_smoother *s = new famg_smoother();
+    s->ctx = ctx; s->kind = SM_DIAG; s->n = n;
+    famg_status st = dev_alloc(&s->d, n);
+    if (st != FAMG_OK) { smoother_release(s); return st; }
+    const unsigned grid = (unsigned)ceil_div(std::max(n, 1), 256);
+    if (kind == FAMG_DIAG_L1) {
+        diag_l1_kernel<<<grid, 256, 0, ctx->stream>>>(a->row_ptr, a->val, n, s->d);
+        count_launch(ctx);
+    } else if (kind == FAMG_DIAG_L2 || kind == FAMG_DIAG_JACOBI) {
+        double *diag = nullptr; int *missing = nullptr;
+        st = dev_alloc(&diag, n);
+        if (st == FAMG_OK) st = dev_alloc(&missing, 1);
+        if (st != FAMG_OK) { cudaFree(diag); smoother_release(s); return st; }
+        cudaMemsetAsync(missing, 0, sizeof(int), ctx->stream);
+        diag_extract_kernel<<<grid, 256, 0, ctx->stream>>>(a->row_ptr, a->col, a->val, n, diag, missing);
+        if (kind == FAMG_DIAG_L2) {
+            diag_sqrt_kernel<<<grid, 256, 0, ctx->stream>>>(diag, n);
+            diag_l2_kernel<<<grid, 256, 0, ctx->stream>>>(a->row_ptr, a->col, a->val, n, diag, s->d);
+            count_launch(ctx, 3);
+        } else {
+            diag_jacobi_kernel<<<grid, 256, 0, ctx->stream>>>(diag, n, omega, s->d);
+            count_launch(ctx, 2);
+        }
+        int h_missing = 0;
+        cudaError_t e = cudaMemcpyAsync(&h_missing, missing, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        cudaFree(diag); cudaFree(missing);
+        if (e != cudaSuccess) { smoother_release(s); FAMG_FAIL(FAMG_ERR_CUDA, "diag setup failed: %s", cudaGetErrorString(e)); }
+        if (h_missing) {  // mat.get(i,i).unwrap() panics in the reference (smoothers.rs:46,83)
+            smoother_release(s);
+            FAMG_FAIL(FAMG_ERR_NUMERIC, "%d rows have no diagonal entry", h_missing);
+        }
+    } else {
+        smoother_release(s);
+        FAMG_FAIL(FAMG_ERR_INVALID, "unknown diagonal smoother kind %d", kind);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { smoother_release(s); FAMG_FAIL(FAMG_ERR_CUDA, "diag setup failed: %s", cudaGetErrorString(e)); }
+    *out = s;
+    return FAMG_OK;
+}
+
+famg_status famg_smoother_diag_from_host(famg_ctx *ctx, int64_t n, const double *d, famg_smoother **out) {
+    if (!ctx || !out || (n && !d)) FAMG_FAIL(FAMG_ERR_INVALID, "null argument");
+    *out = nullptr;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    famg_smoother *s = new famg_smoother();
+    s->ctx = ctx; s->kind = SM_DIAG; s->n = n;
+    famg_status st = dev_alloc(&s->d, n);
+    if (st != FAMG_OK) { smoother_release(s); return st; }
+    cudaError_t e = cudaMemcpyAsync(s->d, d, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { smoother_release(s); FAMG_FAIL(FAMG_ERR_CUDA, "diag upload failed: %s", cudaGetErrorString(e)); }
+    *out = s;
+    return FAMG_OK;
+}
+
+famg_status famg_smoother_cholesky(const famg_csr *a, famg_smoother **out) {
+    if (!a || !out) FAMG_FAIL(FAMG_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (a->nrows != a->ncols) FAMG_FAIL(FAMG_ERR_INVALID, "Cholesky solve needs a square matrix");
+    CUDA_TRY(cudaSetDevice(a->ctx->device));
+    famg_smoother *s = new famg_smoother();
+    s->ctx = a->ctx; s->kind = SM_DENSE_INV; s->n = a->nrows;
+    famg_status st = dense_inverse_from_csr(a, &s->inv);
+    if (st != FAMG_OK) { smoother_release(s); return st; }
+    *out = s;
+    return FAMG_OK;
+}
+
+// Dense SPD inverse of a small block on the host (Cholesky, then solve for the identity).
+static bool host_spd_inverse(int n, std::vector<double> &m /* n x n col-major, in: A, out: A^-1 */) {
+    std::vector<double> l((size_t)n * n, 0.0);
+    for (int j = 0; j < n; ++j) {
+        double d = m[(size_t)j + (size_t)j * n];
+        for (int k = 0; k < j; ++k) d -= l[(size_t)j + (size_t)k * n] * l[(size_t)j + (size_t)k * n];
+        if (!(d > 0.0)) return false;
+        d = sqrt(d);
+        l[(size_t)j + (size_t)j * n] = d;
+        for (int i = j + 1; i < n; ++i) {
+            double s = m[(size_t)i + (size_t)j * n];
+            for (int k = 0; k < j; ++k) s -= l[(size_t)i + (size_t)k * n] * l[(size_t)j + (size_t)k * n];
+            l[(size_t)i + (size_t)j * n] = s / d;
+        }
+    }
+    for (int c = 0; c < n; ++c) {
+        double *x = &m[(size_t)c * n];
+        for (int i = 0; i < n; ++i) x[i] = i == c ? 1.0 : 0.0;
+        for (int i = 0; i < n; ++i) {
+            double s = x[i];
+            for (int j = 0; j < i; ++j) s -= l[(size_t)i + (size_t)j * n] * x[j];
+            x[i] = s / l[(size_t)i + (size_t)i * n];
+        }
+        for (int i = n - 1; i >= 0; --i) {
+            double s = x[i];
+            for (int j = i + 1; j < n; ++j) s -= l[(size_t)j + (size_t)i * n] * x[j];
+            x[i] = s / l[(size_t)i + (size_t)i * n];
+        }
+    }
+    return true;
+}
+
+famg_status famg_smoother_block(const famg_csr *a, int64_t n_aggs, const uint64_t *agg_ptr, const uint64_t *agg_nodes,
+                                famg_smoother **out) {
+    if (!a || !out || !agg_ptr || !agg_nodes || n_aggs < 0) FAMG_FAIL(FAMG_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (a->nrows != a->ncols) FAMG_FAIL(FAMG_ERR_INVALID, "block smoother needs a square matrix");
+    if ((int64_t)agg_ptr[n_aggs] != a->nrows) FAMG_FAIL(FAMG_ERR_INVALID, "partition does not cover the matrix");  // block_smoothers.rs:91
+    CUDA_TRY(cudaSetDevice(a->ctx->device));
+    HostCsr h;
+    FAMG_TRY(csr_to_host(a, &h));
+    const int64_t n = a->nrows;
+    std::vector<double> diag((size_t)n, 0.0);
+    for (int64_t i = 0; i < n; ++i) {
+        bool found = false;
+        for (int q = h.row_ptr[(size_t)i]; q < h.row_ptr[(size_t)i + 1]; ++q)
+            if (h.col[(size_t)q] == i) { diag[(size_t)i] = h.val[(size_t)q]; found = true; break; }
+        if (!found) FAMG_FAIL(FAMG_ERR_NUMERIC, "row %lld has no diagonal entry", (long long)i);
+    }
+    // per aggregate: compensated principal block -> inverse; scatter as rows of block-diagonal M^-1
+    std::vector<int64_t> node_agg((size_t)n, -1), node_local((size_t)n, 0);
+    for (int64_t g = 0; g < n_aggs; ++g)
+        for (uint64_t u = agg_ptr[g]; u < agg_ptr[g + 1]; ++u) {
+            uint64_t node = agg_nodes[u];
+            if (node >= (uint64_t)n || node_agg[(size_t)node] != -1) FAMG_FAIL(FAMG_ERR_INVALID, "invalid partition");
+            if (u > agg_ptr[g] && agg_nodes[u - 1] >= node) FAMG_FAIL(FAMG_ERR_INVALID, "aggregate nodes must ascend");
+            node_agg[(size_t)node] = g; node_local[(size_t)node] = (int64_t)(u - agg_ptr[g]);
+        }
+    std::vector<int> rp((size_t)n + 1, 0);
+    for (int64_t i = 0; i < n; ++i) {
+        int64_t g = node_agg[(size_t)i];
+        rp[(size_t)i + 1] = (int)(agg_ptr[g + 1] - agg_ptr[g]);
+    }
+    for (int64_t i = 0; i < n; ++i) rp[(size_t)i + 1] += rp[(size_t)i];
+    std::vector<int> ci((size_t)rp[(size_t)n]);
+    std::vector<double> cv((size_t)rp[(size_t)n]);
+    std::vector<double> blk;
+    for (int64_t g = 0; g < n_aggs; ++g) {
+        const int na = (int)(agg_ptr[g + 1] - agg_ptr[g]);
+        const uint64_t *nodes = agg_nodes + agg_ptr[g];
+        blk.assign((size_t)na * na, 0.0);
+        for (int li = 0; li < na; ++li) {
+            const int64_t i = (int64_t)nodes[li];
+            // triplets in row order; duplicates on (li,li) summed in order (try_new_from_triplets)
+            bool diag_seen = false; double dsum = 0.0;
+            for (int q = h.row_ptr[(size_t)i]; q < h.row_ptr[(size_t)i + 1]; ++q) {
+                const int64_t j = h.col[(size_t)q];
+                if (node_agg[(size_t)j] == g) {
+                    const int lj = (int)node_local[(size_t)j];
+                    if (lj == li) { dsum = diag_seen ? dsum + h.val[(size_t)q] : h.val[(size_t)q]; diag_seen = true; }
+                    else blk[(size_t)li + (size_t)lj * na] = h.val[(size_t)q];
+                } else {
+                    const double comp = 0.5 * sqrt(diag[(size_t)i] / diag[(size_t)j]) * fabs(h.val[(size_t)q]);
+                    dsum = diag_seen ? dsum + comp : comp; diag_seen = true;
+                }
+            }
+            blk[(size_t)li + (size_t)li * na] = dsum;
+        }
+        // the reference factorises the upper side of the transpose == lower triangle of the block
+        for (int c = 0; c < na; ++c)
+            for (int r = 0; r < c; ++r) blk[(size_t)r + (size_t)c * na] = blk[(size_t)c + (size_t)r * na];
+        if (!host_spd_inverse(na, blk)) FAMG_FAIL(FAMG_ERR_NUMERIC, "aggregate %lld block is not positive definite", (long long)g);
+        for (int li = 0; li < na; ++li) {
+            const int64_t i = (int64_t)nodes[li];
+            for (int lj = 0; lj < na; ++lj) {
+                ci[(size_t)rp[(size_t)i] + lj] = (int)nodes[lj];
+                cv[(size_t)rp[(size_t)i] + lj] = blk[(size_t)li + (size_t)lj * na];
+            }
+        }
+    }
+    famg_smoother *s = new famg_smoother();
+    s->ctx = a->ctx; s->kind = SM_SPARSE_INV; s->n = n;
+    famg_status st = csr_from_host_i32(a->ctx, n, n, rp.data(), ci.data(), cv.data(), &s->minv);
+    if (st != FAMG_OK) { smoother_release(s); return st; }
+    *out = s;
+    return FAMG_OK;
+}
+
+famg_status famg_smoother_retain(famg_smoother *s) {
+    if (!s) FAMG_FAIL(FAMG_ERR_INVALID, "null smoother");
+    s->refs.fetch_add(1);
+    return FAMG_OK;
+}
+famg_status famg_smoother_destroy(famg_smoother *s) {
+    if (s) { cudaSetDevice(s->ctx->device); smoother_release(s); }
+    return FAMG_OK;
+}
+famg_status famg_smoother_dim(const famg_smoother *s, int64_t *n) {
+    if (!s || !n) FAMG_FAIL(FAMG_ERR_INVALID, "null argument");
+    *n = s->n;
+    return FAMG_OK;
+}
+famg_status famg_smoother_diag_download(const famg_smoother *s, double *d) {
+    if (!s || !d) FAMG_FAIL(FAMG_ERR_INVALID, "null argument");
+    if (s->kind != SM_DIAG) FAMG_FAIL(FAMG_ERR_INVALID, "not a diagonal smoother");
+    CUDA_TRY(cudaSetDevice(s->ctx->device));
+    CUDA_TRY(cudaStreamSynchronize(s->ctx->stream));
+    CUDA_TRY(cudaMemcpy(d, s->d, sizeof(double) * s->n, cudaMemcpyDeviceToHost));
+    return FAMG_OK;
+}
+
+famg_status famg_smoother_apply_dev(const famg_smoother *s, famg_vec *out, const famg_vec *rhs) {
+    if (!s || !out || !rhs) FAMG_FAIL(FAMG_ERR_INVALID, "null argument");
+    if (rhs->nrows != s->n || out->nrows != s->n || out->ncols != rhs->ncols) FAMG_FAIL(FAMG_ERR_INVALID, "smoother apply shape mismatch");
+    CUDA_TRY(cudaSetDevice(s->ctx->device));
+    return smoother_apply_dev(s, rhs->p, rhs->ld, out->p, out->ld, (int)rhs->ncols);
+}
+
+famg_status famg_smoother_apply(const famg_smoother *s, double *out, int64_t ld_out, const double *rhs, int64_t ld_rhs, int64_t k) {
+    if (!s || !out || !rhs || k < 0) FAMG_FAIL(FAMG_ERR_INVALID, "bad argument");
+    if (k == 0) return FAMG_OK;
+    famg_vec *x = nullptr, *y = nullptr;
+    FAMG_TRY(famg_vec_create(s->ctx, s->n, k, &x));
+    famg_status st = famg_vec_create(s->ctx, s->n, k, &y);
+    if (st == FAMG_OK) st = famg_vec_upload(x, rhs, ld_rhs);
+    if (st == FAMG_OK) st = famg_smoother_apply_dev(s, y, x);
+    if (st == FAMG_OK) st = famg_vec_download(y, out, ld_out);
+    famg_vec_destroy(x); famg_vec_destroy(y);
+    return st;
+}
+
+// smooth(): iters x { x += M^-1 (b - A x) }.  Diag: one fused kernel per sweep (ping-pong buffer).
+famg_status famg_smooth_dev(const famg_csr *a, const famg_smoother *s, famg_vec *x, const famg_vec *b, int iters) {
+    if (!a || !s || !x || !b || iters < 0) FAMG_FAIL(FAMG_ERR_INVALID, "bad argument");
+    if (a->nrows != a->ncols || s->n != a->nrows || x->nrows != a->nrows || b->nrows != a->nrows || b->ncols != x->ncols)
+        FAMG_FAIL(FAMG_ERR_INVALID, "smooth shape mismatch");
+    famg_ctx *ctx = a->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (iters == 0) return FAMG_OK;
+    famg_vec *t = nullptr, *t2 = nullptr;
+    FAMG_TRY(famg_vec_create(ctx, x->nrows, x->ncols, &t));
+    famg_status st = FAMG_OK;
+    const int k = (int)x->ncols;
+    double *cur = x->p; int64_t ldc = x->ld;
+    double *oth = t->p; int64_t ldo = t->ld;
+    if (s->kind != SM_DIAG) st = famg_vec_create(ctx, x->nrows, x->ncols, &t2);
+    for (int it = 0; it < iters && st == FAMG_OK; ++it) {
+        if (s->kind == SM_DIAG) {
+            SpmvArgs g; g.a = a; g.epi = EPI_SMOOTH; g.x = cur; g.ldx = ldc; g.y = oth; g.ldy = ldo; g.b = b->p; g.ldb = b->ld;
+            g.d = s->d; g.k = k;
+            st = spmv_launch(g);
+            std::swap(cur, oth); std::swap(ldc, ldo);
+        } else {
+            // r = b - A x ; z = M^-1 r ; x += z
+            SpmvArgs g; g.a = a; g.epi = EPI_RESID; g.x = cur; g.ldx = ldc; g.y = oth; g.ldy = ldo; g.b = b->p; g.ldb = b->ld; g.k = k;
+            st = spmv_launch(g);
+            if (st == FAMG_OK) st = smoother_apply_dev(s, oth, ldo, t2->p, t2->ld, k);
+            for (int c = 0; c < k && st == FAMG_OK; ++c) st = vec_add_inplace(ctx, cur + c * ldc, t2->p + c * t2->ld, x->nrows);
+        }
+    }
+    if (st == FAMG_OK && cur != x->p) st = vec_copy(ctx, x->p, x->ld, cur, ldc, x->nrows, k);
+    famg_vec_destroy(t);  // synchronises the stream
+    famg_vec_destroy(t2);
+    return st;
+}
+
+famg_status famg_stationary_iteration_dev(const famg_csr *a, const famg_smoother *diag, int iters, famg_vec *io) {
+    if (!a || !diag || !io) FAMG_FAIL(FAMG_ERR_INVALID, "null argument");
+    if (diag->kind != SM_DIAG) FAMG_FAIL(FAMG_ERR_UNSUPPORTED, "stationary iteration supports Diag preconditioners");
+    if (a->nrows != a->ncols || diag->n != a->nrows || io->nrows != a->nrows) FAMG_FAIL(FAMG_ERR_INVALID, "shape mismatch");
+    famg_ctx *ctx = a->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    famg_vec *t = nullptr;
+    FAMG_TRY(famg_vec_create(ctx, io->nrows, io->ncols, &t));
+    const int k = (int)io->ncols;
+    // x = M rhs
+    famg_status st = vec_scale_rows(ctx, diag->d, io->p, io->ld, t->p, t->ld, io->nrows, k);
+    double *cur = t->p; int64_t ldc = t->ld;
+    double *oth = io->p; int64_t ldo = io->ld;
+    for (int it = 1; it < iters && st == FAMG_OK; ++it) {
+        SpmvArgs g; g.a = a; g.epi = EPI_SI; g.x = cur; g.ldx = ldc; g.y = oth; g.ldy = ldo; g.d = diag->d; g.k = k;
+        st = spmv_launch(g);
+        std::swap(cur, oth); std::swap(ldc, ldo);
+    }
+    if (st == FAMG_OK && cur != io->p) st = vec_copy(ctx, io->p, io->ld, cur, ldc, io->nrows, k);
+    famg_vec_destroy(t);
+    return st;
+}
+
+}  // extern "C"

@@ -1,0 +1,309 @@
+// spmv.cu -- the CSR mat-apply family: y = A x, r = b - A x, fused diagonal smoother sweep,
+// y += A x, and the stationary-iteration step; one or many right-hand sides.
+//
+// Replaces ParSpmmOp::apply / BlockRow::spmm (par_spmm.rs:98-133), the serial CSR LinOp used for
+// R and P (multigrid.rs:157-159), and the unfused smooth()/residual passes (multigrid.rs:341-350,
+// 407-424).
+//
+// Kernel design (HBM-bound, no tensor cores):
+//   * one CTA of 256 threads owns ROWS = 256/TPR consecutive rows; TPR (threads per row: 1, 2, 4,
+//     ..., 32) is picked per matrix from its row-length statistics (csr_finalize_plan) so that a
+//     CTA covers ~2k non-zeros: scalar-per-row for 7-point rows, 4 lanes per row for 27-point
+//     rows, a full warp per row for >128 non-zeros per row.
+//   * phase 1: the CTA's contiguous slice of val[] / col[] is streamed global -> shared with
+//     fully coalesced 128-bit loads (ld.global.nc.L1::no_allocate), independent of row shape.
+//   * phase 2: each row group walks its row out of shared memory and gathers x through L1/L2.
+//     With TPR = 1 adjacent threads read adjacent rows, so for stencil matrices every gather
+//     instruction touches 1-2 cache lines; the adds happen in ascending column order, i.e. the
+//     exact summation order of the reference (bit-identical results when TPR == 1).
+//   * the epilogue fuses the vector work of the caller (residual, smoother update,
+//     prolongation-add, p.Ap partial) so each sweep reads A once and every vector once.
+//   * a slice that does not fit the staging buffer (very irregular rows) is processed straight
+//     from global memory by the same row groups -- slower, still correct.
+// Compiled with -fmad=false: products and sums are rounded separately, like the reference's
+// scalar `dst += a*b` loops.
+#include "common.cuh"
+
+namespace famg {
+
+constexpr int SPMV_THREADS = 256;
+constexpr int SPMV_CAP = 2560;  // staged non-zeros per CTA (30 KB: 20 KB values + 10 KB indices)
+constexpr int SPMV_U = 8;       // gathers in flight per thread per batch
+
+__device__ __forceinline__ int4 ld_stream_i4(const int4 *p) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ double2 ld_stream_d2(const double2 *p) {
+    double2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+
+struct SpmvKernelParams {
+    const int *row_ptr; const int *col; const double *val;
+    int row_begin, row_end;  // rows handled by this launch
+    const double *x; long long ldx;
+    double *y; long long ldy;
+    const double *b; long long ldb;
+    const double *d;
+    int k;
+    double *dot_partials;
+};
+
+template <int TPR, int EPI, bool DOT>
+__global__ void __launch_bounds__(SPMV_THREADS, 4) spmv_kernel(const SpmvKernelParams p) {
+    constexpr int ROWS = SPMV_THREADS / TPR;
+    __shared__ __align__(16) double s_val[SPMV_CAP];
+    __shared__ __align__(16) int s_col[SPMV_CAP];
+    __shared__ double s_red[SPMV_THREADS / 32];
+
+    const int tid = threadIdx.x;
+    const int r0 = p.row_begin + blockIdx.x * ROWS;
+    const int r1 = min(r0 + ROWS, p.row_end);
+    const int q0 = __ldg(p.row_ptr + r0);
+    const int q1 = __ldg(p.row_ptr + r1);
+    const int q0a = q0 & ~3;  // 16-byte aligned start for int4 / 32-byte for double2 pairs
+    const int cnt = q1 - q0a;
+    const bool staged = cnt <= SPMV_CAP;
+
+    if (staged) {
+        const int n4 = (cnt + 3) >> 2;
+        const int4 *gc = reinterpret_cast<const int4 *>(p.col + q0a);
+        const double2 *gv = reinterpret_cast<const double2 *>(p.val + q0a);
+        int4 *sc = reinterpret_cast<int4 *>(s_col);
+        double2 *sv = reinterpret_cast<double2 *>(s_val);
+        // issue all loads of a thread before the stores (memory-level parallelism)
+        for (int i = tid; i < n4; i += SPMV_THREADS * 2) {
+            const int i2 = i + SPMV_THREADS;
+            int4 c0 = ld_stream_i4(gc + i);
+            double2 v0 = ld_stream_d2(gv + 2 * i), v1 = ld_stream_d2(gv + 2 * i + 1);
+            int4 c1 = make_int4(0, 0, 0, 0);
+            double2 v2 = make_double2(0, 0), v3 = make_double2(0, 0);
+            if (i2 < n4) {
+                c1 = ld_stream_i4(gc + i2);
+                v2 = ld_stream_d2(gv + 2 * i2);
+                v3 = ld_stream_d2(gv + 2 * i2 + 1);
+            }
+            sc[i] = c0; sv[2 * i] = v0; sv[2 * i + 1] = v1;
+            if (i2 < n4) { sc[i2] = c1; sv[2 * i2] = v2; sv[2 * i2 + 1] = v3; }
+        }
+    }
+    __syncthreads();
+
+    const int g = tid / TPR;
+    const int lane = tid % TPR;
+    const int row = r0 + g;
+    const bool active = row < r1;
+    int a = 0, e = 0;
+    if (active) { a = __ldg(p.row_ptr + row); e = __ldg(p.row_ptr + row + 1); }
+
+    double dot_acc = 0.0;
+    for (int c = 0; c < p.k; ++c) {
+        const double *__restrict__ xc = p.x + (long long)c * p.ldx;
+        double s = 0.0;
+        if (staged) {
+            for (int q = a - q0a + lane; q < e - q0a; q += TPR * SPMV_U) {
+                double pr[SPMV_U];
+#pragma unroll
+                for (int u = 0; u < SPMV_U; ++u) {
+                    const int qq = q + u * TPR;
+                    pr[u] = 0.0;
+                    if (qq < e - q0a) pr[u] = s_val[qq] * __ldg(xc + s_col[qq]);
+                }
+#pragma unroll
+                for (int u = 0; u < SPMV_U; ++u) s += pr[u];
+            }
+        } else {
+            for (int q = a + lane; q < e; q += TPR * SPMV_U) {
+                double pr[SPMV_U];
+#pragma unroll
+                for (int u = 0; u < SPMV_U; ++u) {
+                    const int qq = q + u * TPR;
+                    pr[u] = 0.0;
+                    if (qq < e) pr[u] = __ldg(p.val + qq) * __ldg(xc + __ldg(p.col + qq));
+                }
+#pragma unroll
+                for (int u = 0; u < SPMV_U; ++u) s += pr[u];
+            }
+        }
+        if (TPR > 1) {
+#pragma unroll
+            for (int o = TPR >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        }
+        if (active && lane == 0) {
+            double *yc = p.y + (long long)c * p.ldy;
+            if (EPI == EPI_SPMV) {
+                yc[row] = s;
+            } else if (EPI == EPI_RESID) {
+                yc[row] = p.b[(long long)c * p.ldb + row] - s;
+            } else if (EPI == EPI_SMOOTH) {
+                // x' = x + d .* (b - A x)   (multigrid.rs:419-422)
+                const double r = p.b[(long long)c * p.ldb + row] - s;
+                yc[row] = xc[row] + p.d[row] * r;
+            } else if (EPI == EPI_ADD) {
+                yc[row] = yc[row] + s;
+            } else {  // EPI_SI: x' = x + d .* (x - A x)   (smoothers.rs:153-156, literal)
+                const double xr = xc[row];
+                yc[row] = xr + p.d[row] * (xr - s);
+            }
+            if (DOT) dot_acc += xc[row] * s;
+        }
+    }
+    if (DOT) {
+        // deterministic CTA reduction of x_i * (A x)_i -> one partial per CTA
+        double v = dot_acc;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((tid & 31) == 0) s_red[tid >> 5] = v;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < SPMV_THREADS / 32; ++w) t += s_red[w];
+            p.dot_partials[blockIdx.x] = t;
+        }
+    }
+}
+
+template <int TPR, int EPI>
+static void launch_tpr_epi(const SpmvKernelParams &kp, bool dot, int grid, cudaStream_t st) {
+    if (dot) spmv_kernel<TPR, EPI, true><<<grid, SPMV_THREADS, 0, st>>>(kp);
+    else spmv_kernel<TPR, EPI, false><<<grid, SPMV_THREADS, 0, st>>>(kp);
+}
+
+template <int TPR>
+static void launch_tpr(const SpmvKernelParams &kp, int epi, bool dot, int grid, cudaStream_t st) {
+    switch (epi) {
+        case EPI_SPMV: launch_tpr_epi<TPR, EPI_SPMV>(kp, dot, grid, st); break;
+        case EPI_RESID: launch_tpr_epi<TPR, EPI_RESID>(kp, false, grid, st); break;
+        case EPI_SMOOTH: launch_tpr_epi<TPR, EPI_SMOOTH>(kp, false, grid, st); break;
+        case EPI_ADD: launch_tpr_epi<TPR, EPI_ADD>(kp, false, grid, st); break;
+        default: launch_tpr_epi<TPR, EPI_SI>(kp, false, grid, st); break;
+    }
+}
+
+famg_status spmv_launch(const SpmvArgs &args, int *num_ctas) {
+    const famg_csr *a = args.a;
+    famg_ctx *ctx = a->ctx;
+    cudaStream_t st = args.stream ? args.stream : ctx->stream;
+    int row_begin = args.row_begin;
+    int row_end = args.row_end < 0 ? (int)a->nrows : args.row_end;
+    if (num_ctas) *num_ctas = 0;
+    if (row_end <= row_begin || args.k <= 0) return FAMG_OK;
+    if ((args.epi == EPI_RESID || args.epi == EPI_SMOOTH) && !args.b) FAMG_FAIL(FAMG_ERR_INVALID, "spmv: missing rhs");
+    if ((args.epi == EPI_SMOOTH || args.epi == EPI_SI) && (!args.d || args.y == args.x))
+        FAMG_FAIL(FAMG_ERR_INVALID, "spmv: smoother sweep needs a diagonal and distinct in/out vectors");
+    if (args.dot_partials && (args.k != 1 || args.epi != EPI_SPMV)) FAMG_FAIL(FAMG_ERR_INVALID, "spmv: dot needs k == 1");
+    SpmvKernelParams kp;
+    kp.row_ptr = a->row_ptr; kp.col = a->col; kp.val = a->val;
+    kp.row_begin = row_begin; kp.row_end = row_end;
+    kp.x = args.x; kp.ldx = args.ldx; kp.y = args.y; kp.ldy = args.ldy;
+    kp.b = args.b; kp.ldb = args.ldb; kp.d = args.d; kp.k = args.k;
+    kp.dot_partials = args.dot_partials;
+    const int tpr = a->tpr;
+    const int rows_per_cta = SPMV_THREADS / tpr;
+    const int grid = (int)ceil_div(row_end - row_begin, rows_per_cta);
+    const bool dot = args.dot_partials != nullptr;
+    switch (tpr) {
+        case 1: launch_tpr<1>(kp, args.epi, dot, grid, st); break;
+        case 2: launch_tpr<2>(kp, args.epi, dot, grid, st); break;
+        case 4: launch_tpr<4>(kp, args.epi, dot, grid, st); break;
+        case 8: launch_tpr<8>(kp, args.epi, dot, grid, st); break;
+        case 16: launch_tpr<16>(kp, args.epi, dot, grid, st); break;
+        default: launch_tpr<32>(kp, args.epi, dot, grid, st); break;
+    }
+    count_launch(ctx);
+    KERNEL_CHECK();
+    if (num_ctas) *num_ctas = grid;
+    return FAMG_OK;
+}
+
+}  // namespace famg
+
+using namespace famg;
+
+static famg_status check_apply(const famg_csr *a, const famg_vec *out, const famg_vec *rhs) {
+    if (!a || !out || !rhs) FAMG_FAIL(FAMG_ERR_INVALID, "null argument");
+    if (rhs->nrows != a->ncols || out->nrows != a->nrows || out->ncols != rhs->ncols)
+        FAMG_FAIL(FAMG_ERR_INVALID, "spmm shape mismatch: A %lldx%lld, rhs %lldx%lld, out %lldx%lld", (long long)a->nrows,
+                  (long long)a->ncols, (long long)rhs->nrows, (long long)rhs->ncols, (long long)out->nrows, (long long)out->ncols);
+    if (out->p == rhs->p) FAMG_FAIL(FAMG_ERR_INVALID, "out aliases rhs");
+    return FAMG_OK;
+}
+
+extern "C" {
+
+famg_status famg_spmm_dev(const famg_csr *a, famg_vec *out, const famg_vec *rhs) {
+    FAMG_TRY(check_apply(a, out, rhs));
+    CUDA_TRY(cudaSetDevice(a->ctx->device));
+    SpmvArgs s; s.a = a; s.epi = EPI_SPMV; s.x = rhs->p; s.ldx = rhs->ld; s.y = out->p; s.ldy = out->ld; s.k = (int)rhs->ncols;
+    return spmv_launch(s);
+}
+
+famg_status famg_residual_dev(const famg_csr *a, famg_vec *out, const famg_vec *b, const famg_vec *x) {
+    FAMG_TRY(check_apply(a, out, x));
+    if (!b || b->nrows != a->nrows || b->ncols != x->ncols) FAMG_FAIL(FAMG_ERR_INVALID, "residual: rhs shape mismatch");
+    CUDA_TRY(cudaSetDevice(a->ctx->device));
+    SpmvArgs s; s.a = a; s.epi = EPI_RESID; s.x = x->p; s.ldx = x->ld; s.y = out->p; s.ldy = out->ld;
+    s.b = b->p; s.ldb = b->ld; s.k = (int)x->ncols;
+    return spmv_launch(s);
+}
+
+famg_status famg_spmm_add_dev(const famg_csr *a, famg_vec *y, const famg_vec *x) {
+    FAMG_TRY(check_apply(a, y, x));
+    CUDA_TRY(cudaSetDevice(a->ctx->device));
+    SpmvArgs s; s.a = a; s.epi = EPI_ADD; s.x = x->p; s.ldx = x->ld; s.y = y->p; s.ldy = y->ld; s.k = (int)x->ncols;
+    return spmv_launch(s);
+}
+
+// LinOp::apply(out: MatMut, rhs: MatRef) with host buffers: stage in, apply, stage out.
+famg_status famg_spmm(const famg_csr *a, double *out, int64_t ld_out, const double *rhs, int64_t ld_rhs, int64_t k) {
+    if (!a || !out || !rhs || k < 0) FAMG_FAIL(FAMG_ERR_INVALID, "bad argument");
+    if (ld_out < a->nrows || ld_rhs < a->ncols) FAMG_FAIL(FAMG_ERR_INVALID, "leading dimension too small");
+    if (k == 0) return FAMG_OK;
+    famg_vec *x = nullptr, *y = nullptr;
+    FAMG_TRY(famg_vec_create(a->ctx, a->ncols, k, &x));
+    famg_status st = famg_vec_create(a->ctx, a->nrows, k, &y);
+    if (st == FAMG_OK) st = famg_vec_upload(x, rhs, ld_rhs);
+    if (st == FAMG_OK) st = famg_spmm_dev(a, y, x);
+    if (st == FAMG_OK) st = famg_vec_download(y, out, ld_out);
+    famg_vec_destroy(x); famg_vec_destroy(y);
+    return st;
+}
+
+famg_status famg_time_kernel(const famg_csr *a, int which, int reps, int warmup, float *ms_avg) {
+    if (!a || !ms_avg || reps <= 0 || a->nrows != a->ncols) FAMG_FAIL(FAMG_ERR_INVALID, "bad argument (square operator required)");
+    famg_ctx *ctx = a->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    famg_vec *x = nullptr, *y = nullptr, *b = nullptr, *d = nullptr;
+    FAMG_TRY(famg_vec_create(ctx, a->nrows, 1, &x));
+    famg_status st = famg_vec_create(ctx, a->nrows, 1, &y);
+    if (st == FAMG_OK) st = famg_vec_create(ctx, a->nrows, 1, &b);
+    if (st == FAMG_OK) st = famg_vec_create(ctx, a->nrows, 1, &d);
+    if (st == FAMG_OK) st = famg_vec_fill(x, 1.0);
+    if (st == FAMG_OK) st = famg_vec_fill(b, 1.0);
+    if (st == FAMG_OK) st = famg_vec_fill(d, 0.125);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (st == FAMG_OK) {
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        SpmvArgs s; s.a = a; s.x = x->p; s.ldx = x->ld; s.y = y->p; s.ldy = y->ld; s.b = b->p; s.ldb = b->ld; s.d = d->p; s.k = 1;
+        s.epi = which == 0 ? EPI_SPMV : which == 1 ? EPI_RESID : EPI_SMOOTH;
+        for (int i = 0; i < warmup && st == FAMG_OK; ++i) st = spmv_launch(s);
+        cudaEventRecord(e0, ctx->stream);
+        for (int i = 0; i < reps && st == FAMG_OK; ++i) st = spmv_launch(s);
+        cudaEventRecord(e1, ctx->stream);
+        cudaError_t e = cudaEventSynchronize(e1);
+        float ms = 0;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+        if (e != cudaSuccess && st == FAMG_OK) { set_error("timing failed: %s", cudaGetErrorString(e)); st = FAMG_ERR_CUDA; }
+        *ms_avg = ms / (float)reps;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
+    famg_vec_destroy(x); famg_vec_destroy(y); famg_vec_destroy(b); famg_vec_destroy(d);
+    return st;
+}
+
+}  // extern "C"

@@ -1,0 +1,245 @@
+/*
+ * famg.h -- C ABI of the B200-native faer-amg hot path (libfamg.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types, no exceptions
+ * across it.  Every entry point names the interface of the reference crate (aujxn/faer-amg,
+ * paths relative to the crate root) that it replaces.  The Rust-side binding a maintainer would
+ * add is shown in INTEGRATION.md (rust/faer-amg-b200/src/ffi.rs).
+ *
+ * Conventions
+ *   - Host CSR inputs use the reference's index width: `usize` == uint64_t row_ptr[nrows+1],
+ *     col_idx[nnz] (sorted, unique per row, compressed), f64 values.  On the device indices are
+ *     32-bit (nnz and ncols must be < 2^31 per device matrix).
+ *   - Dense multivectors are column-major with unit row stride (faer Mat<f64>): ptr, ld >= nrows.
+ *   - Every function returns famg_status (0 = OK).  On failure famg_last_error() returns a
+ *     message for the calling thread; the Rust shim turns non-zero into panic! to keep the
+ *     reference's error convention (par_spmm.rs:35,78; hierarchy.rs:259-264).
+ *   - Handles are immutable after creation and reference-counted internally: a multigrid keeps
+ *     its level operators alive after the caller destroys its own handles (Arc semantics,
+ *     core.rs:11-12, multigrid.rs:172-179).
+ *   - All work of one famg_ctx is ordered on that context's CUDA stream.  Functions taking host
+ *     pointers stage through device memory and return after the result is on the host;
+ *     `_dev` functions only enqueue.
+ *   - There is no CPU fallback: every entry point that computes fails with FAMG_ERR_CUDA when
+ *     no sm_100 device is usable.
+ */
+#ifndef FAMG_H
+#define FAMG_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int famg_status;
+enum {
+    FAMG_OK = 0,
+    FAMG_ERR_INVALID = 1,      /* bad argument / shape mismatch (reference: assert!/panic!) */
+    FAMG_ERR_CUDA = 2,         /* CUDA runtime failure, no device */
+    FAMG_ERR_ALLOC = 3,
+    FAMG_ERR_NUMERIC = 4,      /* missing/non-positive diagonal, Cholesky breakdown */
+    FAMG_ERR_NO_CONVERGENCE = 5, /* CgError::NoConvergence (utils.rs:649-653) */
+    FAMG_ERR_NOT_SPD = 6,      /* CgError non-positive-definite variants */
+    FAMG_ERR_COMM = 7,         /* NCCL failure */
+    FAMG_ERR_UNSUPPORTED = 8
+};
+
+typedef struct famg_ctx famg_ctx;
+typedef struct famg_csr famg_csr;           /* device CSR: SparseRowMat<usize,f64> (core.rs:14) */
+typedef struct famg_vec famg_vec;           /* device Mat<f64>, column-major */
+typedef struct famg_smoother famg_smoother; /* Arc<dyn BiPrecond<f64>> of one level */
+typedef struct famg_mg famg_mg;             /* Multigrid (multigrid.rs:171-179) */
+typedef struct famg_comm famg_comm;         /* one rank of a row-partitioned multi-GPU job */
+typedef struct famg_dist_mg famg_dist_mg;   /* row-partitioned Multigrid + PCG */
+
+const char *famg_last_error(void);
+const char *famg_version(void);
+
+/* ---- context ---------------------------------------------------------------------------- */
+/* One context per (process, device).  Replaces faer::set_global_parallelism / Par::Rayon(n)
+ * (examples/amg/main.rs:227-228) as the "where does the work run" switch. */
+famg_status famg_ctx_create(int device, famg_ctx **out);
+famg_status famg_ctx_destroy(famg_ctx *ctx);
+famg_status famg_ctx_sync(famg_ctx *ctx);
+/* the context's cudaStream_t (as void*) so a caller can order its own work / events on it */
+famg_status famg_ctx_stream(famg_ctx *ctx, void **stream);
+/* SM count, device name, free/total memory -- for reports */
+famg_status famg_ctx_info(famg_ctx *ctx, int *num_sms, int64_t *mem_free, int64_t *mem_total,
+                          char *name, int name_len);
+
+/* ---- CSR operator: SparseMatOp::new / ParSpmmOp::new (core.rs:56-74, par_spmm.rs:31-96) ---- */
+famg_status famg_csr_create(famg_ctx *ctx, int64_t nrows, int64_t ncols, const uint64_t *row_ptr,
+                            const uint64_t *col_idx, const double *val, famg_csr **out);
+/* SparseRowMat::try_new_from_triplets (interpolation/mod.rs:807, simple_geometric.rs:76):
+ * sorted unique columns per row, duplicates summed in input order, explicit zeros kept. */
+famg_status famg_csr_create_from_triplets(famg_ctx *ctx, int64_t nrows, int64_t ncols, int64_t nt,
+                                          const uint64_t *rows, const uint64_t *cols,
+                                          const double *vals, famg_csr **out);
+famg_status famg_csr_retain(famg_csr *a);
+famg_status famg_csr_destroy(famg_csr *a); /* release */
+famg_status famg_csr_dims(const famg_csr *a, int64_t *nrows, int64_t *ncols, int64_t *nnz);
+/* caller-allocated host buffers (row_ptr: nrows+1, col_idx/val: nnz) so Rust owns what it wraps
+ * in SparseRowMat::new(SymbolicSparseRowMat::new_checked(..), vals). */
+famg_status famg_csr_download(const famg_csr *a, uint64_t *row_ptr, uint64_t *col_idx, double *val);
+/* row-length statistics that drive the kernel selection (threads-per-row, staged fraction) */
+famg_status famg_csr_plan(const famg_csr *a, int *threads_per_row, int *rows_per_cta,
+                          double *avg_row_nnz, int *max_row_nnz);
+/* rows [row_begin,row_end) of `a` as a new matrix with the same column space
+ * (row partitioning for multi-GPU) */
+famg_status famg_csr_row_slab(const famg_csr *a, int64_t row_begin, int64_t row_end, famg_csr **out);
+
+/* Synthetic operators generated on the device (the reference ships no 3-D
+ * generator, F8).  G7: 7-point Laplacian; G27: 27-point anisotropic diffusion. */
+famg_status famg_gallery_g7(famg_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, famg_csr **out);
+famg_status famg_gallery_g27(famg_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, double eps_y,
+                             double eps_z, famg_csr **out);
+
+/* ---- dense multivectors on the device ----------------------------------------------------- */
+famg_status famg_vec_create(famg_ctx *ctx, int64_t nrows, int64_t ncols, famg_vec **out);
+famg_status famg_vec_destroy(famg_vec *v);
+famg_status famg_vec_dims(const famg_vec *v, int64_t *nrows, int64_t *ncols);
+famg_status famg_vec_upload(famg_vec *v, const double *host, int64_t ld);
+famg_status famg_vec_download(const famg_vec *v, double *host, int64_t ld);
+famg_status famg_vec_fill(famg_vec *v, double value);
+famg_status famg_vec_copy(famg_vec *dst, const famg_vec *src);
+/* raw device pointer + leading dimension (for CUDA-event timing harnesses / torch interop) */
+famg_status famg_vec_ptr(const famg_vec *v, void **dev_ptr, int64_t *ld);
+/* column-wise ||v_j||_2 into host `out` (ncols doubles) */
+famg_status famg_vec_norm2(const famg_vec *v, double *out);
+
+/* ---- mat-apply: ParSpmmOp::apply / LinOp::apply (par_spmm.rs:98-158) ----------------------- */
+/* out = A * rhs with host buffers (the literal LinOp::apply(out: MatMut, rhs: MatRef) drop-in) */
+famg_status famg_spmm(const famg_csr *a, double *out, int64_t ld_out, const double *rhs,
+                      int64_t ld_rhs, int64_t k);
+famg_status famg_spmm_dev(const famg_csr *a, famg_vec *out, const famg_vec *rhs);
+/* out = rhs_b - A * x   (multigrid.rs:341-342, fused) */
+famg_status famg_residual_dev(const famg_csr *a, famg_vec *out, const famg_vec *b, const famg_vec *x);
+/* y += A * x            (multigrid.rs:349-350, fused prolongation-correct) */
+famg_status famg_spmm_add_dev(const famg_csr *a, famg_vec *y, const famg_vec *x);
+
+/* ---- smoothers ---------------------------------------------------------------------------- */
+enum { FAMG_DIAG_L1 = 0, FAMG_DIAG_L2 = 1, FAMG_DIAG_JACOBI = 2 };
+/* new_l1 / new_l2 / new_jacobi (smoothers.rs:63-76, 43-61, 78-86) -> faer Diag<f64> */
+famg_status famg_smoother_diag(const famg_csr *a, int kind, double omega, famg_smoother **out);
+/* a caller-computed Diag (any LinOp that is a row scaling) */
+famg_status famg_smoother_diag_from_host(famg_ctx *ctx, int64_t n, const double *d, famg_smoother **out);
+/* CoarseSolverKind::Cholesky.build_from_sparse -> SparseCholeskySolve (coarse_solvers.rs:20-31,
+ * 173-206): exact solve; realised as host Cholesky + explicit inverse applied as a device GEMV */
+famg_status famg_smoother_cholesky(const famg_csr *a, famg_smoother **out);
+/* BlockSmoother::new over aggregates with diagonal compensation (block_smoothers.rs:88-123,
+ * 293-324), materialised as the block-diagonal M^-1 of into_sparse_mat (:125-146).
+ * agg_ptr[n_aggs+1], agg_nodes ascending inside each aggregate. */
+famg_status famg_smoother_block(const famg_csr *a, int64_t n_aggs, const uint64_t *agg_ptr,
+                                const uint64_t *agg_nodes, famg_smoother **out);
+famg_status famg_smoother_retain(famg_smoother *s);
+famg_status famg_smoother_destroy(famg_smoother *s);
+famg_status famg_smoother_dim(const famg_smoother *s, int64_t *n);
+/* Diag smoothers only: copy d to host (n doubles) */
+famg_status famg_smoother_diag_download(const famg_smoother *s, double *d);
+/* LinOp::apply: out = M^-1 rhs (host buffers / device vectors) */
+famg_status famg_smoother_apply(const famg_smoother *s, double *out, int64_t ld_out,
+                                const double *rhs, int64_t ld_rhs, int64_t k);
+famg_status famg_smoother_apply_dev(const famg_smoother *s, famg_vec *out, const famg_vec *rhs);
+/* smooth() (multigrid.rs:407-424): iters x { x += M^-1 (b - A x) }, one fused kernel per sweep
+ * for Diag smoothers (A is read once per sweep). */
+famg_status famg_smooth_dev(const famg_csr *a, const famg_smoother *s, famg_vec *x, const famg_vec *b,
+                            int iters);
+/* StationaryIteration::apply_in_place with a Diag preconditioner (smoothers.rs:146-159 as used
+ * by hierarchy.rs:219-226), restated literally including r = x - A x. */
+famg_status famg_stationary_iteration_dev(const famg_csr *a, const famg_smoother *diag, int iters,
+                                          famg_vec *io);
+
+/* ---- Multigrid (multigrid.rs:190-249, 251-380, 469-473) ------------------------------------ */
+famg_status famg_mg_create(const famg_csr *a0, const famg_smoother *s0, famg_mg **out); /* new */
+famg_status famg_mg_add_level(famg_mg *mg, const famg_csr *a, const famg_smoother *s,
+                              const famg_csr *r, const famg_csr *p);                /* add_level */
+famg_status famg_mg_set_cycle(famg_mg *mg, int mu, int smoothing_steps); /* with_cycle_type/_steps */
+famg_status famg_mg_levels(const famg_mg *mg, int *levels);
+famg_status famg_mg_destroy(famg_mg *mg);
+/* Multigrid::apply: out = B rhs, one mu-cycle from a zero guess; host buffers */
+famg_status famg_mg_apply(famg_mg *mg, double *out, int64_t ld_out, const double *rhs,
+                          int64_t ld_rhs, int64_t k);
+famg_status famg_mg_apply_dev(famg_mg *mg, famg_vec *out, const famg_vec *rhs);
+/* algorithmic HBM bytes of one cycle with k right-hand sides (SURVEY 8(d) formulas) */
+famg_status famg_mg_cycle_bytes(const famg_mg *mg, int64_t k, double *bytes);
+
+/* ---- hierarchy construction: the sparse expressions of smoothed_aggregation ---------------- */
+/* `&a * &b` on SparseRowMat (interpolation/mod.rs:828,938): sorted, unpruned structural product;
+ * every entry accumulates in ascending inner index. */
+famg_status famg_spgemm(const famg_csr *a, const famg_csr *b, famg_csr **out);
+/* p.transpose().to_row_major() (interpolation/mod.rs:824-827) */
+famg_status famg_transpose(const famg_csr *a, famg_csr **out);
+/* smooth_interpolation(mat, p, jacobi_weight) (interpolation/mod.rs:927-946), fused into the
+ * SpGEMM numeric epilogue */
+famg_status famg_smooth_interpolation(const famg_csr *a, const famg_csr *p, double omega,
+                                      famg_csr **out);
+/* interpolation/mod.rs:811-828 in one call: P = smooth^steps(P0); R = P^T; A_c = R (A P). */
+famg_status famg_galerkin(const famg_csr *a, const famg_csr *p0, int smoothing_steps, double omega,
+                          famg_csr **p, famg_csr **r, famg_csr **a_coarse);
+/* tentative prolongator of smoothed_aggregation (interpolation/mod.rs:747-809): per-aggregate
+ * thin SVD of the near-null block on the host (tiny dense work), P uploaded as CSR.
+ * near_null: n_fine x k column-major; coarse_nn (out): (n_aggs*cand) x k column-major. */
+famg_status famg_tentative_p(famg_ctx *ctx, int64_t n_fine, int64_t block_size, int64_t k,
+                             int64_t cand, const double *near_null, int64_t ld_nn, int64_t n_aggs,
+                             const uint64_t *agg_ptr, const uint64_t *agg_nodes, famg_csr **p,
+                             double *coarse_nn);
+/* coarse_nn.qr().compute_thin_Q() (hierarchy.rs:228); host, in place, R with positive diagonal */
+famg_status famg_thin_q(int64_t n, int64_t k, double *a, int64_t lda);
+
+/* ---- PCG: faer conjugate_gradient as driven by utils.rs:574-609 ----------------------------- */
+typedef struct {
+    int64_t iter_count;
+    double abs_residual;
+    double rel_residual;
+} famg_cg_info;
+enum { FAMG_PC_NONE = 0, FAMG_PC_SMOOTHER = 1, FAMG_PC_MG = 2 };
+/* x (in: initial guess unless zero_guess; out: solution) and b are host buffers of a.nrows
+ * doubles.  precond: famg_smoother* or famg_mg* according to pc_kind.  Returns
+ * FAMG_ERR_NO_CONVERGENCE with info filled when max_iters is hit. */
+famg_status famg_pcg_solve(const famg_csr *a, int pc_kind, void *precond, double *x, const double *b,
+                           double rel_tol, double abs_tol, int64_t max_iters, int zero_guess,
+                           famg_cg_info *info);
+famg_status famg_pcg_solve_dev(const famg_csr *a, int pc_kind, void *precond, famg_vec *x,
+                               const famg_vec *b, double rel_tol, double abs_tol, int64_t max_iters,
+                               int zero_guess, famg_cg_info *info);
+/* stationary_solver (examples/simple_geometric.rs:117-158); returns iterations in *iters */
+famg_status famg_stationary_solve(const famg_csr *a, int pc_kind, void *precond, double *x,
+                                  const double *b, double rel_tol, int64_t max_iters, int64_t *iters);
+
+/* ---- multi-GPU: 1-D row partition, NCCL halo exchange ------------------------- */
+#define FAMG_UNIQUE_ID_BYTES 128
+famg_status famg_comm_unique_id(void *id_bytes /* 128 */);
+famg_status famg_comm_create(famg_ctx *ctx, int nranks, int rank, const void *id_bytes, famg_comm **out);
+famg_status famg_comm_destroy(famg_comm *c);
+/* sum-all-reduce of n doubles on the host (setup-time plumbing; also a smoke test of the comm) */
+famg_status famg_comm_allreduce_sum(famg_comm *c, double *vals, int n);
+/* Row-partitioned multigrid from a replicated global hierarchy: level l owns rows
+ * [row_splits[l][rank], row_splits[l][rank+1]).  Levels with fewer than `replicate_below` rows
+ * per rank are run replicated after an all-gather of the restricted residual. */
+famg_status famg_dist_mg_create(famg_comm *c, famg_mg *global_mg, const int64_t *const *row_splits,
+                                int64_t replicate_below, famg_dist_mg **out);
+famg_status famg_dist_mg_destroy(famg_dist_mg *d);
+/* PCG on the partitioned system: x_local/b_local are this rank's rows (host buffers). */
+famg_status famg_dist_pcg_solve(famg_dist_mg *d, double *x_local, const double *b_local,
+                                double rel_tol, double abs_tol, int64_t max_iters, int zero_guess,
+                                famg_cg_info *info);
+famg_status famg_dist_pcg_solve_dev(famg_dist_mg *d, famg_vec *x_local, const famg_vec *b_local,
+                                    double rel_tol, double abs_tol, int64_t max_iters,
+                                    int zero_guess, famg_cg_info *info);
+/* distributed y_local = A x_local (halo exchange + overlap), device vectors of local rows */
+famg_status famg_dist_spmv_dev(famg_dist_mg *d, famg_vec *y_local, const famg_vec *x_local);
+famg_status famg_dist_mg_apply_dev(famg_dist_mg *d, famg_vec *out_local, const famg_vec *rhs_local);
+
+/* ---- instrumentation ---------------------------------------------------------------------- */
+/* kernels launched by this context since creation (bench.py's gpu_launches) */
+famg_status famg_ctx_launch_count(const famg_ctx *ctx, int64_t *count);
+/* time `reps` back-to-back launches of one fused kernel class with CUDA events on the context
+ * stream; returns average milliseconds per launch.  which: 0 SpMV y=Ax, 1 residual,
+ * 2 fused diagonal smoother sweep.  Vectors are internal scratch (values irrelevant). */
+famg_status famg_time_kernel(const famg_csr *a, int which, int reps, int warmup, float *ms_avg);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FAMG_H */

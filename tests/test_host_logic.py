@@ -1,0 +1,93 @@
+"""CPU tests of host-side logic: partitions, row splits for the multi-GPU path, and the
+world_size-2 rendezvous plumbing over gloo."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+import oracle as O
+from faer_amg_b200.partitioners import GeometricPartitioner, Partition, geometric_partition
+from faer_amg_b200.distributed import level_row_splits, slab_splits
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_geometric_partition_matches_oracle_aggregates():
+    for dims in [(8, 8, 8), (6, 4, 2), (5, 7, 3), (16, 1, 1)]:
+        part, coarse = geometric_partition(dims)
+        ap, an, dc = O.geometric_aggregates(dims)
+        assert np.array_equal(part.agg_ptr, ap) and np.array_equal(part.agg_nodes, an) and tuple(coarse) == tuple(dc)
+        for agg in part.aggregates():
+            assert np.all(np.diff(agg) > 0)
+        assert np.array_equal(np.sort(part.agg_nodes), np.arange(np.prod(dims)))
+
+
+def test_partition_validation():
+    with pytest.raises(ValueError):
+        Partition([0, 2, 3], [0, 1, 1], 3)
+    p = Partition.from_node_to_agg([1, 0, 1, 0])
+    assert p.naggs() == 2 and p.node_to_agg().tolist() == [1, 0, 1, 0]
+
+
+def test_geometric_partitioner_tracks_levels():
+    gp = GeometricPartitioner((8, 8, 8))
+    assert gp(0, None, None).naggs() == 64
+    assert gp(1, None, None).naggs() == 8
+    assert gp.dims == [(8, 8, 8), (4, 4, 4), (2, 2, 2)]
+
+
+def test_slab_splits_keep_aggregates_on_one_rank():
+    # z-slabs of even thickness: 2x2x2 aggregates never straddle a rank boundary
+    dims = [(16, 16, 16), (8, 8, 8), (4, 4, 4), (2, 2, 2)]
+    for nranks in (1, 2, 4, 8):
+        splits = level_row_splits(dims, nranks)
+        assert len(splits) == len(dims)
+        for lvl, (d, s) in enumerate(zip(dims, splits)):
+            assert s[0] == 0 and s[-1] == np.prod(d) and np.all(np.diff(s) >= 0)
+        fine, coarse = splits[0], splits[1]
+        part, _ = geometric_partition(dims[0])
+        n2a = part.node_to_agg()
+        for r in range(nranks):
+            aggs = np.unique(n2a[fine[r]:fine[r + 1]])
+            if len(aggs):
+                assert aggs.min() >= coarse[r] and aggs.max() < coarse[r + 1]
+    assert slab_splits((4, 4, 6), 4).tolist() == [0, 32, 64, 96, 96] or slab_splits((4, 4, 6), 4)[-1] == 96
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from faer_amg_b200.distributed import broadcast_unique_id, gather_rows, level_row_splits
+    # rank 0 invents the 128-byte id (no NCCL needed for the plumbing test); everyone must agree
+    uid = broadcast_unique_id(make=lambda: bytes(range(128)))
+    splits = level_row_splits([(4, 4, 8), (2, 2, 4)], world)
+    lo, hi = splits[0][rank], splits[0][rank + 1]
+    full = gather_rows(np.arange(lo, hi, dtype=np.float64), splits[0])
+    q.put((rank, uid == bytes(range(128)), bool(np.array_equal(full, np.arange(128.0)))))
+    dist.destroy_process_group()
+
+
+def test_world_size_2_plumbing_over_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True, True), (1, True, True)]
