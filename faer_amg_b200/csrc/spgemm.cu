@@ -66,7 +66,9 @@ __device__ int sg_row_insert(int i, int lane, const SgMat &a, const SgMat &b, in
         }
     }
     group_sync<GROUP>();
-    return *cnt;
+    const int distinct = *cnt;
+    group_sync<GROUP>();  // every lane has read the counter before a caller reuses it
+    return distinct;
 }
 
 template <int GROUP>
