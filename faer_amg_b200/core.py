@@ -65,6 +65,10 @@ class Context:
         call("famg_ctx_info", self._h, C.byref(sms), C.byref(free), C.byref(total), name, 256)
         return {"num_sms": sms.value, "mem_free": free.value, "mem_total": total.value, "name": name.value.decode()}
 
+    def set_option(self, key: str, value: int):
+        """Kernel-selection knobs for A/B measurements (see famg_ctx_set_option)."""
+        call("famg_ctx_set_option", self._h, key.encode(), int(value))
+
     def launch_count(self) -> int:
         n = C.c_int64()
         call("famg_ctx_launch_count", self._h, C.byref(n))

@@ -65,6 +65,11 @@ struct famg_ctx {
     double *pcg_ws = nullptr;     // PCG work vectors (r, p, z, q), kept so the V-cycle graph is reused
     int64_t pcg_ws_cap = 0;
     std::mutex mu;
+    // SpMV kernel selection (spmv.cu): 1 = one staged chunk per CTA, 2 = persistent TMA pipeline for
+    // operators with at least tma_min_rows rows.  Overridable with FAMG_SPMV_VARIANT / FAMG_TMA_MIN_ROWS
+    // for A/B measurements.
+    int spmv_variant = 2;
+    int tma_min_rows = 1 << 17;
 };
 
 struct famg_csr {

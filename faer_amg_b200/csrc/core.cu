@@ -167,7 +167,7 @@ famg_status csr_finalize_plan(famg_csr *a) {
     // stages <= ~2048 non-zeros (spmv.cu).  Row-length statistics pick scalar-, sub-warp- or
     // warp-per-row.
     int tpr = 1;
-    while (tpr < 32 && a->avg_row_nnz > 8.0 * tpr) tpr <<= 1;
+    while (tpr < 32 && a->avg_row_nnz > 7.5 * tpr) tpr <<= 1;
     a->tpr = tpr;
     return FAMG_OK;
 }
@@ -241,6 +241,8 @@ famg_status famg_ctx_create(int device, famg_ctx **out) {
     famg_ctx *ctx = new famg_ctx();
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
+    if (const char *v = getenv("FAMG_SPMV_VARIANT")) ctx->spmv_variant = atoi(v) == 1 ? 1 : 2;
+    if (const char *v = getenv("FAMG_TMA_MIN_ROWS")) ctx->tma_min_rows = std::max(atoi(v), 1);
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaMalloc((void **)&ctx->d_scalars, 64 * sizeof(double)));
@@ -285,6 +287,19 @@ famg_status famg_ctx_info(famg_ctx *ctx, int *num_sms, int64_t *mem_free, int64_
         cudaDeviceProp prop;
         CUDA_TRY(cudaGetDeviceProperties(&prop, ctx->device));
         snprintf(name, name_len, "%s", prop.name);
+    }
+    return FAMG_OK;
+}
+
+famg_status famg_ctx_set_option(famg_ctx *ctx, const char *key, int64_t value) {
+    if (!ctx || !key) FAMG_FAIL(FAMG_ERR_INVALID, "null argument");
+    if (!strcmp(key, "spmv_variant")) {
+        if (value != 1 && value != 2) FAMG_FAIL(FAMG_ERR_INVALID, "spmv_variant must be 1 or 2");
+        ctx->spmv_variant = (int)value;
+    } else if (!strcmp(key, "tma_min_rows")) {
+        ctx->tma_min_rows = (int)std::max<int64_t>(value, 1);
+    } else {
+        FAMG_FAIL(FAMG_ERR_INVALID, "unknown option '%s'", key);
     }
     return FAMG_OK;
 }

@@ -53,6 +53,41 @@ struct SpmvKernelParams {
     double *dot_partials;
 };
 
+
+// Epilogue operands are loaded *before* the row's gathers (and before the stage wait) so their
+// latency overlaps the streaming of A instead of being exposed once per chunk.
+struct EpiOps { double b, d, x, y; };
+
+template <int EPI, bool DOT>
+__device__ __forceinline__ EpiOps epi_prefetch(const SpmvKernelParams &p, const double *__restrict__ xc, const double *yc, int c,
+                                               int row, bool on) {
+    EpiOps o{0.0, 0.0, 0.0, 0.0};
+    if (on) {
+        if (EPI == EPI_RESID || EPI == EPI_SMOOTH) o.b = p.b[(long long)c * p.ldb + row];
+        if (EPI == EPI_SMOOTH || EPI == EPI_SI) o.d = p.d[row];
+        if (EPI == EPI_SMOOTH || EPI == EPI_SI || DOT) o.x = xc[row];
+        if (EPI == EPI_ADD) o.y = yc[row];
+    }
+    return o;
+}
+
+template <int EPI, bool DOT>
+__device__ __forceinline__ void epi_store(double *yc, int row, double s, const EpiOps &o, double &dot_acc) {
+    if (EPI == EPI_SPMV) {
+        yc[row] = s;
+    } else if (EPI == EPI_RESID) {
+        yc[row] = o.b - s;                       // multigrid.rs:341-342
+    } else if (EPI == EPI_SMOOTH) {
+        const double r = o.b - s;                // x' = x + d .* (b - A x)   (multigrid.rs:419-422)
+        yc[row] = o.x + o.d * r;
+    } else if (EPI == EPI_ADD) {
+        yc[row] = o.y + s;                       // multigrid.rs:349-350
+    } else {
+        yc[row] = o.x + o.d * (o.x - s);         // EPI_SI: x' = x + d .* (x - A x)   (smoothers.rs:153-156, literal)
+    }
+    if (DOT) dot_acc += o.x * s;
+}
+
 template <int TPR, int EPI, bool DOT>
 __global__ void __launch_bounds__(SPMV_THREADS, 4) spmv_kernel(const SpmvKernelParams p) {
     constexpr int ROWS = SPMV_THREADS / TPR;
@@ -68,6 +103,14 @@ __global__ void __launch_bounds__(SPMV_THREADS, 4) spmv_kernel(const SpmvKernelP
     const int q0a = q0 & ~3;  // 16-byte aligned start for int4 / 32-byte for double2 pairs
     const int cnt = q1 - q0a;
     const bool staged = cnt <= SPMV_CAP;
+
+    const int g = tid / TPR;
+    const int lane = tid % TPR;
+    const int row = r0 + g;
+    const bool active = row < r1;
+    int a = 0, e = 0;
+    if (active) { a = __ldg(p.row_ptr + row); e = __ldg(p.row_ptr + row + 1); }
+    EpiOps ops = epi_prefetch<EPI, DOT>(p, p.x, p.y, 0, row, active && lane == 0);
 
     if (staged) {
         const int n4 = (cnt + 3) >> 2;
@@ -93,16 +136,11 @@ __global__ void __launch_bounds__(SPMV_THREADS, 4) spmv_kernel(const SpmvKernelP
     }
     __syncthreads();
 
-    const int g = tid / TPR;
-    const int lane = tid % TPR;
-    const int row = r0 + g;
-    const bool active = row < r1;
-    int a = 0, e = 0;
-    if (active) { a = __ldg(p.row_ptr + row); e = __ldg(p.row_ptr + row + 1); }
-
     double dot_acc = 0.0;
     for (int c = 0; c < p.k; ++c) {
         const double *__restrict__ xc = p.x + (long long)c * p.ldx;
+        double *yc = p.y + (long long)c * p.ldy;
+        if (c > 0) ops = epi_prefetch<EPI, DOT>(p, xc, yc, c, row, active && lane == 0);
         double s = 0.0;
         if (staged) {
             for (int q = a - q0a + lane; q < e - q0a; q += TPR * SPMV_U) {
@@ -133,24 +171,7 @@ __global__ void __launch_bounds__(SPMV_THREADS, 4) spmv_kernel(const SpmvKernelP
 #pragma unroll
             for (int o = TPR >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         }
-        if (active && lane == 0) {
-            double *yc = p.y + (long long)c * p.ldy;
-            if (EPI == EPI_SPMV) {
-                yc[row] = s;
-            } else if (EPI == EPI_RESID) {
-                yc[row] = p.b[(long long)c * p.ldb + row] - s;
-            } else if (EPI == EPI_SMOOTH) {
-                // x' = x + d .* (b - A x)   (multigrid.rs:419-422)
-                const double r = p.b[(long long)c * p.ldb + row] - s;
-                yc[row] = xc[row] + p.d[row] * r;
-            } else if (EPI == EPI_ADD) {
-                yc[row] = yc[row] + s;
-            } else {  // EPI_SI: x' = x + d .* (x - A x)   (smoothers.rs:153-156, literal)
-                const double xr = xc[row];
-                yc[row] = xr + p.d[row] * (xr - s);
-            }
-            if (DOT) dot_acc += xc[row] * s;
-        }
+        if (active && lane == 0) epi_store<EPI, DOT>(yc, row, s, ops, dot_acc);
     }
     if (DOT) {
         // deterministic CTA reduction of x_i * (A x)_i -> one partial per CTA
@@ -168,20 +189,209 @@ __global__ void __launch_bounds__(SPMV_THREADS, 4) spmv_kernel(const SpmvKernelP
     }
 }
 
-template <int TPR, int EPI>
-static void launch_tpr_epi(const SpmvKernelParams &kp, bool dot, int grid, cudaStream_t st) {
-    if (dot) spmv_kernel<TPR, EPI, true><<<grid, SPMV_THREADS, 0, st>>>(kp);
-    else spmv_kernel<TPR, EPI, false><<<grid, SPMV_THREADS, 0, st>>>(kp);
+// ===================================================================================================
+// Variant 2: persistent, warp-specialised, TMA-fed pipeline.
+//   * grid = (resident CTAs per SM) x (SM count); every CTA walks chunks c = blockIdx.x, +gridDim.x, ...
+//   * warp 8 is the producer: one elected lane turns each chunk into two bulk async copies
+//     (cp.async.bulk global -> shared, SASS UBLKCP) of the chunk's col[] and val[] slices into a
+//     TMA_STAGES-deep ring, completion signalled on an mbarrier with expect_tx;
+//   * warps 0..7 are consumers: wait for the stage's "full" barrier, walk their rows out of shared
+//     memory exactly as variant 1 (same summation order => same bits), then release the stage on
+//     its "empty" barrier.  No __syncthreads in the steady state, no register staging of A.
+// ===================================================================================================
+constexpr int TMA_STAGES = 3;
+constexpr int TMA_CAP = 2048;  // non-zeros per stage: 16 KB values + 8 KB indices
+constexpr int TMA_CONSUMERS = 256;
+constexpr int TMA_THREADS = TMA_CONSUMERS + 32;
+constexpr int TMA_SMEM = TMA_STAGES * TMA_CAP * 12 + 2 * TMA_STAGES * 8 + 8 * 8;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int TPR, int EPI, bool DOT>
+__global__ void __launch_bounds__(TMA_THREADS, 3) spmv_tma_kernel(const SpmvKernelParams p, const int nchunks) {
+    constexpr int ROWS = TMA_CONSUMERS / TPR;
+    extern __shared__ __align__(128) unsigned char smem[];
+    double *s_val = reinterpret_cast<double *>(smem);
+    int *s_col = reinterpret_cast<int *>(smem + (size_t)TMA_STAGES * TMA_CAP * 8);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)TMA_STAGES * TMA_CAP * 12);
+    uint64_t *empty = full + TMA_STAGES;
+    double *s_red = reinterpret_cast<double *>(empty + TMA_STAGES);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < TMA_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], TMA_CONSUMERS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == TMA_CONSUMERS / 32) {
+        // ------------------------------------------------------------------ producer
+        if ((tid & 31) == 0) {
+            int stage = 0, uses = 0;
+            uint32_t ephase = 0;
+            for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
+                const int r0 = p.row_begin + c * ROWS;
+                const int r1 = min(r0 + ROWS, p.row_end);
+                const int q0a = __ldg(p.row_ptr + r0) & ~3;
+                const int cnt = __ldg(p.row_ptr + r1) - q0a;
+                if (cnt <= 0 || cnt > TMA_CAP) continue;  // consumers take the direct path
+                if (uses >= TMA_STAGES) { mbar_wait(&empty[stage], (ephase >> stage) & 1u); ephase ^= 1u << stage; }
+                const uint32_t n4 = (uint32_t)(cnt + 3) >> 2;
+                mbar_expect_tx(&full[stage], n4 * 48u);
+                bulk_g2s(s_col + stage * TMA_CAP, p.col + q0a, n4 * 16u, &full[stage]);
+                bulk_g2s(s_val + stage * TMA_CAP, p.val + q0a, n4 * 32u, &full[stage]);
+                ++uses;
+                stage = stage + 1 == TMA_STAGES ? 0 : stage + 1;
+            }
+        }
+        return;
+    }
+    // ---------------------------------------------------------------------- consumers
+    const int g = tid / TPR;
+    const int lane = tid % TPR;
+    int stage = 0;
+    uint32_t fphase = 0;
+    double dot_acc = 0.0;
+    int c = blockIdx.x;
+    int q0 = 0, q1 = 0, a = 0, e = 0;
+    if (c < nchunks) {
+        const int r0 = p.row_begin + c * ROWS, r1 = min(r0 + ROWS, p.row_end);
+        q0 = __ldg(p.row_ptr + r0); q1 = __ldg(p.row_ptr + r1);
+        if (r0 + g < r1) { a = __ldg(p.row_ptr + r0 + g); e = __ldg(p.row_ptr + r0 + g + 1); }
+    }
+    while (c < nchunks) {
+        const int r0 = p.row_begin + c * ROWS;
+        const int r1 = min(r0 + ROWS, p.row_end);
+        const int row = r0 + g;
+        const bool active = row < r1;
+        // prefetch the next chunk's row pointers (consumed one iteration later)
+        const int cn = c + gridDim.x;
+        int nq0 = 0, nq1 = 0, na = 0, ne = 0;
+        if (cn < nchunks) {
+            const int s0 = p.row_begin + cn * ROWS, s1 = min(s0 + ROWS, p.row_end);
+            nq0 = __ldg(p.row_ptr + s0); nq1 = __ldg(p.row_ptr + s1);
+            if (s0 + g < s1) { na = __ldg(p.row_ptr + s0 + g); ne = __ldg(p.row_ptr + s0 + g + 1); }
+        }
+        const int q0a = q0 & ~3;
+        const int cnt = q1 - q0a;
+        const bool staged = cnt > 0 && cnt <= TMA_CAP;
+        const double *sv = s_val + stage * TMA_CAP;
+        const int *sc = s_col + stage * TMA_CAP;
+        for (int col = 0; col < p.k; ++col) {
+            const double *__restrict__ xc = p.x + (long long)col * p.ldx;
+            double *yc = p.y + (long long)col * p.ldy;
+            const EpiOps ops = epi_prefetch<EPI, DOT>(p, xc, yc, col, row, active && lane == 0);
+            if (col == 0 && staged) { mbar_wait(&full[stage], (fphase >> stage) & 1u); fphase ^= 1u << stage; }
+            double s = 0.0;
+            if (staged) {
+                for (int q = a - q0a + lane; q < e - q0a; q += TPR * SPMV_U) {
+                    double pr[SPMV_U];
+#pragma unroll
+                    for (int u = 0; u < SPMV_U; ++u) {
+                        const int qq = q + u * TPR;
+                        pr[u] = 0.0;
+                        if (qq < e - q0a) pr[u] = sv[qq] * __ldg(xc + sc[qq]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < SPMV_U; ++u) s += pr[u];
+                }
+            } else {
+                for (int q = a + lane; q < e; q += TPR * SPMV_U) {
+                    double pr[SPMV_U];
+#pragma unroll
+                    for (int u = 0; u < SPMV_U; ++u) {
+                        const int qq = q + u * TPR;
+                        pr[u] = 0.0;
+                        if (qq < e) pr[u] = __ldg(p.val + qq) * __ldg(xc + __ldg(p.col + qq));
+                    }
+#pragma unroll
+                    for (int u = 0; u < SPMV_U; ++u) s += pr[u];
+                }
+            }
+            if (TPR > 1) {
+#pragma unroll
+                for (int o = TPR >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            }
+            if (active && lane == 0) epi_store<EPI, DOT>(yc, row, s, ops, dot_acc);
+        }
+        if (staged) {
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&empty[stage]);
+            stage = stage + 1 == TMA_STAGES ? 0 : stage + 1;
+        }
+        c = cn; q0 = nq0; q1 = nq1; a = na; e = ne;
+    }
+    if (DOT) {
+        double v = dot_acc;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((tid & 31) == 0) s_red[warp] = v;
+        asm volatile("bar.sync 1, %0;" ::"n"(TMA_CONSUMERS) : "memory");
+        if (tid == 0) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < TMA_CONSUMERS / 32; ++w) t += s_red[w];
+            p.dot_partials[blockIdx.x] = t;
+        }
+    }
+}
+
+template <int TPR, int EPI, bool DOT>
+static famg_status launch_one(const SpmvKernelParams &kp, int variant, int nrows, int num_sms, cudaStream_t st, int *grid_out) {
+    if (variant == 2) {
+        const int nchunks = (int)ceil_div(nrows, TMA_CONSUMERS / TPR);
+        const int grid = std::min(nchunks, 3 * num_sms);
+        static bool configured = false;  // per template instance
+        if (!configured) {
+            CUDA_TRY(cudaFuncSetAttribute(spmv_tma_kernel<TPR, EPI, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM));
+            configured = true;
+        }
+        spmv_tma_kernel<TPR, EPI, DOT><<<grid, TMA_THREADS, TMA_SMEM, st>>>(kp, nchunks);
+        *grid_out = grid;
+    } else {
+        const int grid = (int)ceil_div(nrows, SPMV_THREADS / TPR);
+        spmv_kernel<TPR, EPI, DOT><<<grid, SPMV_THREADS, 0, st>>>(kp);
+        *grid_out = grid;
+    }
+    return FAMG_OK;
 }
 
 template <int TPR>
-static void launch_tpr(const SpmvKernelParams &kp, int epi, bool dot, int grid, cudaStream_t st) {
+static famg_status launch_tpr(const SpmvKernelParams &kp, int epi, bool dot, int variant, int nrows, int sms, cudaStream_t st, int *grid) {
     switch (epi) {
-        case EPI_SPMV: launch_tpr_epi<TPR, EPI_SPMV>(kp, dot, grid, st); break;
-        case EPI_RESID: launch_tpr_epi<TPR, EPI_RESID>(kp, false, grid, st); break;
-        case EPI_SMOOTH: launch_tpr_epi<TPR, EPI_SMOOTH>(kp, false, grid, st); break;
-        case EPI_ADD: launch_tpr_epi<TPR, EPI_ADD>(kp, false, grid, st); break;
-        default: launch_tpr_epi<TPR, EPI_SI>(kp, false, grid, st); break;
+        case EPI_SPMV:
+            return dot ? launch_one<TPR, EPI_SPMV, true>(kp, variant, nrows, sms, st, grid)
+                       : launch_one<TPR, EPI_SPMV, false>(kp, variant, nrows, sms, st, grid);
+        case EPI_RESID: return launch_one<TPR, EPI_RESID, false>(kp, variant, nrows, sms, st, grid);
+        case EPI_SMOOTH: return launch_one<TPR, EPI_SMOOTH, false>(kp, variant, nrows, sms, st, grid);
+        case EPI_ADD: return launch_one<TPR, EPI_ADD, false>(kp, variant, nrows, sms, st, grid);
+        default: return launch_one<TPR, EPI_SI, false>(kp, variant, nrows, sms, st, grid);
     }
 }
 
@@ -204,17 +414,21 @@ famg_status spmv_launch(const SpmvArgs &args, int *num_ctas) {
     kp.b = args.b; kp.ldb = args.ldb; kp.d = args.d; kp.k = args.k;
     kp.dot_partials = args.dot_partials;
     const int tpr = a->tpr;
-    const int rows_per_cta = SPMV_THREADS / tpr;
-    const int grid = (int)ceil_div(row_end - row_begin, rows_per_cta);
+    const int nrows = row_end - row_begin;
     const bool dot = args.dot_partials != nullptr;
+    // small operators (coarse levels) do not fill a persistent grid: keep the one-chunk-per-CTA kernel
+    const int variant = (ctx->spmv_variant == 2 && nrows >= ctx->tma_min_rows) ? 2 : 1;
+    int grid = 0;
+    famg_status stt;
     switch (tpr) {
-        case 1: launch_tpr<1>(kp, args.epi, dot, grid, st); break;
-        case 2: launch_tpr<2>(kp, args.epi, dot, grid, st); break;
-        case 4: launch_tpr<4>(kp, args.epi, dot, grid, st); break;
-        case 8: launch_tpr<8>(kp, args.epi, dot, grid, st); break;
-        case 16: launch_tpr<16>(kp, args.epi, dot, grid, st); break;
-        default: launch_tpr<32>(kp, args.epi, dot, grid, st); break;
+        case 1: stt = launch_tpr<1>(kp, args.epi, dot, variant, nrows, ctx->num_sms, st, &grid); break;
+        case 2: stt = launch_tpr<2>(kp, args.epi, dot, variant, nrows, ctx->num_sms, st, &grid); break;
+        case 4: stt = launch_tpr<4>(kp, args.epi, dot, variant, nrows, ctx->num_sms, st, &grid); break;
+        case 8: stt = launch_tpr<8>(kp, args.epi, dot, variant, nrows, ctx->num_sms, st, &grid); break;
+        case 16: stt = launch_tpr<16>(kp, args.epi, dot, variant, nrows, ctx->num_sms, st, &grid); break;
+        default: stt = launch_tpr<32>(kp, args.epi, dot, variant, nrows, ctx->num_sms, st, &grid); break;
     }
+    FAMG_TRY(stt);
     count_launch(ctx);
     KERNEL_CHECK();
     if (num_ctas) *num_ctas = grid;

@@ -232,6 +232,9 @@ famg_status famg_dist_spmv_dev(famg_dist_mg *d, famg_vec *y_local, const famg_ve
 famg_status famg_dist_mg_apply_dev(famg_dist_mg *d, famg_vec *out_local, const famg_vec *rhs_local);
 
 /* ---- instrumentation ---------------------------------------------------------------------- */
+/* tuning knobs for A/B measurements: "spmv_variant" (1 = one staged chunk per CTA, 2 = persistent
+ * TMA-fed pipeline), "tma_min_rows" (smallest operator the persistent kernel is used for) */
+famg_status famg_ctx_set_option(famg_ctx *ctx, const char *key, int64_t value);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 famg_status famg_ctx_launch_count(const famg_ctx *ctx, int64_t *count);
 /* time `reps` back-to-back launches of one fused kernel class with CUDA events on the context

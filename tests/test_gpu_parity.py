@@ -22,6 +22,17 @@ def F():
     return F
 
 
+@pytest.fixture(params=[1, 2], ids=["staged-cta", "tma-pipeline"])
+def variant(request, ctx):
+    """Run a test under both SpMV kernel variants (the persistent TMA pipeline is normally reserved
+    for operators with >= 131072 rows)."""
+    ctx.set_option("spmv_variant", request.param)
+    ctx.set_option("tma_min_rows", 1)
+    yield request.param
+    ctx.set_option("spmv_variant", 2)
+    ctx.set_option("tma_min_rows", 1 << 17)
+
+
 # ------------------------------------------------------------------ containers / generators
 def test_gallery_bit_exact(ctx, F):
     for dims in [(8, 8, 8), (7, 5, 3), (33, 2, 1)]:
@@ -61,7 +72,7 @@ def _case(name, arg):
 
 @pytest.mark.parametrize("name,arg", CASES)
 @pytest.mark.parametrize("k", [1, 3])
-def test_spmm_matches_oracle(ctx, F, name, arg, k):
+def test_spmm_matches_oracle(ctx, F, variant, name, arg, k):
     o = _case(name, arg)
     d = to_dev(ctx, o)
     x = np.random.default_rng(1).standard_normal((o.ncols, k))
@@ -73,7 +84,7 @@ def test_spmm_matches_oracle(ctx, F, name, arg, k):
     assert_rel(got, par, spmv_bound(o, x))
 
 
-def test_spmm_irregular_rows_and_fallback_path(ctx, F):
+def test_spmm_irregular_rows_and_fallback_path(ctx, F, variant):
     """Empty rows, ragged rows, rows longer than one CTA's staging buffer (direct path), rectangular."""
     rng = np.random.default_rng(2)
     lens = rng.integers(0, 9, 700)
@@ -92,7 +103,7 @@ def test_spmm_irregular_rows_and_fallback_path(ctx, F):
     assert np.array_equal(empty.apply(np.ones(10)), np.zeros((10, 1)))
 
 
-def test_residual_add_and_fused_smoother(ctx, F):
+def test_residual_add_and_fused_smoother(ctx, F, variant):
     o = O.gen_g7(20, 18, 16)
     d = to_dev(ctx, o)
     rng = np.random.default_rng(3)
@@ -113,7 +124,7 @@ def test_residual_add_and_fused_smoother(ctx, F):
                 assert np.array_equal(X2.to_host(), O.smooth_diag(o, diag, x, b, iters))  # multigrid.rs:407-424
 
 
-def test_fused_smoother_27pt_within_tolerance(ctx, F):
+def test_fused_smoother_27pt_within_tolerance(ctx, F, variant):
     o = O.gen_g27(10, 9, 8)
     d = to_dev(ctx, o)
     rng = np.random.default_rng(4)
@@ -132,7 +143,7 @@ def test_missing_diagonal_is_an_error(ctx, F):
     assert e.value.status == F._ffi.ERR_NUMERIC
 
 
-def test_stationary_iteration_literal(ctx, F):
+def test_stationary_iteration_literal(ctx, F, variant):
     o = O.gen_g7(9, 8, 7)
     d = to_dev(ctx, o)
     nn = np.random.default_rng(5).standard_normal((o.nrows, 3))
@@ -251,7 +262,7 @@ def test_hierarchy_structure_bit_exact(ctx, F):
 
 
 @pytest.mark.parametrize("mu,nu,smoother", [(1, 1, "l1"), (1, 2, "jacobi"), (2, 1, "l2"), (2, 2, "l1")])
-def test_multigrid_apply_matches_oracle(ctx, F, mu, nu, smoother):
+def test_multigrid_apply_matches_oracle(ctx, F, variant, mu, nu, smoother):
     o, oh, omg, a, h, mg = _build_both(ctx, F, O.gen_g7, F.gallery.poisson7, (16, 12, 8), smoother, coarsest_dim=60, mu=mu, nu=nu)
     assert mg.levels() == oh.levels >= 3
     rhs = np.random.default_rng(11).standard_normal((o.nrows, 3))
@@ -316,7 +327,7 @@ def test_simple_geometric_example_on_gpu(ctx, F):
 
 
 @pytest.mark.parametrize("case", ["g7_32_l1", "g7_48x32x16_jacobi", "g27_24_l1"])
-def test_pcg_amg_iteration_counts(ctx, F, case):
+def test_pcg_amg_iteration_counts(ctx, F, variant, case):
     g = GOLD["amg"][case]
     dims = tuple(g["dims"])
     gen = (O.gen_g27, F.gallery.diffusion27) if case.startswith("g27") else (O.gen_g7, F.gallery.poisson7)
