@@ -70,6 +70,12 @@ struct famg_ctx {
     // for A/B measurements.
     int spmv_variant = 2;
     int tma_min_rows = 1 << 17;
+    // exact-size free lists for multivector storage: the host-pointer entry points (LinOp::apply,
+    // famg_pcg_solve) stage through device vectors on every call, and cudaMalloc/cudaFree cost
+    // milliseconds each; work on one context is stream-ordered, so a freed block can be reused
+    // immediately by later work on the same stream.
+    std::multimap<size_t, void *> pool;
+    size_t pool_bytes = 0;
 };
 
 struct famg_csr {
@@ -90,6 +96,7 @@ struct famg_vec {
     int64_t nrows = 0, ncols = 0, ld = 0;
     double *p = nullptr;
     bool owns = true;
+    size_t bytes = 0;  // size of the pooled allocation behind p
 };
 
 enum SmootherKind { SM_DIAG = 0, SM_DENSE_INV = 1, SM_SPARSE_INV = 2 };
@@ -128,6 +135,9 @@ void smoother_release(famg_smoother *s);
 famg_status vec_wrap(famg_ctx *ctx, double *p, int64_t nrows, int64_t ncols, int64_t ld, famg_vec *out);
 
 famg_status ensure_partials(famg_ctx *ctx, int64_t count);
+famg_status pool_alloc(famg_ctx *ctx, size_t bytes, void **p);
+void pool_free(famg_ctx *ctx, void *p, size_t bytes);
+void pool_trim(famg_ctx *ctx);
 
 inline void count_launch(famg_ctx *ctx, int n = 1) { ctx->launches.fetch_add(n, std::memory_order_relaxed); }
 

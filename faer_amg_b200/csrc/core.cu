@@ -209,6 +209,53 @@ famg_status ensure_partials(famg_ctx *ctx, int64_t count) {
     return FAMG_OK;
 }
 
+famg_status pool_alloc(famg_ctx *ctx, size_t bytes, void **p) {
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        auto it = ctx->pool.find(bytes);
+        if (it != ctx->pool.end()) {
+            *p = it->second;
+            ctx->pool.erase(it);
+            ctx->pool_bytes -= bytes;
+            return FAMG_OK;
+        }
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e == cudaErrorMemoryAllocation) {  // give cached blocks back and retry once
+        cudaGetLastError();
+        pool_trim(ctx);
+        e = cudaMalloc(p, bytes);
+    }
+    if (e != cudaSuccess) {
+        *p = nullptr;
+        set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        return e == cudaErrorMemoryAllocation ? FAMG_ERR_ALLOC : FAMG_ERR_CUDA;
+    }
+    return FAMG_OK;
+}
+
+void pool_free(famg_ctx *ctx, void *p, size_t bytes) {
+    if (!p) return;
+    constexpr size_t POOL_CAP = (size_t)8 << 30;
+    std::unique_lock<std::mutex> lk(ctx->mu);
+    if (ctx->pool_bytes + bytes > POOL_CAP) {
+        lk.unlock();
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(p);
+        return;
+    }
+    ctx->pool.emplace(bytes, p);
+    ctx->pool_bytes += bytes;
+}
+
+void pool_trim(famg_ctx *ctx) {
+    cudaStreamSynchronize(ctx->stream);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    for (auto &kv : ctx->pool) cudaFree(kv.second);
+    ctx->pool.clear();
+    ctx->pool_bytes = 0;
+}
+
 famg_status vec_wrap(famg_ctx *ctx, double *p, int64_t nrows, int64_t ncols, int64_t ld, famg_vec *out) {
     out->ctx = ctx; out->p = p; out->nrows = nrows; out->ncols = ncols; out->ld = ld; out->owns = false;
     return FAMG_OK;
@@ -257,6 +304,7 @@ famg_status famg_ctx_destroy(famg_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->comm_stream);
+    pool_trim(ctx);
     cudaFree(ctx->d_scalars); cudaFreeHost(ctx->h_scalars); cudaFree(ctx->d_partials); cudaFree(ctx->pcg_ws);
     cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->comm_stream);
     delete ctx;
@@ -444,16 +492,17 @@ famg_status famg_vec_create(famg_ctx *ctx, int64_t nrows, int64_t ncols, famg_ve
     famg_vec *v = new famg_vec();
     v->ctx = ctx; v->nrows = nrows; v->ncols = ncols;
     v->ld = (nrows + 1) & ~(int64_t)1;  // keep columns 16-byte aligned
-    famg_status st = dev_alloc(&v->p, v->ld * std::max<int64_t>(ncols, 1) + 2);
+    v->bytes = sizeof(double) * (size_t)(v->ld * std::max<int64_t>(ncols, 1) + 2);
+    famg_status st = pool_alloc(ctx, v->bytes, (void **)&v->p);
     if (st != FAMG_OK) { delete v; return st; }
-    cudaMemsetAsync(v->p, 0, sizeof(double) * (size_t)(v->ld * std::max<int64_t>(ncols, 1) + 2), ctx->stream);
+    cudaMemsetAsync(v->p, 0, v->bytes, ctx->stream);
     *out = v;
     return FAMG_OK;
 }
 famg_status famg_vec_destroy(famg_vec *v) {
     if (!v) return FAMG_OK;
     cudaSetDevice(v->ctx->device);
-    if (v->owns) { cudaStreamSynchronize(v->ctx->stream); cudaFree(v->p); }
+    if (v->owns) pool_free(v->ctx, v->p, v->bytes);  // stream-ordered reuse, no synchronisation
     delete v;
     return FAMG_OK;
 }

@@ -63,10 +63,12 @@ __device__ __forceinline__ EpiOps epi_prefetch(const SpmvKernelParams &p, const 
                                                int row, bool on) {
     EpiOps o{0.0, 0.0, 0.0, 0.0};
     if (on) {
-        if (EPI == EPI_RESID || EPI == EPI_SMOOTH) o.b = p.b[(long long)c * p.ldb + row];
-        if (EPI == EPI_SMOOTH || EPI == EPI_SI) o.d = p.d[row];
+        // b, d and y are touched once per sweep: streaming (evict-first) so they do not push the
+        // x lines that the gathers reuse out of L1/L2
+        if (EPI == EPI_RESID || EPI == EPI_SMOOTH) o.b = __ldcs(p.b + (long long)c * p.ldb + row);
+        if (EPI == EPI_SMOOTH || EPI == EPI_SI) o.d = __ldcs(p.d + row);
         if (EPI == EPI_SMOOTH || EPI == EPI_SI || DOT) o.x = xc[row];
-        if (EPI == EPI_ADD) o.y = yc[row];
+        if (EPI == EPI_ADD) o.y = __ldcs(yc + row);
     }
     return o;
 }
