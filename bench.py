@@ -150,7 +150,8 @@ def run_reference(args):
 
 
 def workload_config(args):
-    return {"workload": f"3D 7-point Poisson {args.n}^3 f64, PCG + smoothed-aggregation AMG V(1,1), L1-Jacobi smoother, "
+    name = "7-point Poisson" if args.stencil == 7 else "27-point anisotropic diffusion (eps_z=1e-2)"
+    return {"workload": f"3D {name} {args.n}^3 f64, PCG + smoothed-aggregation AMG V(1,1), L1-Jacobi smoother, "
                         f"rel_tol {REL_TOL:g}, b=1, zero guess (BASELINE configs[3]; configs[1] = 128^3 is a parity-test case)",
             "grid": [args.n] * 3, "rows": args.n ** 3, "rel_tol": REL_TOL, "l2": "inputs larger than L2 (no flush needed)",
             "partition": f"{args.gpus} z-slab(s)"}
@@ -178,13 +179,13 @@ def run_ours(args):
 
     # ---- setup (untimed): operator + hierarchy on the device
     t0 = time.perf_counter()
-    a = F.gallery.poisson7(ctx, n)
+    a = F.gallery.poisson7(ctx, n) if args.stencil == 7 else F.gallery.diffusion27(ctx, n)
     ctx.sync()
     t_gen = time.perf_counter() - t0
     rows = a.nrows
     nn = np.full((rows, 1), 1.0 / np.sqrt(rows))
     t0 = time.perf_counter()
-    gp = F.GeometricPartitioner((n, n, n))
+    gp = F.GeometricPartitioner((n, n, n), tuple(int(v) for v in args.block.split(",")))
     h = F.HierarchyConfig(1000, F.AggregationConfig(1, 1, gp)).build(F.SparseMatOp(a), nn)
     mg = F.MultigridConfig(smoother="l1").build(h)
     ctx.sync()
@@ -322,6 +323,8 @@ def main():
     ap.add_argument("--sample-iters", type=int, default=2, help="PCG iterations per CPU sample")
     ap.add_argument("--replicate-below", type=int, default=32768, help="rows per rank under which a level is replicated")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--stencil", type=int, default=7, choices=[7, 27], help="7-point Poisson (headline) or 27-point anisotropic diffusion")
+    ap.add_argument("--block", default="2,2,2", help="geometric aggregate box")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
