@@ -58,3 +58,18 @@ def test_thin_q_host_helper():
     assert np.allclose(q.T @ q, np.eye(4), atol=1e-14)
     assert np.all(np.diag(q.T @ m) > 0)
     assert np.array_equal(q, O.thin_q(m))  # same algorithm, same bits as the oracle
+
+
+def test_cpp_mirror_links_and_fails_loudly_without_gpu():
+    """include/famg.hpp (the C++ host mirror of the crate API) compiles, links against libfamg.so and,
+    with no GPU, reports FAMG_ERR_CUDA instead of computing anything."""
+    import subprocess
+    import torch
+    exe = os.path.join(ROOT, "tests", "cpp", "mirror_smoke")
+    if not os.path.exists(exe):
+        pytest.skip("run __graft_entry__.build() first")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    if torch.cuda.is_available():
+        assert out.returncode == 0 and "mirror ok" in out.stdout, out.stdout + out.stderr
+    else:
+        assert out.returncode == 3 and "no CPU fallback" in out.stdout

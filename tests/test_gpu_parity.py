@@ -400,3 +400,13 @@ def test_full_size_properties_128(ctx, F):
         assert abs(np.linalg.norm(x) - g["iters"]["1e-08"]["x_norm"]) <= 1e-6 * g["iters"]["1e-08"]["x_norm"]
     else:
         assert 10 <= info.iter_count <= 25
+
+
+def test_cpp_mirror_on_gpu():
+    """include/famg.hpp end to end (Galerkin product, two-level multigrid, PCG) through the C ABI from C++."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "cpp", "mirror_smoke")
+    if not os.path.exists(exe):
+        pytest.skip("run __graft_entry__.build() first")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "mirror ok" in out.stdout, out.stdout + out.stderr
