@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfamg.so")
+LIB_PATH = os.environ.get("FAMG_LIB", os.path.join(_HERE, "libfamg.so"))  # FAMG_LIB: A/B builds of the same ABI
 
 u64p = C.POINTER(C.c_uint64)
 i64p = C.POINTER(C.c_int64)

@@ -163,11 +163,14 @@ famg_status csr_finalize_plan(famg_csr *a) {
     cudaFree(d_max);
     if (e != cudaSuccess) FAMG_FAIL(FAMG_ERR_CUDA, "csr plan failed: %s", cudaGetErrorString(e));
     a->max_row_nnz = h_max;
-    // threads-per-row: each thread should own <= ~8 staged entries so one CTA of 256 threads
-    // stages <= ~2048 non-zeros (spmv.cu).  Row-length statistics pick scalar-, sub-warp- or
+    // threads-per-row: each thread should own <= ~9 staged entries so one chunk of 256/tpr rows
+    // fits a pipeline stage of 2304 non-zeros (spmv.cu).  Row-length statistics pick scalar-, sub-warp- or
     // warp-per-row.
     int tpr = 1;
-    while (tpr < 32 && a->avg_row_nnz > 7.5 * tpr) tpr <<= 1;
+#ifndef FAMG_TPR_FILL
+#define FAMG_TPR_FILL 8.9
+#endif
+    while (tpr < 32 && a->avg_row_nnz > FAMG_TPR_FILL * tpr) tpr <<= 1;
     a->tpr = tpr;
     return FAMG_OK;
 }

@@ -202,6 +202,31 @@ famg_status famg_tentative_p(famg_ctx *ctx, int64_t n_fine, int64_t block_size, 
     std::vector<char> seen((size_t)(n_fine / block_size), 0);
     for (int64_t i = 0; i <= n_fine; ++i) rp[(size_t)i] = (int)(i * cand);
     std::vector<double> u, s, v;
+    if (k == 1 && cand == 1 && block_size == 1) {
+        // scalar problems with one near-null vector (every BASELINE config): the thin SVD of an
+        // m x 1 block is u = local/||local||, s = ||local||, v = 1 -- same operations, same bits as
+        // the general path, without the per-aggregate temporaries
+        for (int64_t g = 0; g < n_aggs; ++g) {
+            const uint64_t b0 = agg_ptr[g], b1 = agg_ptr[g + 1];
+            if (b1 <= b0) FAMG_FAIL(FAMG_ERR_INVALID, "Agg size of 0 cannot support near-null dimension of 1");
+            double nn = 0.0;
+            for (uint64_t t = b0; t < b1; ++t) {
+                const uint64_t node = agg_nodes[t];
+                if (node >= (uint64_t)n_fine || seen[(size_t)node]) FAMG_FAIL(FAMG_ERR_INVALID, "invalid partition");
+                seen[(size_t)node] = 1;
+                const double x = near_null[node];
+                nn += x * x;
+            }
+            const double sv = sqrt(nn);
+            coarse_nn[g] = sv * 1.0;
+            for (uint64_t t = b0; t < b1; ++t) {
+                const uint64_t node = agg_nodes[t];
+                ci[(size_t)node] = (int)g;
+                cv[(size_t)node] = sv > 0 ? near_null[node] / sv : 0.0;
+            }
+        }
+        return csr_from_host_i32(ctx, n_fine, nc, rp.data(), ci.data(), cv.data(), p);
+    }
     for (int64_t g = 0; g < n_aggs; ++g) {
         const int64_t na = (int64_t)(agg_ptr[g + 1] - agg_ptr[g]);
         const int64_t m = na * block_size;

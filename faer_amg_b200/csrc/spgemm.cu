@@ -8,23 +8,22 @@
 // contributions a_ik * b_kj taken in ascending k, each product and each add rounded separately.
 //
 // Algorithm: row-wise Gustavson with a hash table per output row.
-//   pass 0  ub_i = sum_k nnz(B_k)                 upper bound, bins rows into 4 size classes
-//   pass 1  insert the candidate columns into the row's table -> exact nnz(C_i); scan -> row_ptr
-//   pass 2  re-insert, compact, rank-sort the distinct columns (sorted pattern, bit-exact with a
-//           CPU Gustavson), then accumulate: k runs *sequentially* (ascending), the lanes of the
-//           row's thread group take the entries of B_k in parallel and locate their slot by binary
-//           search.  Within one k every j is unique, so there are no write conflicts and no atomics
-//           on values: the result is deterministic and has the reference's summation order.
-//   classes warp/128 and warp/1024 keep table + values in shared memory (one warp per row),
-//           cta/8192 uses 128 KB of shared memory (one CTA per row), rows above that use
-//           per-CTA tables in global memory (persistent CTAs).
+//   pass 0  ub_i = sum_k nnz(B_k)                 upper bound of the row length
+//   pass 1  rows binned by ub; insert the candidate columns into a key-only table sized from ub
+//           -> exact nnz(C_i); scan -> row_ptr
+//   pass 2  rows re-binned by their *exact* length (tables sized 2x the distinct count, not the
+//           often 10x larger ub); re-insert, compact, bitonic-sort the distinct columns (sorted
+//           pattern, bit-exact with a CPU Gustavson), then accumulate: k runs *sequentially*
+//           (ascending), the lanes of the row's thread group take the entries of B_k in parallel
+//           and locate their slot by binary search.  Within one k every j is unique, so there are
+//           no write conflicts and no atomics on values: the result is deterministic and has the
+//           reference's summation order.
+//   classes one warp per row (tables of 64..4096 slots in shared memory), one CTA per row (up to
+//           192 KB of shared memory), and per-CTA tables in global memory for anything larger.
 // The prolongator-smoothing epilogue  S_i <- -(w/a_ii) S_i + P_i  is fused into pass 2.
 #include "common.cuh"
 
 namespace famg {
-
-constexpr int SG_CLASSES = 4;
-constexpr int SG_H0 = 128, SG_H1 = 1024, SG_H2 = 8192;
 
 struct SgMat { const int *rp; const int *col; const double *val; };
 
@@ -42,7 +41,7 @@ __device__ __forceinline__ void group_sync() {
     if (GROUP == 32) __syncwarp(); else __syncthreads();
 }
 
-// Insert every candidate column of row i of A*B into `table` (size H = hmask+1, cleared here).
+// Insert every candidate column of row i of A*B into `table` (size hmask+1, cleared here).
 // Returns the number of distinct columns (same value on every lane of the group).
 template <int GROUP>
 __device__ int sg_row_insert(int i, int lane, const SgMat &a, const SgMat &b, int *table, int hmask, int *cnt) {
@@ -78,29 +77,42 @@ __device__ void sg_row_count(int i, int lane, const SgMat &a, const SgMat &b, in
     group_sync<GROUP>();
 }
 
-// Pass 2 for one row. table/list: H ints each, vals: H doubles.
+// Pass 2 for one row.  table: H = hmask+1 ints (8-byte aligned; reused as the H/2 f64 accumulators
+// once the keys have been compacted), list: H/2 ints.  The row has n <= H/2 distinct columns.
 template <int GROUP>
-__device__ void sg_row_fill(int i, int lane, const SgMat &a, const SgMat &b, int *table, int *list, double *vals, int hmask,
-                            int *cnt, const int *c_rp, int *c_col, double *c_val, const SgEpilogue &ep) {
+__device__ void sg_row_fill(int i, int lane, const SgMat &a, const SgMat &b, int *table, int *list, int hmask, int *cnt,
+                            const int *c_rp, int *c_col, double *c_val, const SgEpilogue &ep) {
     const int n = sg_row_insert<GROUP>(i, lane, a, b, table, hmask, cnt);
-    // compact the distinct columns
+    const int half = (hmask + 1) >> 1;
+    // compact the distinct columns, pad with INT_MAX up to the sort width (power of two >= n)
+    int width = 1;
+    while (width < n) width <<= 1;
     if (lane == 0) *cnt = 0;
+    for (int t = lane; t < width; t += GROUP) list[t] = 0x7fffffff;
     group_sync<GROUP>();
     for (int t = lane; t <= hmask; t += GROUP) {
         const int key = table[t];
         if (key != -1) list[atomicAdd(cnt, 1)] = key;
     }
     group_sync<GROUP>();
-    // rank sort (keys distinct) into table[0..n)
-    for (int e = lane; e < n; e += GROUP) {
-        const int key = list[e];
-        int rank = 0;
-        for (int f = 0; f < n; ++f) rank += list[f] < key;
-        table[rank] = key;
+    // bitonic sort of list[0..width) (keys distinct) -> sorted pattern, identical to a CPU Gustavson
+    for (int k = 2; k <= width; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = lane; t < width; t += GROUP) {
+                const int u = t ^ j;
+                if (u > t) {
+                    const int x = list[t], y = list[u];
+                    if ((x > y) == ((t & k) == 0)) { list[t] = y; list[u] = x; }
+                }
+            }
+            group_sync<GROUP>();
+        }
     }
+    double *vals = reinterpret_cast<double *>(table);  // keys are in `list` now
+    (void)half;
     for (int t = lane; t < n; t += GROUP) vals[t] = 0.0;
     group_sync<GROUP>();
-    // numeric: ascending k, lanes over the entries of B_k
+    // numeric: ascending k, lanes over the entries of B_k (each j unique within one k => no races)
     const int a0 = a.rp[i], a1 = a.rp[i + 1];
     for (int q = a0; q < a1; ++q) {
         const int k = a.col[q];
@@ -111,7 +123,7 @@ __device__ void sg_row_fill(int i, int lane, const SgMat &a, const SgMat &b, int
             int lo = 0, hi = n;
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
-                if (table[mid] < j) lo = mid + 1; else hi = mid;
+                if (list[mid] < j) lo = mid + 1; else hi = mid;
             }
             vals[lo] = vals[lo] + av * b.val[p];
         }
@@ -119,7 +131,7 @@ __device__ void sg_row_fill(int i, int lane, const SgMat &a, const SgMat &b, int
     }
     const int base = c_rp[i];
     if (!ep.enabled) {
-        for (int t = lane; t < n; t += GROUP) { c_col[base + t] = table[t]; c_val[base + t] = vals[t]; }
+        for (int t = lane; t < n; t += GROUP) { c_col[base + t] = list[t]; c_val[base + t] = vals[t]; }
     } else {
         // smooth_interpolation: scalar = w * (1/a_ii); v *= -scalar; then += P_ij where present
         double dv = 0.0; bool found = false;
@@ -133,7 +145,7 @@ __device__ void sg_row_fill(int i, int lane, const SgMat &a, const SgMat &b, int
         const int p0 = ep.p.rp[i], p1 = ep.p.rp[i + 1];
         int matched = 0;
         for (int t = lane; t < n; t += GROUP) {
-            const int j = table[t];
+            const int j = list[t];
             double v = vals[t] * -scalar;
             int lo = p0, hi = p1;
             while (lo < hi) { const int mid = (lo + hi) >> 1; if (ep.p.col[mid] < j) lo = mid + 1; else hi = mid; }
@@ -157,18 +169,29 @@ __device__ void sg_row_fill(int i, int lane, const SgMat &a, const SgMat &b, int
 }
 
 // ---- kernels ------------------------------------------------------------------------------
-__global__ void sg_ub_kernel(SgMat a, SgMat b, int m, int *__restrict__ ub, int *__restrict__ cls, int *__restrict__ class_count,
-                             int *__restrict__ max_ub) {
+constexpr int SG_NCLS = 8;   // size classes per pass (see sg_plan)
+constexpr int SG_WARPS = 4;  // rows per CTA in the warp-per-row classes
+
+__global__ void sg_ub_kernel(SgMat a, SgMat b, int m, int *__restrict__ ub) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
     long long s = 0;
     for (int q = a.rp[i]; q < a.rp[i + 1]; ++q) { const int k = a.col[q]; s += b.rp[k + 1] - b.rp[k]; }
-    const int u = s > 0x3fffffff ? 0x3fffffff : (int)s;
-    ub[i] = u;
-    const int c = u <= SG_H0 ? 0 : u <= SG_H1 ? 1 : u <= SG_H2 ? 2 : 3;
+    ub[i] = s > 0x3fffffff ? 0x3fffffff : (int)s;
+}
+
+struct SgBounds { int limit[SG_NCLS]; };  // class c holds rows with size <= limit[c] (ascending; last = INT_MAX)
+
+__global__ void sg_classify_kernel(const int *__restrict__ size, int m, SgBounds bnd, int *__restrict__ cls,
+                                   int *__restrict__ class_count, int *__restrict__ max_size) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int u = size[i];
+    int c = 0;
+    while (c < SG_NCLS - 1 && u > bnd.limit[c]) ++c;
     cls[i] = c;
     atomicAdd(&class_count[c], 1);
-    if (c == 3) atomicMax(max_ub, u);
+    if (c == SG_NCLS - 1) atomicMax(max_size, u);
 }
 
 __global__ void sg_bin_kernel(const int *__restrict__ cls, int m, int *__restrict__ cursor, int *__restrict__ perm) {
@@ -180,82 +203,118 @@ __global__ void sg_bin_kernel(const int *__restrict__ cls, int m, int *__restric
 struct SgArgs {
     SgMat a, b;
     const int *perm; int count;   // rows of this class
+    int hmask;                    // table size - 1 for this class
     int *row_nnz;                 // pass 1 output
     const int *c_rp; int *c_col; double *c_val;  // pass 2 output
     SgEpilogue ep;
-    int *g_table; int *g_list; double *g_vals; int g_hmask;  // class 3 scratch (per CTA slices)
+    int *g_table; int *g_list;    // global-table class scratch (per CTA slices)
 };
 
-template <int H, int WARPS, bool FILL>
-__global__ void __launch_bounds__(WARPS * 32) sg_warp_kernel(SgArgs s) {
-    __shared__ int s_table[WARPS][H];
-    __shared__ int s_list[FILL ? WARPS : 1][FILL ? H : 1];
-    __shared__ double s_vals[FILL ? WARPS : 1][FILL ? H : 1];
-    __shared__ int s_cnt[WARPS];
+// one warp per row; dynamic shared memory: per warp (hmask+1) ints (+ half as many for the list)
+template <bool FILL>
+__global__ void __launch_bounds__(SG_WARPS * 32) sg_warp_kernel(SgArgs s) {
+    extern __shared__ __align__(16) int sg_smem[];
+    __shared__ int s_cnt[SG_WARPS];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int idx = blockIdx.x * WARPS + w;
+    const int h = s.hmask + 1;
+    const int per_warp = FILL ? h + (h >> 1) : h;
+    int *table = sg_smem + w * per_warp;
+    const int idx = blockIdx.x * SG_WARPS + w;
     if (idx >= s.count) return;
     const int i = s.perm[idx];
-    if (FILL) sg_row_fill<32>(i, lane, s.a, s.b, s_table[w], s_list[w], s_vals[w], H - 1, &s_cnt[w], s.c_rp, s.c_col, s.c_val, s.ep);
-    else sg_row_count<32>(i, lane, s.a, s.b, s_table[w], H - 1, &s_cnt[w], s.row_nnz);
+    if (FILL) sg_row_fill<32>(i, lane, s.a, s.b, table, table + h, s.hmask, &s_cnt[w], s.c_rp, s.c_col, s.c_val, s.ep);
+    else sg_row_count<32>(i, lane, s.a, s.b, table, s.hmask, &s_cnt[w], s.row_nnz);
 }
 
 template <bool FILL>
 __global__ void __launch_bounds__(256) sg_cta_kernel(SgArgs s) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    double *vals = reinterpret_cast<double *>(smem);                 // H2 doubles (FILL only)
-    int *table = reinterpret_cast<int *>(smem + (FILL ? sizeof(double) * SG_H2 : 0));
-    int *list = table + SG_H2;                                       // FILL only
+    extern __shared__ __align__(16) int sg_smem[];
     __shared__ int s_cnt;
+    const int h = s.hmask + 1;
     const int i = s.perm[blockIdx.x];
-    if (FILL) sg_row_fill<256>(i, threadIdx.x, s.a, s.b, table, list, vals, SG_H2 - 1, &s_cnt, s.c_rp, s.c_col, s.c_val, s.ep);
-    else sg_row_count<256>(i, threadIdx.x, s.a, s.b, table, SG_H2 - 1, &s_cnt, s.row_nnz);
+    if (FILL) sg_row_fill<256>(i, threadIdx.x, s.a, s.b, sg_smem, sg_smem + h, s.hmask, &s_cnt, s.c_rp, s.c_col, s.c_val, s.ep);
+    else sg_row_count<256>(i, threadIdx.x, s.a, s.b, sg_smem, s.hmask, &s_cnt, s.row_nnz);
 }
 
 template <bool FILL>
 __global__ void __launch_bounds__(256) sg_global_kernel(SgArgs s) {
     __shared__ int s_cnt;
-    const size_t h = (size_t)s.g_hmask + 1;
+    const size_t h = (size_t)s.hmask + 1;
     int *table = s.g_table + (size_t)blockIdx.x * h;
-    int *list = s.g_list + (size_t)blockIdx.x * h;
-    double *vals = s.g_vals + (size_t)blockIdx.x * h;
+    int *list = s.g_list + (size_t)blockIdx.x * (h >> 1);
     for (int idx = blockIdx.x; idx < s.count; idx += gridDim.x) {
         const int i = s.perm[idx];
-        if (FILL) sg_row_fill<256>(i, threadIdx.x, s.a, s.b, table, list, vals, s.g_hmask, &s_cnt, s.c_rp, s.c_col, s.c_val, s.ep);
-        else sg_row_count<256>(i, threadIdx.x, s.a, s.b, table, s.g_hmask, &s_cnt, s.row_nnz);
+        if (FILL) sg_row_fill<256>(i, threadIdx.x, s.a, s.b, table, list, s.hmask, &s_cnt, s.c_rp, s.c_col, s.c_val, s.ep);
+        else sg_row_count<256>(i, threadIdx.x, s.a, s.b, table, s.hmask, &s_cnt, s.row_nnz);
         __syncthreads();
     }
 }
 
+// Class plan.  Pass 1 sizes tables from the upper bound ub (keys only, load factor <= 0.75);
+// pass 2 from the exact row length (load factor <= 0.5; 6 bytes of shared memory per table slot).
+//   kind 0: warp per row (SG_WARPS rows per CTA), 1: CTA per row, 2: CTA per row, global tables
+struct SgClass { int limit, h, kind; };
+// Only the last class is open-ended (it alone tracks the maximum row size for its table); unused
+// slots repeat the previous limit so that nothing falls into them.
+static const SgClass SG_PASS1[SG_NCLS] = {{48, 64, 0},       {192, 256, 0},     {768, 1024, 0},    {3072, 4096, 0},
+                                          {12288, 16384, 1}, {12288, 16384, 1}, {12288, 16384, 1}, {0x7fffffff, 0, 2}};
+static const SgClass SG_PASS2[SG_NCLS] = {{32, 64, 0},       {128, 256, 0},     {512, 1024, 0},    {2048, 4096, 1},
+                                          {16384, 32768, 1}, {16384, 32768, 1}, {16384, 32768, 1}, {0x7fffffff, 0, 2}};
+
 template <bool FILL>
-static famg_status sg_launch_all(famg_ctx *ctx, SgArgs base, const int *perm, const int *h_count, int h_max_ub, int **scratch_i,
-                                 double **scratch_d) {
+static famg_status sg_run_pass(famg_ctx *ctx, SgArgs base, const int *d_size, int m, int *d_cls, int *d_perm, int *d_counters,
+                               int **scratch) {
+    const SgClass *plan = FILL ? SG_PASS2 : SG_PASS1;
+    SgBounds bnd;
+    for (int c = 0; c < SG_NCLS; ++c) bnd.limit[c] = plan[c].limit;
+    int h_counters[16] = {0};
+    cudaMemsetAsync(d_counters, 0, sizeof(int) * 16, ctx->stream);
+    sg_classify_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, ctx->stream>>>(d_size, m, bnd, d_cls, d_counters, d_counters + 8);
+    count_launch(ctx);
+    CUDA_TRY(cudaMemcpyAsync(h_counters, d_counters, sizeof(int) * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    int h_cursor[SG_NCLS], acc = 0;
+    for (int c = 0; c < SG_NCLS; ++c) { h_cursor[c] = acc; acc += h_counters[c]; }
+    CUDA_TRY(cudaMemcpyAsync(d_counters, h_cursor, sizeof(int) * SG_NCLS, cudaMemcpyHostToDevice, ctx->stream));
+    sg_bin_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, ctx->stream>>>(d_cls, m, d_counters, d_perm);
+    count_launch(ctx);
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // h_cursor is a stack buffer
+    const int max_size = h_counters[8];
     int off = 0;
-    for (int c = 0; c < SG_CLASSES; ++c) {
-        const int cnt = h_count[c];
+    // merge the open-ended global classes into one launch
+    int global_count = 0, global_off = -1;
+    for (int c = 0; c < SG_NCLS; ++c) {
+        const int cnt = h_counters[c];
         SgArgs s = base;
-        s.perm = perm + off; s.count = cnt;
+        s.perm = d_perm + off; s.count = cnt;
+        const int my_off = off;
         off += cnt;
         if (cnt == 0) continue;
-        if (c == 0) {
-            sg_warp_kernel<SG_H0, 8, FILL><<<(unsigned)ceil_div(cnt, 8), 256, 0, ctx->stream>>>(s);
-        } else if (c == 1) {
-            sg_warp_kernel<SG_H1, 2, FILL><<<(unsigned)ceil_div(cnt, 2), 64, 0, ctx->stream>>>(s);
-        } else if (c == 2) {
-            const size_t smem = FILL ? (sizeof(double) + 2 * sizeof(int)) * SG_H2 : sizeof(int) * SG_H2;
-            CUDA_TRY(cudaFuncSetAttribute(sg_cta_kernel<FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            sg_cta_kernel<FILL><<<(unsigned)cnt, 256, smem, ctx->stream>>>(s);
+        if (plan[c].kind == 2) { if (global_off < 0) global_off = my_off; global_count += cnt; continue; }
+        s.hmask = plan[c].h - 1;
+        const size_t per_row = (size_t)(FILL ? plan[c].h + plan[c].h / 2 : plan[c].h) * sizeof(int);
+        if (plan[c].kind == 0) {
+            const size_t smem = per_row * SG_WARPS;
+            if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(sg_warp_kernel<FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            sg_warp_kernel<FILL><<<(unsigned)ceil_div(cnt, SG_WARPS), SG_WARPS * 32, smem, ctx->stream>>>(s);
         } else {
-            int h = 1;
-            while (h < 2 * h_max_ub) h <<= 1;
-            const int grid = std::min(cnt, 2 * ctx->num_sms);
-            if (!*scratch_i) {
-                FAMG_TRY(dev_alloc(scratch_i, (int64_t)grid * h * 2));
-                FAMG_TRY(dev_alloc(scratch_d, (int64_t)grid * h));
-            }
-            s.g_table = *scratch_i; s.g_list = *scratch_i + (size_t)grid * h; s.g_vals = *scratch_d; s.g_hmask = h - 1;
-            sg_global_kernel<FILL><<<grid, 256, 0, ctx->stream>>>(s);
+            if (per_row > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(sg_cta_kernel<FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            sg_cta_kernel<FILL><<<(unsigned)cnt, 256, per_row, ctx->stream>>>(s);
         }
+        count_launch(ctx);
+        KERNEL_CHECK();
+    }
+    if (global_count > 0) {
+        if (max_size > (1 << 27)) FAMG_FAIL(FAMG_ERR_UNSUPPORTED, "spgemm: a row of the product has %d candidate entries", max_size);
+        int h = 1;
+        while (h < 2 * max_size) h <<= 1;
+        const int grid = std::min(global_count, 2 * ctx->num_sms);
+        if (*scratch) { cudaStreamSynchronize(ctx->stream); cudaFree(*scratch); *scratch = nullptr; }
+        FAMG_TRY(dev_alloc(scratch, (int64_t)grid * (h + h / 2)));
+        SgArgs s = base;
+        s.perm = d_perm + global_off; s.count = global_count; s.hmask = h - 1;
+        s.g_table = *scratch; s.g_list = *scratch + (size_t)grid * h;
+        sg_global_kernel<FILL><<<grid, 256, 0, ctx->stream>>>(s);
         count_launch(ctx);
         KERNEL_CHECK();
     }
@@ -268,57 +327,36 @@ famg_status spgemm_impl(const famg_csr *a, const famg_csr *b, const famg_csr *p_
     famg_ctx *ctx = a->ctx;
     const int m = (int)a->nrows;
     SgMat A{a->row_ptr, a->col, a->val}, B{b->row_ptr, b->col, b->val};
-    int *ub = nullptr, *cls = nullptr, *perm = nullptr, *counters = nullptr, *row_nnz = nullptr, *scratch_i = nullptr;
-    double *scratch_d = nullptr;
+    // one pooled scratch block: ub | cls | perm | row_nnz(+1) | rp(+1) | counters(16)
+    const size_t words = (size_t)5 * (m + 2) + 32;
+    int *blk = nullptr, *scratch = nullptr;
     famg_csr *c = nullptr;
-    famg_status st = FAMG_OK;
+    famg_status st = pool_alloc(ctx, words * sizeof(int), (void **)&blk);
+    if (st != FAMG_OK) return st;
+    int *ub = blk, *cls = ub + (m + 2), *perm = cls + (m + 2), *row_nnz = perm + (m + 2), *rp = row_nnz + (m + 2),
+        *counters = rp + (m + 2);
     auto cleanup = [&]() {
-        cudaStreamSynchronize(ctx->stream);
-        cudaFree(ub); cudaFree(cls); cudaFree(perm); cudaFree(counters); cudaFree(row_nnz); cudaFree(scratch_i); cudaFree(scratch_d);
+        pool_free(ctx, blk, words * sizeof(int));
+        if (scratch) { cudaStreamSynchronize(ctx->stream); cudaFree(scratch); }
     };
 #define SG_TRY(expr) do { st = (expr); if (st != FAMG_OK) { cleanup(); if (c) csr_release(c); return st; } } while (0)
-    SG_TRY(dev_alloc(&ub, m));
-    SG_TRY(dev_alloc(&cls, m));
-    SG_TRY(dev_alloc(&perm, m));
-    SG_TRY(dev_alloc(&counters, 16));
-    SG_TRY(dev_alloc(&row_nnz, m + 1));
-    cudaMemsetAsync(counters, 0, sizeof(int) * 16, ctx->stream);
-    int h_counters[16] = {0};
-    if (m > 0) {
-        sg_ub_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, ctx->stream>>>(A, B, m, ub, cls, counters, counters + 8);
-        count_launch(ctx);
-        cudaError_t e = cudaMemcpyAsync(h_counters, counters, sizeof(int) * 16, cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) { set_error("spgemm: %s", cudaGetErrorString(e)); SG_TRY(FAMG_ERR_CUDA); }
-        // cursors = exclusive offsets of the classes
-        int h_cursor[SG_CLASSES], acc = 0;
-        for (int k = 0; k < SG_CLASSES; ++k) { h_cursor[k] = acc; acc += h_counters[k]; }
-        cudaMemcpyAsync(counters + 4, h_cursor, sizeof(int) * SG_CLASSES, cudaMemcpyHostToDevice, ctx->stream);
-        sg_bin_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, ctx->stream>>>(cls, m, counters + 4, perm);
-        count_launch(ctx);
-        cudaStreamSynchronize(ctx->stream);  // h_cursor is a stack buffer
-    }
     SgArgs base{};
     base.a = A; base.b = B; base.row_nnz = row_nnz;
     base.ep.enabled = 0;
-    SG_TRY((sg_launch_all<false>(ctx, base, perm, h_counters, h_counters[8], &scratch_i, &scratch_d)));
-    // row_ptr = exclusive scan of the exact row counts
-    {
-        int *rp = nullptr;
-        SG_TRY(dev_alloc(&rp, m + 1));
-        st = exclusive_scan_i32(ctx, row_nnz, rp, m);
-        int total = 0;
-        if (st == FAMG_OK) {
-            cudaError_t e = cudaMemcpy(&total, rp + m, sizeof(int), cudaMemcpyDeviceToHost);
-            if (e != cudaSuccess) { set_error("spgemm: %s", cudaGetErrorString(e)); st = FAMG_ERR_CUDA; }
-        }
-        if (st == FAMG_OK && total < 0) { set_error("spgemm: product has more than 2^31 non-zeros"); st = FAMG_ERR_UNSUPPORTED; }
-        if (st == FAMG_OK) st = csr_alloc(ctx, a->nrows, b->ncols, total, &c);
-        if (st == FAMG_OK) cudaMemcpyAsync(c->row_ptr, rp, sizeof(int) * (m + 1), cudaMemcpyDeviceToDevice, ctx->stream);
-        cudaStreamSynchronize(ctx->stream);
-        cudaFree(rp);
-        SG_TRY(st);
+    int total = 0;
+    if (m > 0) {
+        sg_ub_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, ctx->stream>>>(A, B, m, ub);
+        count_launch(ctx);
+        SG_TRY((sg_run_pass<false>(ctx, base, ub, m, cls, perm, counters, &scratch)));
     }
+    SG_TRY(exclusive_scan_i32(ctx, row_nnz, rp, m));
+    {
+        cudaError_t e = cudaMemcpy(&total, rp + m, sizeof(int), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { set_error("spgemm: %s", cudaGetErrorString(e)); SG_TRY(FAMG_ERR_CUDA); }
+        if (total < 0) { set_error("spgemm: product has more than 2^31 non-zeros"); SG_TRY(FAMG_ERR_UNSUPPORTED); }
+    }
+    SG_TRY(csr_alloc(ctx, a->nrows, b->ncols, total, &c));
+    cudaMemcpyAsync(c->row_ptr, rp, sizeof(int) * (m + 1), cudaMemcpyDeviceToDevice, ctx->stream);
     int *err_flag = counters + 12;
     base.c_rp = c->row_ptr; base.c_col = c->col; base.c_val = c->val;
     if (p_for_smoothing) {
@@ -326,9 +364,9 @@ famg_status spgemm_impl(const famg_csr *a, const famg_csr *b, const famg_csr *p_
         base.ep.p = SgMat{p_for_smoothing->row_ptr, p_for_smoothing->col, p_for_smoothing->val};
         base.ep.error_flag = err_flag;
     }
-    SG_TRY((sg_launch_all<true>(ctx, base, perm, h_counters, h_counters[8], &scratch_i, &scratch_d)));
+    if (m > 0) SG_TRY((sg_run_pass<true>(ctx, base, row_nnz, m, cls, perm, counters, &scratch)));
     int h_err = 0;
-    {
+    if (p_for_smoothing) {
         cudaError_t e = cudaMemcpyAsync(&h_err, err_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) { set_error("spgemm: %s", cudaGetErrorString(e)); SG_TRY(FAMG_ERR_CUDA); }

@@ -106,8 +106,12 @@ __global__ void __launch_bounds__(SPMV_THREADS, 4) spmv_kernel(const SpmvKernelP
     const int cnt = q1 - q0a;
     const bool staged = cnt <= SPMV_CAP;
 
-    const int g = tid / TPR;
-    const int lane = tid % TPR;
+    // lane mapping inside a warp: the row varies fastest (GPW = 32/TPR adjacent rows), the entry
+    // slot slowest, so one gather instruction reads GPW consecutive x entries per slot for a stencil
+    // matrix, and the epilogue lanes (slot 0) hold GPW consecutive rows (coalesced vector traffic)
+    constexpr int GPW = 32 / TPR;
+    const int g = (tid >> 5) * GPW + ((tid & 31) % GPW);
+    const int lane = (tid & 31) / GPW;
     const int row = r0 + g;
     const bool active = row < r1;
     int a = 0, e = 0;
@@ -171,7 +175,7 @@ __global__ void __launch_bounds__(SPMV_THREADS, 4) spmv_kernel(const SpmvKernelP
         }
         if (TPR > 1) {
 #pragma unroll
-            for (int o = TPR >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            for (int o = 16; o >= GPW; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         }
         if (active && lane == 0) epi_store<EPI, DOT>(yc, row, s, ops, dot_acc);
     }
@@ -194,6 +198,9 @@ __global__ void __launch_bounds__(SPMV_THREADS, 4) spmv_kernel(const SpmvKernelP
 // ===================================================================================================
 // Variant 2: persistent, warp-specialised, TMA-fed pipeline.
 //   * grid = (resident CTAs per SM) x (SM count); every CTA walks chunks c = blockIdx.x, +gridDim.x, ...
+//   * measured configuration sweep on B200 (profiles/r1_kernel_ab.md): 4 CTAs/SM x 2 stages x 2304
+//     non-zeros beats 3 x 3 x 2048 by 10-15 % on the fused variants -- consumer warps per SM matter
+//     more than pipeline depth; 5 CTAs/SM (40 registers, spills) and 2 CTAs/SM are both clearly worse.
 //   * warp 8 is the producer: one elected lane turns each chunk into two bulk async copies
 //     (cp.async.bulk global -> shared, SASS UBLKCP) of the chunk's col[] and val[] slices into a
 //     TMA_STAGES-deep ring, completion signalled on an mbarrier with expect_tx;
@@ -201,8 +208,18 @@ __global__ void __launch_bounds__(SPMV_THREADS, 4) spmv_kernel(const SpmvKernelP
 //     memory exactly as variant 1 (same summation order => same bits), then release the stage on
 //     its "empty" barrier.  No __syncthreads in the steady state, no register staging of A.
 // ===================================================================================================
-constexpr int TMA_STAGES = 3;
-constexpr int TMA_CAP = 2048;  // non-zeros per stage: 16 KB values + 8 KB indices
+#ifndef FAMG_TMA_STAGES
+#define FAMG_TMA_STAGES 2
+#endif
+#ifndef FAMG_TMA_CAP
+#define FAMG_TMA_CAP 2304
+#endif
+#ifndef FAMG_TMA_CTAS
+#define FAMG_TMA_CTAS 4
+#endif
+constexpr int TMA_STAGES = FAMG_TMA_STAGES;
+constexpr int TMA_CAP = FAMG_TMA_CAP;  // non-zeros per stage (12 bytes each: f64 value + i32 index)
+constexpr int TMA_CTAS = FAMG_TMA_CTAS;  // resident CTAs per SM the grid is sized for
 constexpr int TMA_CONSUMERS = 256;
 constexpr int TMA_THREADS = TMA_CONSUMERS + 32;
 constexpr int TMA_SMEM = TMA_STAGES * TMA_CAP * 12 + 2 * TMA_STAGES * 8 + 8 * 8;
@@ -233,7 +250,7 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 }
 
 template <int TPR, int EPI, bool DOT>
-__global__ void __launch_bounds__(TMA_THREADS, 3) spmv_tma_kernel(const SpmvKernelParams p, const int nchunks) {
+__global__ void __launch_bounds__(TMA_THREADS, TMA_CTAS) spmv_tma_kernel(const SpmvKernelParams p, const int nchunks) {
     constexpr int ROWS = TMA_CONSUMERS / TPR;
     extern __shared__ __align__(128) unsigned char smem[];
     double *s_val = reinterpret_cast<double *>(smem);
@@ -275,8 +292,9 @@ __global__ void __launch_bounds__(TMA_THREADS, 3) spmv_tma_kernel(const SpmvKern
         return;
     }
     // ---------------------------------------------------------------------- consumers
-    const int g = tid / TPR;
-    const int lane = tid % TPR;
+    constexpr int GPW = 32 / TPR;  // row groups per warp; rows fastest, entry slot slowest (see variant 1)
+    const int g = (tid >> 5) * GPW + ((tid & 31) % GPW);
+    const int lane = (tid & 31) / GPW;
     int stage = 0;
     uint32_t fphase = 0;
     double dot_acc = 0.0;
@@ -338,7 +356,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 3) spmv_tma_kernel(const SpmvKern
             }
             if (TPR > 1) {
 #pragma unroll
-                for (int o = TPR >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                for (int o = 16; o >= GPW; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             }
             if (active && lane == 0) epi_store<EPI, DOT>(yc, row, s, ops, dot_acc);
         }
@@ -368,7 +386,7 @@ template <int TPR, int EPI, bool DOT>
 static famg_status launch_one(const SpmvKernelParams &kp, int variant, int nrows, int num_sms, cudaStream_t st, int *grid_out) {
     if (variant == 2) {
         const int nchunks = (int)ceil_div(nrows, TMA_CONSUMERS / TPR);
-        const int grid = std::min(nchunks, 3 * num_sms);
+        const int grid = std::min(nchunks, TMA_CTAS * num_sms);
         static bool configured = false;  // per template instance
         if (!configured) {
             CUDA_TRY(cudaFuncSetAttribute(spmv_tma_kernel<TPR, EPI, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM));

@@ -16,11 +16,12 @@ import numpy as np
 class Partition:
     """Aggregates in CSR form: ``agg_nodes[agg_ptr[a]:agg_ptr[a+1]]`` ascending (BTreeSet order)."""
 
-    def __init__(self, agg_ptr, agg_nodes, nnodes: int):
+    def __init__(self, agg_ptr, agg_nodes, nnodes: int, validate: bool = True):
         self.agg_ptr = np.ascontiguousarray(agg_ptr, dtype=np.int64)
         self.agg_nodes = np.ascontiguousarray(agg_nodes, dtype=np.int64)
         self._nnodes = int(nnodes)
-        self.validate()
+        if validate:
+            self.validate()
 
     @classmethod
     def from_node_to_agg(cls, node_to_agg) -> "Partition":
@@ -60,6 +61,15 @@ def geometric_partition(dims: Sequence[int], block: Sequence[int] = (2, 2, 2)) -
     nx, ny, nz = dims
     bx, by, bz = block
     cx, cy, cz = max(nx // bx, 1), max(ny // by, 1), max(nz // bz, 1)
+    if nx == cx * bx and ny == cy * by and nz == cz * bz:
+        # regular case, built directly (no sort): aggregate (X,Y,Z) lists its nodes in (dz,dy,dx)
+        # order, which is ascending node order
+        ix = (bx * np.arange(cx, dtype=np.int64)[:, None] + np.arange(bx, dtype=np.int64)[None, :])
+        iy = (by * np.arange(cy, dtype=np.int64)[:, None] + np.arange(by, dtype=np.int64)[None, :]) * nx
+        iz = (bz * np.arange(cz, dtype=np.int64)[:, None] + np.arange(bz, dtype=np.int64)[None, :]) * (nx * ny)
+        nodes = (iz[:, None, None, :, None, None] + iy[None, :, None, None, :, None] + ix[None, None, :, None, None, :])
+        ptr = np.arange(cx * cy * cz + 1, dtype=np.int64) * (bx * by * bz)
+        return Partition(ptr, nodes.reshape(-1), nx * ny * nz, validate=False), (cx, cy, cz)
     x = np.minimum(np.arange(nx) // bx, cx - 1)
     y = np.minimum(np.arange(ny) // by, cy - 1)
     z = np.minimum(np.arange(nz) // bz, cz - 1)
