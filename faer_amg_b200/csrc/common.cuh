@@ -157,6 +157,8 @@ struct SpmvArgs {
     int k = 1;
     double *dot_partials = nullptr;              // k == 1: per-CTA partial of sum_i x[i]*(A x)[i]
     int row_begin = 0, row_end = -1;             // row range (distributed interior/boundary split)
+    int row2_begin = 0, row2_end = 0;            // optional second range handled by the same launch
+    int reserve_ctas = 0;                        // leave this many CTA slots free (room for NCCL kernels)
     cudaStream_t stream = nullptr;               // default: ctx stream
 };
 famg_status spmv_launch(const SpmvArgs &args, int *num_ctas = nullptr);

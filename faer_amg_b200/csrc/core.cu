@@ -294,7 +294,11 @@ famg_status famg_ctx_create(int device, famg_ctx **out) {
     if (const char *v = getenv("FAMG_SPMV_VARIANT")) ctx->spmv_variant = atoi(v) == 1 ? 1 : 2;
     if (const char *v = getenv("FAMG_TMA_MIN_ROWS")) ctx->tma_min_rows = std::max(atoi(v), 1);
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+    {   // halo exchanges must not queue behind bulk compute: highest priority for the comm stream
+        int lo = 0, hi = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&ctx->comm_stream, cudaStreamNonBlocking, hi));
+    }
     CUDA_TRY(cudaMalloc((void **)&ctx->d_scalars, 64 * sizeof(double)));
     CUDA_TRY(cudaMemset(ctx->d_scalars, 0, 64 * sizeof(double)));
     CUDA_TRY(cudaMallocHost((void **)&ctx->h_scalars, 64 * sizeof(double)));

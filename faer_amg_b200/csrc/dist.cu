@@ -111,6 +111,10 @@ struct famg_dist_mg {
     double *g_f = nullptr, *g_v = nullptr, *fc_loc = nullptr;
     // PCG work vectors (with ghost tail for p)
     double *pcg = nullptr; int64_t pcg_ld = 0;
+    // the distributed cycle (kernels on two streams + NCCL point-to-point / broadcast calls) is
+    // captured into one CUDA graph per (out, rhs) pair and replayed; disabled on the first failure
+    std::map<std::pair<const void *, const void *>, GraphEntry> graphs;
+    bool use_graph = true;
 };
 
 namespace famg {
@@ -273,6 +277,8 @@ static famg_status halo_begin(famg_comm *cm, const HaloPlan &h, double *x_ext) {
     }
     CUDA_TRY(cudaEventRecord(cm->ev_packed, ctx->stream));
     CUDA_TRY(cudaStreamWaitEvent(ctx->comm_stream, cm->ev_packed, 0));
+    static const bool skip_comm = getenv("FAMG_DEBUG_SKIP_HALO") != nullptr;  // timing experiments only (wrong results)
+    if (skip_comm) { CUDA_TRY(cudaEventRecord(cm->ev_halo, ctx->comm_stream)); return FAMG_OK; }
     NCCL_TRY(g_nccl.GroupStart());
     for (int p = 0; p < cm->nranks; ++p) {
         if (h.send_cnt[p]) NCCL_TRY(g_nccl.Send(h.d_sendbuf + h.send_off[p], (size_t)h.send_cnt[p], ncclDouble, p, cm->comm, ctx->comm_stream));
@@ -303,16 +309,17 @@ static famg_status dist_apply(famg_comm *cm, const DistOp &op, int epi, double *
     }
     FAMG_TRY(halo_begin(cm, op.halo, x_ext));
     if (op.ie > op.ib) {
+        // the persistent kernel would otherwise occupy every CTA slot for its whole duration and
+        // the NCCL send/recv kernel could not start until it retires: leave a few slots free
         g.row_begin = op.ib; g.row_end = op.ie; g.dot_partials = dot_partials ? dot_partials + total : nullptr;
+        g.reserve_ctas = 4 * 8;
         FAMG_TRY(spmv_launch(g, &n)); total += n;
+        g.reserve_ctas = 0;
     }
     FAMG_TRY(halo_end(cm, op.halo));
-    if (op.ib > 0) {
-        g.row_begin = 0; g.row_end = op.ib; g.dot_partials = dot_partials ? dot_partials + total : nullptr;
-        FAMG_TRY(spmv_launch(g, &n)); total += n;
-    }
-    if (op.ie < nrows) {
-        g.row_begin = op.ie; g.row_end = nrows; g.dot_partials = dot_partials ? dot_partials + total : nullptr;
+    if (op.ib > 0 || op.ie < nrows) {  // both boundary slabs in one launch
+        g.row_begin = 0; g.row_end = op.ib; g.row2_begin = op.ie; g.row2_end = nrows;
+        g.dot_partials = dot_partials ? dot_partials + total : nullptr;
         FAMG_TRY(spmv_launch(g, &n)); total += n;
     }
     if (num_partials) *num_partials = total;
@@ -403,6 +410,7 @@ static void dist_free(famg_dist_mg *d) {
         distop_free(l.A); distop_free(l.R); distop_free(l.P);
         cudaFree(l.d); cudaFree(l.x); cudaFree(l.b); cudaFree(l.t);
     }
+    for (auto &g : d->graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
     cudaFree(d->g_f); cudaFree(d->g_v); cudaFree(d->fc_loc); cudaFree(d->pcg);
     delete d;
 }
@@ -484,6 +492,7 @@ famg_status famg_dist_mg_create(famg_comm *c, famg_mg *gm, const int64_t *const 
         if (!ok) { dist_free(d); FAMG_FAIL(FAMG_ERR_INVALID, "row_splits of level %d do not partition its rows", l); }
     }
     // first replicated level: too few rows per rank, a non-Diag smoother, or the coarsest level
+    if (const char *v = getenv("FAMG_DIST_GRAPH")) d->use_graph = atoi(v) != 0;
     int lrep = nl - 1;
     for (int l = 0; l < nl - 1; ++l)
         if (gm->lv[l].a->nrows / nr < replicate_below || gm->lv[l].s->kind != SM_DIAG) { lrep = l; break; }
@@ -557,7 +566,36 @@ static famg_status dist_check_local(const famg_dist_mg *d, const famg_vec *v) {
 
 // out_local = B rhs_local: one distributed mu-cycle from a zero guess. (buffers: pcg slot 4/5)
 static famg_status dist_precond(famg_dist_mg *d, double *out_ext, const double *rhs) {
-    return dist_cycle(d, 0, out_ext, rhs, true);
+    famg_ctx *ctx = d->comm->ctx;
+    if (!d->use_graph) return dist_cycle(d, 0, out_ext, rhs, true);
+    auto key = std::make_pair((const void *)out_ext, (const void *)rhs);
+    auto it = d->graphs.find(key);
+    if (it == d->graphs.end()) {
+        const int64_t before = ctx->launches.load();
+        cudaError_t e = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
+        famg_status st = FAMG_ERR_CUDA;
+        cudaGraph_t graph = nullptr;
+        if (e == cudaSuccess) {
+            st = dist_cycle(d, 0, out_ext, rhs, true);
+            e = cudaStreamEndCapture(ctx->stream, &graph);
+        }
+        GraphEntry ent;
+        if (st == FAMG_OK && e == cudaSuccess && graph) e = cudaGraphInstantiate(&ent.exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (st != FAMG_OK || e != cudaSuccess || !ent.exec) {
+            // capture is an optimisation: fall back to eager launches for the rest of this object's life
+            cudaGetLastError();
+            d->use_graph = false;
+            ctx->launches.store(before);
+            return dist_cycle(d, 0, out_ext, rhs, true);
+        }
+        ent.launches = ctx->launches.load() - before;
+        ctx->launches.store(before);
+        it = d->graphs.emplace(key, ent).first;
+    }
+    CUDA_TRY(cudaGraphLaunch(it->second.exec, ctx->stream));
+    count_launch(ctx, (int)it->second.launches);
+    return FAMG_OK;
 }
 
 famg_status famg_dist_mg_apply_dev(famg_dist_mg *d, famg_vec *out_local, const famg_vec *rhs_local) {

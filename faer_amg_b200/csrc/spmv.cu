@@ -44,7 +44,9 @@ __device__ __forceinline__ double2 ld_stream_d2(const double2 *p) {
 
 struct SpmvKernelParams {
     const int *row_ptr; const int *col; const double *val;
-    int row_begin, row_end;  // rows handled by this launch
+    int row_begin, row_end;  // rows handled by this launch ...
+    int row2_begin, row2_end;  // ... plus an optional second range (the two boundary slabs of a
+    int nchunks1;              //     distributed operator in one launch); chunks >= nchunks1 map to it
     const double *x; long long ldx;
     double *y; long long ldy;
     const double *b; long long ldb;
@@ -53,6 +55,13 @@ struct SpmvKernelParams {
     double *dot_partials;
 };
 
+
+// chunk index -> [r0, r1) over the (up to two) row ranges of a launch
+template <int ROWS>
+__device__ __forceinline__ void chunk_rows(const SpmvKernelParams &p, int c, int &r0, int &r1) {
+    if (c < p.nchunks1) { r0 = p.row_begin + c * ROWS; r1 = min(r0 + ROWS, p.row_end); }
+    else { r0 = p.row2_begin + (c - p.nchunks1) * ROWS; r1 = min(r0 + ROWS, p.row2_end); }
+}
 
 // Epilogue operands are loaded *before* the row's gathers (and before the stage wait) so their
 // latency overlaps the streaming of A instead of being exposed once per chunk.
@@ -98,8 +107,8 @@ __global__ void __launch_bounds__(SPMV_THREADS, 4) spmv_kernel(const SpmvKernelP
     __shared__ double s_red[SPMV_THREADS / 32];
 
     const int tid = threadIdx.x;
-    const int r0 = p.row_begin + blockIdx.x * ROWS;
-    const int r1 = min(r0 + ROWS, p.row_end);
+    int r0, r1;
+    chunk_rows<ROWS>(p, blockIdx.x, r0, r1);
     const int q0 = __ldg(p.row_ptr + r0);
     const int q1 = __ldg(p.row_ptr + r1);
     const int q0a = q0 & ~3;  // 16-byte aligned start for int4 / 32-byte for double2 pairs
@@ -275,8 +284,8 @@ __global__ void __launch_bounds__(TMA_THREADS, TMA_CTAS) spmv_tma_kernel(const S
             int stage = 0, uses = 0;
             uint32_t ephase = 0;
             for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
-                const int r0 = p.row_begin + c * ROWS;
-                const int r1 = min(r0 + ROWS, p.row_end);
+                int r0, r1;
+                chunk_rows<ROWS>(p, c, r0, r1);
                 const int q0a = __ldg(p.row_ptr + r0) & ~3;
                 const int cnt = __ldg(p.row_ptr + r1) - q0a;
                 if (cnt <= 0 || cnt > TMA_CAP) continue;  // consumers take the direct path
@@ -301,20 +310,22 @@ __global__ void __launch_bounds__(TMA_THREADS, TMA_CTAS) spmv_tma_kernel(const S
     int c = blockIdx.x;
     int q0 = 0, q1 = 0, a = 0, e = 0;
     if (c < nchunks) {
-        const int r0 = p.row_begin + c * ROWS, r1 = min(r0 + ROWS, p.row_end);
+        int r0, r1;
+        chunk_rows<ROWS>(p, c, r0, r1);
         q0 = __ldg(p.row_ptr + r0); q1 = __ldg(p.row_ptr + r1);
         if (r0 + g < r1) { a = __ldg(p.row_ptr + r0 + g); e = __ldg(p.row_ptr + r0 + g + 1); }
     }
     while (c < nchunks) {
-        const int r0 = p.row_begin + c * ROWS;
-        const int r1 = min(r0 + ROWS, p.row_end);
+        int r0, r1;
+        chunk_rows<ROWS>(p, c, r0, r1);
         const int row = r0 + g;
         const bool active = row < r1;
         // prefetch the next chunk's row pointers (consumed one iteration later)
         const int cn = c + gridDim.x;
         int nq0 = 0, nq1 = 0, na = 0, ne = 0;
         if (cn < nchunks) {
-            const int s0 = p.row_begin + cn * ROWS, s1 = min(s0 + ROWS, p.row_end);
+            int s0, s1;
+            chunk_rows<ROWS>(p, cn, s0, s1);
             nq0 = __ldg(p.row_ptr + s0); nq1 = __ldg(p.row_ptr + s1);
             if (s0 + g < s1) { na = __ldg(p.row_ptr + s0 + g); ne = __ldg(p.row_ptr + s0 + g + 1); }
         }
@@ -383,10 +394,13 @@ __global__ void __launch_bounds__(TMA_THREADS, TMA_CTAS) spmv_tma_kernel(const S
 }
 
 template <int TPR, int EPI, bool DOT>
-static famg_status launch_one(const SpmvKernelParams &kp, int variant, int nrows, int num_sms, cudaStream_t st, int *grid_out) {
+static famg_status launch_one(SpmvKernelParams kp, int variant, int nrows1, int nrows2, int num_sms, int reserve_ctas, cudaStream_t st,
+                              int *grid_out) {
+    constexpr int ROWS = 256 / TPR;  // both variants use 256 row-walking threads
+    kp.nchunks1 = (int)ceil_div(nrows1, ROWS);
+    const int nchunks = kp.nchunks1 + (int)ceil_div(nrows2, ROWS);
     if (variant == 2) {
-        const int nchunks = (int)ceil_div(nrows, TMA_CONSUMERS / TPR);
-        const int grid = std::min(nchunks, TMA_CTAS * num_sms);
+        const int grid = std::max(1, std::min(nchunks, TMA_CTAS * num_sms - reserve_ctas));
         static bool configured = false;  // per template instance
         if (!configured) {
             CUDA_TRY(cudaFuncSetAttribute(spmv_tma_kernel<TPR, EPI, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM));
@@ -395,23 +409,22 @@ static famg_status launch_one(const SpmvKernelParams &kp, int variant, int nrows
         spmv_tma_kernel<TPR, EPI, DOT><<<grid, TMA_THREADS, TMA_SMEM, st>>>(kp, nchunks);
         *grid_out = grid;
     } else {
-        const int grid = (int)ceil_div(nrows, SPMV_THREADS / TPR);
-        spmv_kernel<TPR, EPI, DOT><<<grid, SPMV_THREADS, 0, st>>>(kp);
-        *grid_out = grid;
+        spmv_kernel<TPR, EPI, DOT><<<nchunks, SPMV_THREADS, 0, st>>>(kp);
+        *grid_out = nchunks;
     }
     return FAMG_OK;
 }
 
 template <int TPR>
-static famg_status launch_tpr(const SpmvKernelParams &kp, int epi, bool dot, int variant, int nrows, int sms, cudaStream_t st, int *grid) {
+static famg_status launch_tpr(const SpmvKernelParams &kp, int epi, bool dot, int variant, int nrows, int nrows2, int sms, int reserve, cudaStream_t st, int *grid) {
     switch (epi) {
         case EPI_SPMV:
-            return dot ? launch_one<TPR, EPI_SPMV, true>(kp, variant, nrows, sms, st, grid)
-                       : launch_one<TPR, EPI_SPMV, false>(kp, variant, nrows, sms, st, grid);
-        case EPI_RESID: return launch_one<TPR, EPI_RESID, false>(kp, variant, nrows, sms, st, grid);
-        case EPI_SMOOTH: return launch_one<TPR, EPI_SMOOTH, false>(kp, variant, nrows, sms, st, grid);
-        case EPI_ADD: return launch_one<TPR, EPI_ADD, false>(kp, variant, nrows, sms, st, grid);
-        default: return launch_one<TPR, EPI_SI, false>(kp, variant, nrows, sms, st, grid);
+            return dot ? launch_one<TPR, EPI_SPMV, true>(kp, variant, nrows, nrows2, sms, reserve, st, grid)
+                       : launch_one<TPR, EPI_SPMV, false>(kp, variant, nrows, nrows2, sms, reserve, st, grid);
+        case EPI_RESID: return launch_one<TPR, EPI_RESID, false>(kp, variant, nrows, nrows2, sms, reserve, st, grid);
+        case EPI_SMOOTH: return launch_one<TPR, EPI_SMOOTH, false>(kp, variant, nrows, nrows2, sms, reserve, st, grid);
+        case EPI_ADD: return launch_one<TPR, EPI_ADD, false>(kp, variant, nrows, nrows2, sms, reserve, st, grid);
+        default: return launch_one<TPR, EPI_SI, false>(kp, variant, nrows, nrows2, sms, reserve, st, grid);
     }
 }
 
@@ -422,7 +435,8 @@ famg_status spmv_launch(const SpmvArgs &args, int *num_ctas) {
     int row_begin = args.row_begin;
     int row_end = args.row_end < 0 ? (int)a->nrows : args.row_end;
     if (num_ctas) *num_ctas = 0;
-    if (row_end <= row_begin || args.k <= 0) return FAMG_OK;
+    if ((row_end <= row_begin && args.row2_end <= args.row2_begin) || args.k <= 0) return FAMG_OK;
+    if (row_end < row_begin) row_end = row_begin;
     if ((args.epi == EPI_RESID || args.epi == EPI_SMOOTH) && !args.b) FAMG_FAIL(FAMG_ERR_INVALID, "spmv: missing rhs");
     if ((args.epi == EPI_SMOOTH || args.epi == EPI_SI) && (!args.d || args.y == args.x))
         FAMG_FAIL(FAMG_ERR_INVALID, "spmv: smoother sweep needs a diagonal and distinct in/out vectors");
@@ -430,23 +444,25 @@ famg_status spmv_launch(const SpmvArgs &args, int *num_ctas) {
     SpmvKernelParams kp;
     kp.row_ptr = a->row_ptr; kp.col = a->col; kp.val = a->val;
     kp.row_begin = row_begin; kp.row_end = row_end;
+    kp.row2_begin = args.row2_begin; kp.row2_end = std::max(args.row2_end, args.row2_begin); kp.nchunks1 = 0;
     kp.x = args.x; kp.ldx = args.ldx; kp.y = args.y; kp.ldy = args.ldy;
     kp.b = args.b; kp.ldb = args.ldb; kp.d = args.d; kp.k = args.k;
     kp.dot_partials = args.dot_partials;
     const int tpr = a->tpr;
     const int nrows = row_end - row_begin;
+    const int nrows2 = kp.row2_end - kp.row2_begin;
     const bool dot = args.dot_partials != nullptr;
     // small operators (coarse levels) do not fill a persistent grid: keep the one-chunk-per-CTA kernel
-    const int variant = (ctx->spmv_variant == 2 && nrows >= ctx->tma_min_rows) ? 2 : 1;
+    const int variant = (ctx->spmv_variant == 2 && nrows + nrows2 >= ctx->tma_min_rows) ? 2 : 1;
     int grid = 0;
     famg_status stt;
     switch (tpr) {
-        case 1: stt = launch_tpr<1>(kp, args.epi, dot, variant, nrows, ctx->num_sms, st, &grid); break;
-        case 2: stt = launch_tpr<2>(kp, args.epi, dot, variant, nrows, ctx->num_sms, st, &grid); break;
-        case 4: stt = launch_tpr<4>(kp, args.epi, dot, variant, nrows, ctx->num_sms, st, &grid); break;
-        case 8: stt = launch_tpr<8>(kp, args.epi, dot, variant, nrows, ctx->num_sms, st, &grid); break;
-        case 16: stt = launch_tpr<16>(kp, args.epi, dot, variant, nrows, ctx->num_sms, st, &grid); break;
-        default: stt = launch_tpr<32>(kp, args.epi, dot, variant, nrows, ctx->num_sms, st, &grid); break;
+        case 1: stt = launch_tpr<1>(kp, args.epi, dot, variant, nrows, nrows2, ctx->num_sms, args.reserve_ctas, st, &grid); break;
+        case 2: stt = launch_tpr<2>(kp, args.epi, dot, variant, nrows, nrows2, ctx->num_sms, args.reserve_ctas, st, &grid); break;
+        case 4: stt = launch_tpr<4>(kp, args.epi, dot, variant, nrows, nrows2, ctx->num_sms, args.reserve_ctas, st, &grid); break;
+        case 8: stt = launch_tpr<8>(kp, args.epi, dot, variant, nrows, nrows2, ctx->num_sms, args.reserve_ctas, st, &grid); break;
+        case 16: stt = launch_tpr<16>(kp, args.epi, dot, variant, nrows, nrows2, ctx->num_sms, args.reserve_ctas, st, &grid); break;
+        default: stt = launch_tpr<32>(kp, args.epi, dot, variant, nrows, nrows2, ctx->num_sms, args.reserve_ctas, st, &grid); break;
     }
     FAMG_TRY(stt);
     count_launch(ctx);
