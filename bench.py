@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the faer-amg hot path on B200.
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--n 256]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--grid 256]
 
 Workload (BASELINE.json north_star / configs[3]): PCG + AMG V(1,1)-cycle solve of the 3-D 7-point
 Poisson problem on an n^3 grid (default 256^3, 16.8 M unknowns) to rel. residual 1e-8, b = 1, zero
@@ -325,7 +325,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=256, help="grid points per dimension")
+    ap.add_argument("--grid", "--n", dest="n", type=int, default=256,
+                    help="grid points per dimension (use --grid under torchrun: its parser treats --n as an abbreviation)")
     ap.add_argument("--sample-iters", type=int, default=2, help="PCG iterations per CPU sample")
     ap.add_argument("--replicate-below", type=int, default=32768, help="rows per rank under which a level is replicated")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
