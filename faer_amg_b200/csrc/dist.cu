@@ -36,6 +36,7 @@ struct NcclApi {
     decltype(&ncclRecv) Recv = nullptr;
     decltype(&ncclAllReduce) AllReduce = nullptr;
     decltype(&ncclBroadcast) Broadcast = nullptr;
+    decltype(&ncclAllGather) AllGather = nullptr;
 };
 static NcclApi g_nccl;
 static std::mutex g_nccl_mu;
@@ -50,7 +51,7 @@ static famg_status nccl_load() {
     g_nccl.name = (decltype(g_nccl.name))dlsym(h, "nccl" #name);                     \
     if (!g_nccl.name) { dlclose(h); FAMG_FAIL(FAMG_ERR_COMM, "libnccl lacks nccl" #name); }
     LOAD(GetUniqueId) LOAD(CommInitRank) LOAD(CommDestroy) LOAD(GetErrorString) LOAD(GroupStart) LOAD(GroupEnd)
-    LOAD(Send) LOAD(Recv) LOAD(AllReduce) LOAD(Broadcast)
+    LOAD(Send) LOAD(Recv) LOAD(AllReduce) LOAD(Broadcast) LOAD(AllGather)
 #undef LOAD
     g_nccl.handle = h;
     return FAMG_OK;
@@ -74,7 +75,31 @@ struct famg_comm {
 namespace famg {
 
 // ---------------------------------------------------------------- halo plans
+// Peer-memory halo exchange (NVLink loads/stores instead of NCCL send/recv): every rank owns an
+// "arena" exported with CUDA IPC; per plan it holds one flag per peer, an epoch counter and two
+// receive buffers (parity = epoch & 1).  A pack kernel stores this rank's boundary entries straight
+// into its neighbours' receive buffers, fences, and publishes the epoch in their flag slots; the
+// consumer spins on its own flag slots (acquire, with a timeout) and moves the ghosts into the
+// vector's tail.  Epochs live in device memory, so the sequence replays inside CUDA graphs.
+constexpr int P2P_MAX_NB = 8;
+struct P2PPlanDev {
+    int nnb;                                  // neighbours (peers we exchange flags with, both ways)
+    int nghost;
+    double *rdst[2][P2P_MAX_NB];              // where my entries go on neighbour nb (per parity)
+    unsigned long long *rflag[P2P_MAX_NB];    // my slot in neighbour nb's flag array
+    const unsigned long long *lflag[P2P_MAX_NB];  // neighbour nb's slot in my flag array
+    int soff[P2P_MAX_NB], scnt[P2P_MAX_NB];   // my pack-list range for neighbour nb
+    unsigned long long *epoch;                // this plan's exchange counter (device)
+    unsigned int *done;                       // blocks of the pack kernel that have finished their stores
+    int total_send;
+    const double *lrecv[2];                   // my receive buffers
+    int *err;                                 // set on spin timeout
+};
+
 struct HaloPlan {
+    bool p2p = false;
+    P2PPlanDev dev{};
+    size_t arena_flags = 0, arena_recv[2] = {0, 0};  // byte offsets inside this rank's arena
     int nloc = 0, nghost = 0;
     std::vector<int> recv_cnt, recv_off, send_cnt, send_off;
     int total_send = 0;
@@ -111,6 +136,11 @@ struct famg_dist_mg {
     double *g_f = nullptr, *g_v = nullptr, *fc_loc = nullptr;
     // PCG work vectors (with ghost tail for p)
     double *pcg = nullptr; int64_t pcg_ld = 0;
+    // peer-memory exchange state
+    unsigned char *arena = nullptr; size_t arena_bytes = 0;
+    std::vector<void *> peer_arena;  // IPC-mapped arenas of the other ranks
+    int *d_p2p_err = nullptr;
+    bool p2p = false;
     // the distributed cycle (kernels on two streams + NCCL point-to-point / broadcast calls) is
     // captured into one CUDA graph per (out, rhs) pair and replayed; disabled on the first failure
     std::map<std::pair<const void *, const void *>, GraphEntry> graphs;
@@ -267,6 +297,78 @@ static famg_status distop_build(famg_comm *cm, const famg_csr *m, const std::vec
     return done(FAMG_OK);
 }
 
+// ---------------------------------------------------------------- peer-memory exchange kernels
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Multi-CTA pack: every CTA stores a slice of each neighbour's entries into that neighbour's
+// receive buffer; the CTA that finishes last publishes the epoch (flags) -- the fine-level halo is
+// one xy-plane (0.5-2 MB), too much for a single SM's store throughput on the critical path.
+__global__ void __launch_bounds__(256) p2p_pack_kernel(const P2PPlanDev pl, const double *__restrict__ x,
+                                                       const int *__restrict__ send_idx) {
+    __shared__ bool s_last;
+    const unsigned long long e = *pl.epoch + 1ull;  // only the last CTA advances *epoch, after everyone has read it
+    const int par = (int)(e & 1ull);
+    const int stride = gridDim.x * blockDim.x;
+    for (int nb = 0; nb < pl.nnb; ++nb) {
+        double *dst = pl.rdst[par][nb];
+        const int *idx = send_idx + pl.soff[nb];
+        for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < pl.scnt[nb]; j += stride) dst[j] = x[idx[j]];
+    }
+    __threadfence_system();  // this thread's peer stores are visible system-wide ...
+    __syncthreads();         // ... for every thread of the CTA, before the CTA is counted as done
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(pl.done, 1u);
+        s_last = prev + 1u == gridDim.x;
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence_system();
+        if (threadIdx.x < pl.nnb) st_release_sys(pl.rflag[threadIdx.x], e);
+        if (threadIdx.x == 0) { *pl.done = 0u; *pl.epoch = e; }
+    }
+}
+
+__global__ void __launch_bounds__(256) p2p_wait_kernel(const P2PPlanDev pl, double *__restrict__ ghost_tail) {
+    const unsigned long long e = *pl.epoch;  // advanced by this rank's pack kernel (stream order)
+    if (threadIdx.x < pl.nnb) {
+        const unsigned long long t0 = global_timer_ns();
+        while (ld_acquire_sys(pl.lflag[threadIdx.x]) < e) {
+            if (global_timer_ns() - t0 > 2000000000ull) { atomicExch(pl.err, 1); break; }  // 2 s: peer died
+        }
+    }
+    __syncthreads();
+    const double *src = pl.lrecv[e & 1ull];
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < pl.nghost; j += gridDim.x * blockDim.x)
+        ghost_tail[j] = __ldcg(src + j);  // bypass L1 (peer-written)
+}
+
+static famg_status p2p_begin(famg_comm *cm, const HaloPlan &h, const double *x_ext) {
+    const int grid = std::max(1, std::min(64, (h.total_send + 1023) / 1024));
+    p2p_pack_kernel<<<grid, 256, 0, cm->ctx->stream>>>(h.dev, x_ext, h.d_send_idx);
+    count_launch(cm->ctx);
+    KERNEL_CHECK();
+    return FAMG_OK;
+}
+static famg_status p2p_end(famg_comm *cm, const HaloPlan &h, double *x_ext) {
+    const int grid = std::max(1, std::min(64, (h.nghost + 1023) / 1024));
+    p2p_wait_kernel<<<grid, 256, 0, cm->ctx->stream>>>(h.dev, x_ext + h.nloc);
+    count_launch(cm->ctx);
+    KERNEL_CHECK();
+    return FAMG_OK;
+}
+
 // start the halo exchange of x_ext ([owned | ghost tail]) for `op`; compute stream keeps going
 static famg_status halo_begin(famg_comm *cm, const HaloPlan &h, double *x_ext) {
     if (!h.any || cm->nranks == 1) return FAMG_OK;
@@ -305,6 +407,23 @@ static famg_status dist_apply(famg_comm *cm, const DistOp &op, int epi, double *
         g.dot_partials = dot_partials;
         FAMG_TRY(spmv_launch(g, &n));
         if (num_partials) *num_partials = n;
+        return FAMG_OK;
+    }
+    if (op.halo.p2p) {
+        // pack -> interior rows -> wait+copy ghosts -> boundary rows, all on the compute stream: the
+        // neighbours' stores land in this rank's arena while the interior kernel runs
+        FAMG_TRY(p2p_begin(cm, op.halo, x_ext));
+        if (op.ie > op.ib) {
+            g.row_begin = op.ib; g.row_end = op.ie; g.dot_partials = dot_partials ? dot_partials + total : nullptr;
+            FAMG_TRY(spmv_launch(g, &n)); total += n;
+        }
+        FAMG_TRY(p2p_end(cm, op.halo, x_ext));
+        if (op.ib > 0 || op.ie < nrows) {
+            g.row_begin = 0; g.row_end = op.ib; g.row2_begin = op.ie; g.row2_end = nrows;
+            g.dot_partials = dot_partials ? dot_partials + total : nullptr;
+            FAMG_TRY(spmv_launch(g, &n)); total += n;
+        }
+        if (num_partials) *num_partials = total;
         return FAMG_OK;
     }
     FAMG_TRY(halo_begin(cm, op.halo, x_ext));
@@ -405,7 +524,91 @@ static famg_status dist_cycle(famg_dist_mg *dm, int level, double *va, const dou
     return FAMG_OK;
 }
 
+// Build the peer-memory exchange state for every plan (collective: all ranks call it with the same
+// plan sequence).  Any failure leaves the NCCL path in place.
+static famg_status p2p_setup(famg_dist_mg *d) {
+    famg_comm *cm = d->comm;
+    famg_ctx *ctx = cm->ctx;
+    const int nr = cm->nranks, me = cm->rank;
+    if (nr == 1 || nr > P2P_MAX_NB + 1) return FAMG_OK;
+    std::vector<HaloPlan *> plans;
+    for (auto &L : d->lv) { plans.push_back(&L.A.halo); plans.push_back(&L.R.halo); plans.push_back(&L.P.halo); }
+    const int np = (int)plans.size();
+    if (np == 0) return FAMG_OK;
+    // arena layout: per plan [flags nr x u64 | epoch u64 | pad to 256] [recv0] [recv1] (256-byte aligned)
+    auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    size_t off = 0;
+    for (HaloPlan *h : plans) {
+        h->arena_flags = off; off = align(off + sizeof(unsigned long long) * (nr + 2));
+        for (int b = 0; b < 2; ++b) { h->arena_recv[b] = off; off = align(off + sizeof(double) * (size_t)std::max(h->nghost, 1)); }
+    }
+    d->arena_bytes = off;
+    FAMG_TRY(dev_alloc(&d->arena, (int64_t)off));
+    CUDA_TRY(cudaMemset(d->arena, 0, off));
+    FAMG_TRY(dev_alloc(&d->d_p2p_err, 1));
+    CUDA_TRY(cudaMemset(d->d_p2p_err, 0, sizeof(int)));
+    // exchange IPC handles and layouts through NCCL all-gathers of raw bytes
+    const int rec = (int)sizeof(cudaIpcMemHandle_t);
+    const int lay = (int)(sizeof(long long) * (size_t)np * (3 + nr));
+    unsigned char *dbuf = nullptr;
+    FAMG_TRY(dev_alloc(&dbuf, (int64_t)(rec + lay) * (nr + 1)));
+    std::vector<unsigned char> mine((size_t)(rec + lay));
+    cudaIpcMemHandle_t hnd;
+    CUDA_TRY(cudaIpcGetMemHandle(&hnd, d->arena));
+    memcpy(mine.data(), &hnd, rec);
+    long long *tab = reinterpret_cast<long long *>(mine.data() + rec);
+    for (int i = 0; i < np; ++i) {
+        long long *row = tab + (size_t)i * (3 + nr);
+        row[0] = (long long)plans[i]->arena_flags; row[1] = (long long)plans[i]->arena_recv[0]; row[2] = (long long)plans[i]->arena_recv[1];
+        for (int p = 0; p < nr; ++p) row[3 + p] = plans[i]->recv_off[p];
+    }
+    unsigned char *dsend = dbuf + (size_t)(rec + lay) * nr;
+    CUDA_TRY(cudaMemcpy(dsend, mine.data(), mine.size(), cudaMemcpyHostToDevice));
+    NCCL_TRY(g_nccl.AllGather(dsend, dbuf, (size_t)(rec + lay), ncclInt8, cm->comm, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    std::vector<unsigned char> all((size_t)(rec + lay) * nr);
+    CUDA_TRY(cudaMemcpy(all.data(), dbuf, all.size(), cudaMemcpyDeviceToHost));
+    cudaFree(dbuf);
+    d->peer_arena.assign(nr, nullptr);
+    for (int p = 0; p < nr; ++p) {
+        if (p == me) { d->peer_arena[p] = d->arena; continue; }
+        cudaIpcMemHandle_t ph;
+        memcpy(&ph, all.data() + (size_t)(rec + lay) * p, rec);
+        cudaError_t e = cudaIpcOpenMemHandle(&d->peer_arena[p], ph, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { cudaGetLastError(); FAMG_FAIL(FAMG_ERR_COMM, "cudaIpcOpenMemHandle(rank %d) failed: %s", p, cudaGetErrorString(e)); }
+    }
+    for (int i = 0; i < np; ++i) {
+        HaloPlan *h = plans[i];
+        P2PPlanDev &v = h->dev;
+        v = P2PPlanDev{};
+        v.nghost = h->nghost;
+        v.epoch = reinterpret_cast<unsigned long long *>(d->arena + h->arena_flags) + nr;
+        v.done = reinterpret_cast<unsigned int *>(reinterpret_cast<unsigned long long *>(d->arena + h->arena_flags) + nr + 1);
+        v.total_send = h->total_send;
+        v.lrecv[0] = reinterpret_cast<const double *>(d->arena + h->arena_recv[0]);
+        v.lrecv[1] = reinterpret_cast<const double *>(d->arena + h->arena_recv[1]);
+        v.err = d->d_p2p_err;
+        for (int p = 0; p < nr; ++p) {
+            if (p == me || (h->send_cnt[p] == 0 && h->recv_cnt[p] == 0)) continue;
+            const long long *prow = reinterpret_cast<const long long *>(all.data() + (size_t)(rec + lay) * p + rec) + (size_t)i * (3 + nr);
+            unsigned char *pa = static_cast<unsigned char *>(d->peer_arena[p]);
+            const int nb = v.nnb++;
+            v.rdst[0][nb] = reinterpret_cast<double *>(pa + prow[1]) + prow[3 + me];
+            v.rdst[1][nb] = reinterpret_cast<double *>(pa + prow[2]) + prow[3 + me];
+            v.rflag[nb] = reinterpret_cast<unsigned long long *>(pa + prow[0]) + me;
+            v.lflag[nb] = reinterpret_cast<const unsigned long long *>(d->arena + h->arena_flags) + p;
+            v.soff[nb] = h->send_off[p]; v.scnt[nb] = h->send_cnt[p];
+        }
+        h->p2p = h->any && v.nnb > 0;
+    }
+    d->p2p = true;
+    return FAMG_OK;
+}
+
 static void dist_free(famg_dist_mg *d) {
+    for (size_t p = 0; p < d->peer_arena.size(); ++p)
+        if (d->peer_arena[p] && (int)p != d->comm->rank) cudaIpcCloseMemHandle(d->peer_arena[p]);
+    cudaFree(d->arena); cudaFree(d->d_p2p_err);
     for (auto &l : d->lv) {
         distop_free(l.A); distop_free(l.R); distop_free(l.P);
         cudaFree(l.d); cudaFree(l.x); cudaFree(l.b); cudaFree(l.t);
@@ -546,6 +749,22 @@ famg_status famg_dist_mg_create(famg_comm *c, famg_mg *gm, const int64_t *const 
     }
     cudaStreamSynchronize(ctx->stream);
     if (st != FAMG_OK) { dist_free(d); return st; }
+    {   // peer-memory halo exchange unless FAMG_HALO=nccl; every rank must reach the same decision
+        const char *mode = getenv("FAMG_HALO");
+        if (!(mode && !strcmp(mode, "nccl"))) {
+            famg_status ps = p2p_setup(d);
+            double ok = (ps == FAMG_OK && d->p2p) ? 1.0 : 0.0, all_ok = ok;
+            if (c->nranks > 1) {
+                double v[1] = {ok};
+                famg_status as = famg_comm_allreduce_sum(c, v, 1);
+                all_ok = (as == FAMG_OK && v[0] == (double)c->nranks) ? 1.0 : 0.0;
+            }
+            if (all_ok != 1.0) {  // somebody could not map a peer: everyone stays on NCCL send/recv
+                for (auto &L : d->lv) { L.A.halo.p2p = false; L.R.halo.p2p = false; L.P.halo.p2p = false; }
+                d->p2p = false;
+            }
+        }
+    }
     *out = d;
     return FAMG_OK;
 }
@@ -684,6 +903,11 @@ famg_status famg_dist_pcg_solve_dev(famg_dist_mg *d, famg_vec *x, const famg_vec
     }
     info->abs_residual = rn; info->rel_residual = rn / b_norm;
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (d->p2p) {
+        int perr = 0;
+        CUDA_TRY(cudaMemcpy(&perr, d->d_p2p_err, sizeof(int), cudaMemcpyDeviceToHost));
+        if (perr) FAMG_FAIL(FAMG_ERR_COMM, "peer-memory halo exchange timed out waiting for a neighbour rank");
+    }
     if (!converged) FAMG_FAIL(FAMG_ERR_NO_CONVERGENCE, "pcg: no convergence in %lld iterations (abs %.3e, rel %.3e)", (long long)max_iters, rn, rn / b_norm);
     return FAMG_OK;
 }

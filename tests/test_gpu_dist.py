@@ -11,12 +11,14 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+@pytest.mark.parametrize("halo", ["p2p", "nccl"])
 @pytest.mark.parametrize("dims,rep", [((32, 32, 32), 500), ((24, 20, 16), 100)])
-def test_two_rank_parity(dims, rep):
+def test_two_rank_parity(dims, rep, halo):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", "29517", os.path.join(ROOT, "scripts", "dist_check.py"), *map(str, dims), str(rep)]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    env = dict(os.environ, FAMG_HALO=halo)  # peer-memory (CUDA IPC) stores vs NCCL send/recv
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert "DIST_CHECK PASS" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
