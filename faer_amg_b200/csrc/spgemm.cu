@@ -172,12 +172,23 @@ __device__ void sg_row_fill(int i, int lane, const SgMat &a, const SgMat &b, int
 constexpr int SG_NCLS = 8;   // size classes per pass (see sg_plan)
 constexpr int SG_WARPS = 4;  // rows per CTA in the warp-per-row classes
 
-__global__ void sg_ub_kernel(SgMat a, SgMat b, int m, int *__restrict__ ub) {
+// ub_i = number of products of row i (work); size_i = min(ub_i, ncols(B)) bounds the distinct columns
+__global__ void sg_ub_kernel(SgMat a, SgMat b, int m, int ncols_b, int *__restrict__ ub, int *__restrict__ size) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
     long long s = 0;
     for (int q = a.rp[i]; q < a.rp[i + 1]; ++q) { const int k = a.col[q]; s += b.rp[k + 1] - b.rp[k]; }
-    ub[i] = s > 0x3fffffff ? 0x3fffffff : (int)s;
+    const int u = s > 0x3fffffff ? 0x3fffffff : (int)s;
+    ub[i] = u;
+    size[i] = min(u, ncols_b);
+}
+
+// pass-2 size: the exact row length, raised for rows with a lot of work per output entry so that
+// they get a whole CTA (the k loop is sequential per row; see sg_row_fill)
+__global__ void sg_size2_kernel(const int *__restrict__ row_nnz, const int *__restrict__ ub, int m, int *__restrict__ size) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    size[i] = max(row_nnz[i], min(ub[i] >> 4, 2048));
 }
 
 struct SgBounds { int limit[SG_NCLS]; };  // class c holds rows with size <= limit[c] (ascending; last = INT_MAX)
@@ -190,14 +201,24 @@ __global__ void sg_classify_kernel(const int *__restrict__ size, int m, SgBounds
     int c = 0;
     while (c < SG_NCLS - 1 && u > bnd.limit[c]) ++c;
     cls[i] = c;
-    atomicAdd(&class_count[c], 1);
+    // one atomic per (warp, class) instead of one per row
+    const unsigned active = __activemask();
+    const unsigned peers = __match_any_sync(active, c);
+    if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&class_count[c], __popc(peers));
     if (c == SG_NCLS - 1) atomicMax(max_size, u);
 }
 
 __global__ void sg_bin_kernel(const int *__restrict__ cls, int m, int *__restrict__ cursor, int *__restrict__ perm) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
-    perm[atomicAdd(&cursor[cls[i]], 1)] = i;
+    const int c = cls[i];
+    const unsigned active = __activemask();
+    const unsigned peers = __match_any_sync(active, c);
+    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&cursor[c], __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    perm[base + __popc(peers & ((1u << lane) - 1u))] = i;  // rows of a warp stay in ascending order
 }
 
 struct SgArgs {
@@ -236,6 +257,36 @@ __global__ void __launch_bounds__(256) sg_cta_kernel(SgArgs s) {
     else sg_row_count<256>(i, threadIdx.x, s.a, s.b, sg_smem, s.hmask, &s_cnt, s.row_nnz);
 }
 
+// Pass 1 for rows with many candidates when B is not too wide: distinct columns counted with a
+// bitmap of ncols(B) bits in shared memory (clearing ncols/8 bytes beats clearing a hash table of
+// 4 * 1.33 * ub bytes for the dense rows of coarse-level products).
+__global__ void __launch_bounds__(256) sg_bitmap_count_kernel(SgArgs s, int words) {
+    extern __shared__ __align__(16) int sg_smem[];
+    __shared__ int s_cnt;
+    unsigned *bm = reinterpret_cast<unsigned *>(sg_smem);
+    const int i = s.perm[blockIdx.x];
+    for (int t = threadIdx.x; t < words; t += 256) bm[t] = 0u;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    const int a0 = s.a.rp[i], a1 = s.a.rp[i + 1];
+    for (int q = a0 + (threadIdx.x >> 3); q < a1; q += 32) {
+        const int k = s.a.col[q];
+        const int b1 = s.b.rp[k + 1];
+        for (int p = s.b.rp[k] + (threadIdx.x & 7); p < b1; p += 8) {
+            const int j = s.b.col[p];
+            atomicOr(&bm[j >> 5], 1u << (j & 31));
+        }
+    }
+    __syncthreads();
+    int c = 0;
+    for (int t = threadIdx.x; t < words; t += 256) c += __popc(bm[t]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_cnt, c);
+    __syncthreads();
+    if (threadIdx.x == 0) s.row_nnz[i] = s_cnt;
+}
+
 template <bool FILL>
 __global__ void __launch_bounds__(256) sg_global_kernel(SgArgs s) {
     __shared__ int s_cnt;
@@ -262,8 +313,8 @@ static const SgClass SG_PASS2[SG_NCLS] = {{32, 64, 0},       {128, 256, 0},     
                                           {16384, 32768, 1}, {16384, 32768, 1}, {16384, 32768, 1}, {0x7fffffff, 0, 2}};
 
 template <bool FILL>
-static famg_status sg_run_pass(famg_ctx *ctx, SgArgs base, const int *d_size, int m, int *d_cls, int *d_perm, int *d_counters,
-                               int **scratch) {
+static famg_status sg_run_pass(famg_ctx *ctx, SgArgs base, const int *d_size, int m, int ncols_b, int *d_cls, int *d_perm,
+                               int *d_counters, int **scratch) {
     const SgClass *plan = FILL ? SG_PASS2 : SG_PASS1;
     SgBounds bnd;
     for (int c = 0; c < SG_NCLS; ++c) bnd.limit[c] = plan[c].limit;
@@ -290,6 +341,16 @@ static famg_status sg_run_pass(famg_ctx *ctx, SgArgs base, const int *d_size, in
         const int my_off = off;
         off += cnt;
         if (cnt == 0) continue;
+        const int bm_words = (ncols_b + 31) / 32;
+        if (!FILL && plan[c].kind >= 1 && (size_t)bm_words * 4 <= 160 * 1024) {
+            // big rows of the count pass: bitmap over the columns of B
+            const size_t smem = (size_t)bm_words * 4;
+            if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(sg_bitmap_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            sg_bitmap_count_kernel<<<(unsigned)cnt, 256, smem, ctx->stream>>>(s, bm_words);
+            count_launch(ctx);
+            KERNEL_CHECK();
+            continue;
+        }
         if (plan[c].kind == 2) { if (global_off < 0) global_off = my_off; global_count += cnt; continue; }
         s.hmask = plan[c].h - 1;
         const size_t per_row = (size_t)(FILL ? plan[c].h + plan[c].h / 2 : plan[c].h) * sizeof(int);
@@ -327,14 +388,14 @@ famg_status spgemm_impl(const famg_csr *a, const famg_csr *b, const famg_csr *p_
     famg_ctx *ctx = a->ctx;
     const int m = (int)a->nrows;
     SgMat A{a->row_ptr, a->col, a->val}, B{b->row_ptr, b->col, b->val};
-    // one pooled scratch block: ub | cls | perm | row_nnz(+1) | rp(+1) | counters(16)
-    const size_t words = (size_t)5 * (m + 2) + 32;
+    // one pooled scratch block: ub | size | cls | perm | row_nnz(+1) | rp(+1) | counters(16)
+    const size_t words = (size_t)6 * (m + 2) + 32;
     int *blk = nullptr, *scratch = nullptr;
     famg_csr *c = nullptr;
     famg_status st = pool_alloc(ctx, words * sizeof(int), (void **)&blk);
     if (st != FAMG_OK) return st;
-    int *ub = blk, *cls = ub + (m + 2), *perm = cls + (m + 2), *row_nnz = perm + (m + 2), *rp = row_nnz + (m + 2),
-        *counters = rp + (m + 2);
+    int *ub = blk, *size = ub + (m + 2), *cls = size + (m + 2), *perm = cls + (m + 2), *row_nnz = perm + (m + 2),
+        *rp = row_nnz + (m + 2), *counters = rp + (m + 2);
     auto cleanup = [&]() {
         pool_free(ctx, blk, words * sizeof(int));
         if (scratch) { cudaStreamSynchronize(ctx->stream); cudaFree(scratch); }
@@ -345,9 +406,9 @@ famg_status spgemm_impl(const famg_csr *a, const famg_csr *b, const famg_csr *p_
     base.ep.enabled = 0;
     int total = 0;
     if (m > 0) {
-        sg_ub_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, ctx->stream>>>(A, B, m, ub);
+        sg_ub_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, ctx->stream>>>(A, B, m, (int)b->ncols, ub, size);
         count_launch(ctx);
-        SG_TRY((sg_run_pass<false>(ctx, base, ub, m, cls, perm, counters, &scratch)));
+        SG_TRY((sg_run_pass<false>(ctx, base, size, m, (int)b->ncols, cls, perm, counters, &scratch)));
     }
     SG_TRY(exclusive_scan_i32(ctx, row_nnz, rp, m));
     {
@@ -364,7 +425,11 @@ famg_status spgemm_impl(const famg_csr *a, const famg_csr *b, const famg_csr *p_
         base.ep.p = SgMat{p_for_smoothing->row_ptr, p_for_smoothing->col, p_for_smoothing->val};
         base.ep.error_flag = err_flag;
     }
-    if (m > 0) SG_TRY((sg_run_pass<true>(ctx, base, row_nnz, m, cls, perm, counters, &scratch)));
+    if (m > 0) {
+        sg_size2_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, ctx->stream>>>(row_nnz, ub, m, size);
+        count_launch(ctx);
+        SG_TRY((sg_run_pass<true>(ctx, base, size, m, (int)b->ncols, cls, perm, counters, &scratch)));
+    }
     int h_err = 0;
     if (p_for_smoothing) {
         cudaError_t e = cudaMemcpyAsync(&h_err, err_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
