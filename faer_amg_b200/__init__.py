@@ -19,6 +19,7 @@ from .preconditioners.smoothers import (Diag, SmootherKind, StationaryIteration,
                                         smooth)
 from .solvers import (CgError, CgInfo, CgParams, conjugate_gradient, conjugate_gradient_dev, stationary_solver,  # noqa: F401
                       test_solver)
+from .adaptivity import ErrorPropogator  # noqa: F401
 from . import gallery  # noqa: F401
 
 __version__ = "0.1.0"

@@ -63,6 +63,7 @@ SIGNATURES = {
     "famg_vec_download": [vp, f64p, i64],
     "famg_vec_fill": [vp, f64],
     "famg_vec_copy": [vp, vp],
+    "famg_vec_axpby": [vp, f64, vp, f64],
     "famg_vec_ptr": [vp, vpp, i64p],
     "famg_vec_norm2": [vp, f64p],
     "famg_spmm": [vp, f64p, i64, f64p, i64, i64],

@@ -106,6 +106,10 @@ class DeviceMat:
     def copy_from(self, other: "DeviceMat"):
         call("famg_vec_copy", self._h, other._h)
 
+    def axpby(self, alpha: float, x: "DeviceMat", beta: float):
+        """self = alpha * x + beta * self."""
+        call("famg_vec_axpby", self._h, float(alpha), x._h, float(beta))
+
     def norm_l2(self) -> np.ndarray:
         out = np.empty(self.ncols)
         call("famg_vec_norm2", self._h, _f(out))

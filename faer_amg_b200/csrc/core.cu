@@ -547,6 +547,11 @@ famg_status famg_vec_copy(famg_vec *dst, const famg_vec *src) {
     CUDA_TRY(cudaSetDevice(dst->ctx->device));
     return vec_copy(dst->ctx, dst->p, dst->ld, src->p, src->ld, src->nrows, (int)src->ncols);
 }
+famg_status famg_vec_axpby(famg_vec *y, double alpha, const famg_vec *x, double beta) {
+    if (!y || !x || y->nrows != x->nrows || y->ncols != x->ncols) FAMG_FAIL(FAMG_ERR_INVALID, "shape mismatch");
+    CUDA_TRY(cudaSetDevice(y->ctx->device));
+    return vec_axpby(y->ctx, y->p, y->ld, x->p, x->ld, y->nrows, (int)y->ncols, alpha, beta);
+}
 famg_status famg_vec_ptr(const famg_vec *v, void **dev_ptr, int64_t *ld) {
     if (!v) FAMG_FAIL(FAMG_ERR_INVALID, "null vec");
     if (dev_ptr) *dev_ptr = v->p;

@@ -157,6 +157,19 @@ famg_status vec_add_inplace(famg_ctx *ctx, double *x, const double *y, int64_t n
     return FAMG_OK;
 }
 
+__global__ void __launch_bounds__(VT) axpby_kernel(double *__restrict__ y, long long ldy, const double *__restrict__ x, long long ldx,
+                                                   long long n, int k, double alpha, double beta) {
+    for (long long i = (long long)blockIdx.x * VT + threadIdx.x; i < n; i += (long long)gridDim.x * VT)
+        for (int c = 0; c < k; ++c) y[c * ldy + i] = alpha * x[c * ldx + i] + beta * y[c * ldy + i];
+}
+famg_status vec_axpby(famg_ctx *ctx, double *y, int64_t ldy, const double *x, int64_t ldx, int64_t n, int k, double alpha, double beta) {
+    if (n == 0 || k == 0) return FAMG_OK;
+    axpby_kernel<<<vec_grid(ctx, n), VT, 0, ctx->stream>>>(y, ldy, x, ldx, n, k, alpha, beta);
+    count_launch(ctx);
+    KERNEL_CHECK();
+    return FAMG_OK;
+}
+
 famg_status read_scalars(famg_ctx *ctx, int first, int count, double *host) {
     CUDA_TRY(cudaMemcpyAsync(ctx->h_scalars + first, ctx->d_scalars + first, sizeof(double) * count, cudaMemcpyDeviceToHost,
                              ctx->stream));

@@ -128,3 +128,14 @@ class StationaryIteration:
         io = DeviceMat.from_host(self.mat.ctx, rhs)
         self.apply_in_place_dev(io)
         return io.to_host()
+
+    def transpose_apply(self, rhs) -> np.ndarray:
+        """smoothers.rs:179-197: work1 = rhs; iters x { work2 = M work1; out = A work2; work1 -= out }."""
+        ctx = self.mat.ctx
+        w1 = DeviceMat.from_host(ctx, rhs)
+        w2, out = DeviceMat(ctx, w1.nrows, w1.ncols), DeviceMat(ctx, w1.nrows, w1.ncols)
+        for _ in range(self.iters):
+            self.prec.apply_dev(w2, w1)
+            self.mat.apply_dev(out, w2)
+            w1.axpby(-1.0, out, 1.0)
+        return w1.to_host()

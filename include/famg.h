@@ -103,6 +103,9 @@ famg_status famg_vec_upload(famg_vec *v, const double *host, int64_t ld);
 famg_status famg_vec_download(const famg_vec *v, double *host, int64_t ld);
 famg_status famg_vec_fill(famg_vec *v, double value);
 famg_status famg_vec_copy(famg_vec *dst, const famg_vec *src);
+/* y = alpha * x + beta * y (column by column; the vector algebra of ErrorPropogator::apply,
+ * adaptivity.rs:191-198, and StationaryIteration::transpose_apply, smoothers.rs:179-197) */
+famg_status famg_vec_axpby(famg_vec *y, double alpha, const famg_vec *x, double beta);
 /* raw device pointer + leading dimension (for CUDA-event timing harnesses / torch interop) */
 famg_status famg_vec_ptr(const famg_vec *v, void **dev_ptr, int64_t *ld);
 /* column-wise ||v_j||_2 into host `out` (ncols doubles) */

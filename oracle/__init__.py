@@ -322,6 +322,23 @@ def stationary_iteration(a: Csr, d, iters: int, x) -> np.ndarray:
     return x
 
 
+def stationary_iteration_transpose(a: Csr, d, iters: int, rhs) -> np.ndarray:
+    """StationaryIteration::transpose_apply (smoothers.rs:179-197) with a Diag preconditioner."""
+    w1 = _fcol(rhs).copy(order="F")
+    d = _f64(d).reshape(-1, 1)
+    for _ in range(iters):
+        w2 = d * w1
+        out = spmm_csr(a, w2)
+        w1 = w1 - out
+    return w1
+
+
+def error_propagator(a: Csr, precond_apply, x) -> np.ndarray:
+    """ErrorPropogator::apply (adaptivity.rs:191-198): x - M^-1 (A x)."""
+    x = _fcol(x)
+    return x - precond_apply(spmm_csr(a, x))
+
+
 # ----------------------------------------------------------------------------- multigrid
 SM_DIAG, SM_LLT, SM_BLOCK = 0, 1, 2
 PC_NONE, PC_DIAG, PC_MG = 0, 1, 2

@@ -151,6 +151,38 @@ def test_stationary_iteration_literal(ctx, F, variant):
     assert np.array_equal(got, O.stationary_iteration(o, O.new_l1(o), 3, nn))  # smoothers.rs:146-159
 
 
+def test_stationary_transpose_and_error_propagator(ctx, F):
+    o = O.gen_g7(9, 8, 7)
+    d = to_dev(ctx, o)
+    rng = np.random.default_rng(21)
+    x = rng.standard_normal((o.nrows, 3))
+    l1 = O.new_l1(o)
+    got = F.StationaryIteration(d, F.new_l1(d), 3).transpose_apply(x)
+    assert np.array_equal(got, O.stationary_iteration_transpose(o, l1, 3, x))       # smoothers.rs:179-197
+    e = F.ErrorPropogator(F.SparseMatOp(d), F.new_l1(d)).apply(x)
+    assert np.array_equal(e, O.error_propagator(o, lambda r: l1.reshape(-1, 1) * r, x))  # adaptivity.rs:191-198
+
+
+def test_degenerate_shapes(ctx, F):
+    """Empty operators, zero right-hand sides, a single huge row."""
+    empty = F.SparseRowMat.from_csr(ctx, 0, 0, [0], [], [])
+    assert empty.apply(np.zeros((0, 2))).shape == (0, 2) and empty.transpose().shape == (0, 0)
+    tall = F.SparseRowMat.from_csr(ctx, 3, 0, [0, 0, 0, 0], [], [])
+    assert np.array_equal(tall.apply(np.zeros((0, 1))), np.zeros((3, 1)))
+    assert (tall.transpose() @ tall).nnz == 0 and (tall.transpose() @ tall).shape == (0, 0)
+    rng = np.random.default_rng(22)
+    one = random_csr(rng, 1, 50000, [30000])
+    dv = to_dev(ctx, one)
+    x = rng.standard_normal((50000, 1))
+    assert_rel(dv.apply(x), O.spmm_csr(one, x), spmv_bound(one, x))
+    t = dv.transpose()
+    ot = O.transpose(one)
+    assert same_pattern(t, ot) and np.array_equal(t.to_host()[2], ot.val)
+    c = dv @ t                                          # 1 x 1 product with 30000 terms, one output entry
+    oc = O.spgemm(one, ot)
+    assert c.nnz == 1 and np.array_equal(c.to_host()[2], oc.val)
+
+
 def test_block_smoother(ctx, F):
     o = O.gen_g7(8, 6, 4)
     part, _ = F.geometric_partition((8, 6, 4))
