@@ -413,6 +413,18 @@ static famg_status dist_apply(famg_comm *cm, const DistOp &op, int epi, double *
         // pack -> interior rows -> wait+copy ghosts -> boundary rows, all on the compute stream: the
         // neighbours' stores land in this rank's arena while the interior kernel runs
         FAMG_TRY(p2p_begin(cm, op.halo, x_ext));
+        // Measured on 2 and 8 B200 (scripts/dist_bench.py): with peer-memory stores the ghosts arrive
+        // within a few microseconds, less than what splitting the apply into interior + boundary
+        // launches costs (persistent-kernel ramp/tail twice, one more dependency) -- even for the
+        // finest level.  The split is kept for operators above FAMG_SPLIT_MIN_ROWS (default: never).
+        static const int split_min_rows = getenv("FAMG_SPLIT_MIN_ROWS") ? atoi(getenv("FAMG_SPLIT_MIN_ROWS")) : 0x7fffffff;
+        if (nrows < split_min_rows) {
+            FAMG_TRY(p2p_end(cm, op.halo, x_ext));
+            g.dot_partials = dot_partials;
+            FAMG_TRY(spmv_launch(g, &n));
+            if (num_partials) *num_partials = n;
+            return FAMG_OK;
+        }
         if (op.ie > op.ib) {
             g.row_begin = op.ib; g.row_end = op.ie; g.dot_partials = dot_partials ? dot_partials + total : nullptr;
             FAMG_TRY(spmv_launch(g, &n)); total += n;
