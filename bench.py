@@ -126,10 +126,14 @@ def scale_sample(seconds, sample_iters, full_iters):
 
 
 def run_reference(args):
-    import oracle as O
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm runs on rank 0 alone and
+    # may use all the host threads it can (libgomp reads the variable when the oracle is loaded)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    import oracle as O
     threads = O.num_threads()
     full = golden_iters(args.n) or 16
     s = args.sample_iters
