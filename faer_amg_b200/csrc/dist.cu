@@ -892,7 +892,7 @@ famg_status famg_dist_pcg_solve_dev(famg_dist_mg *d, famg_vec *x, const famg_vec
         FAMG_TRY(vec_dot(ctx, r, z, n, slot_rtz));
         FAMG_TRY(allreduce_slots(cm, slot_rtz, 1));
         for (int64_t it = 0; it < max_iters; ++it) {
-            FAMG_TRY(ensure_partials(ctx, ceil_div(n, 256 / A.local->tpr) + 8));
+            FAMG_TRY(ensure_partials(ctx, n + 8));
             int np = 0;
             FAMG_TRY(dist_apply(cm, A, EPI_SPMV, p, q, nullptr, nullptr, ctx->d_partials, &np));
             FAMG_TRY(reduce_partials(ctx, ctx->d_partials, np, S_PTQ));

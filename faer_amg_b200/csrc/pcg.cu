@@ -83,8 +83,7 @@ famg_status famg_pcg_solve_dev(const famg_csr *a, int pc_kind, void *precond, fa
         for (int64_t it = 0; it < max_iters && st == FAMG_OK; ++it) {
             // q = A p, fused partial sums of p.q
             SpmvArgs g; g.a = a; g.epi = EPI_SPMV; g.x = p->p; g.ldx = p->ld; g.y = q->p; g.ldy = q->ld; g.k = 1;
-            const int64_t ctas = ceil_div(n, 256 / a->tpr);
-            st = ensure_partials(ctx, ctas);
+            st = ensure_partials(ctx, n + 8);  // one partial per CTA; never more CTAs than rows
             if (st != FAMG_OK) break;
             g.dot_partials = ctx->d_partials;
             int nct = 0;
