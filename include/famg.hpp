@@ -4,6 +4,7 @@
 // and error behaviour (reference panics -> famg::Error exceptions) so host code written against the
 // crate ports line by line.  Nothing here computes: every call forwards to libfamg.so.
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <memory>
 #include <stdexcept>
@@ -130,6 +131,173 @@ public:
 private:
     famg_mg *h_ = nullptr;
     int mu_ = 1, nu_ = 1;
+};
+
+
+// ---------------------------------------------------------------------------------------------
+// Device-resident dense block (faer Mat<f64>, column-major).
+class DeviceMat {
+public:
+    DeviceMat(const Context &ctx, int64_t nrows, int64_t ncols = 1) : nrows_(nrows), ncols_(ncols) { check(famg_vec_create(ctx.raw(), nrows, ncols, &h_)); }
+    ~DeviceMat() { famg_vec_destroy(h_); }
+    DeviceMat(const DeviceMat &) = delete;
+    famg_vec *raw() const { return h_; }
+    int64_t nrows() const { return nrows_; }
+    int64_t ncols() const { return ncols_; }
+    void upload(const double *host, int64_t ld) { check(famg_vec_upload(h_, host, ld)); }
+    void download(double *host, int64_t ld) const { check(famg_vec_download(h_, host, ld)); }
+    void fill(double v) { check(famg_vec_fill(h_, v)); }
+private:
+    famg_vec *h_ = nullptr;
+    int64_t nrows_, ncols_;
+};
+
+// partitioners/mod.rs Partition (the *output* of the host-side partitioner): aggregates in CSR
+// form, nodes ascending inside each aggregate (BTreeSet order).
+struct Partition {
+    std::vector<uint64_t> agg_ptr, agg_nodes;
+    int64_t naggs() const { return (int64_t)agg_ptr.size() - 1; }
+    int64_t nnodes() const { return (int64_t)agg_nodes.size(); }
+};
+
+// Deterministic geometric aggregates of a lexicographic nx*ny*nz grid (bx x by x bz boxes; a
+// trailing partial box joins its predecessor) -- the benchmark configurations' partitioner.
+inline Partition geometric_partition(const int64_t dims[3], const int64_t block[3], int64_t coarse_dims[3]) {
+    int64_t c[3];
+    for (int d = 0; d < 3; ++d) { c[d] = dims[d] / block[d] > 0 ? dims[d] / block[d] : 1; coarse_dims[d] = c[d]; }
+    const int64_t n = dims[0] * dims[1] * dims[2], na = c[0] * c[1] * c[2];
+    std::vector<uint64_t> count((size_t)na + 1, 0), agg((size_t)n);
+    for (int64_t z = 0; z < dims[2]; ++z)
+        for (int64_t y = 0; y < dims[1]; ++y)
+            for (int64_t x = 0; x < dims[0]; ++x) {
+                const int64_t ax = std::min(x / block[0], c[0] - 1), ay = std::min(y / block[1], c[1] - 1), az = std::min(z / block[2], c[2] - 1);
+                const int64_t a = ax + c[0] * (ay + c[1] * az);
+                agg[(size_t)(x + dims[0] * (y + dims[1] * z))] = (uint64_t)a;
+                ++count[(size_t)a + 1];
+            }
+    Partition p;
+    p.agg_ptr.assign(count.begin(), count.end());
+    for (int64_t a = 0; a < na; ++a) p.agg_ptr[(size_t)a + 1] += p.agg_ptr[(size_t)a];
+    p.agg_nodes.resize((size_t)n);
+    std::vector<uint64_t> fill(p.agg_ptr.begin(), p.agg_ptr.end() - 1);
+    for (int64_t i = 0; i < n; ++i) p.agg_nodes[(size_t)fill[(size_t)agg[(size_t)i]]++] = (uint64_t)i;  // ascending node order
+    return p;
+}
+
+// interpolation/mod.rs GalerkinCoarse (:34-40)
+struct GalerkinCoarse {
+    std::shared_ptr<SparseRowMat> interpolation, restriction, coarse_mat;
+    std::vector<double> coarse_nn;  // (naggs*cand) x k column-major
+    Partition partition;
+};
+
+// interpolation/mod.rs smoothed_aggregation (:730-836): tentative P (host SVDs), then
+// P = smooth^steps(P0), R = P^T, A_c = R (A P) on the device in one ABI call.
+inline GalerkinCoarse smoothed_aggregation(const Context &ctx, const SparseRowMat &fine, Partition partition, int64_t block_size,
+                                           const std::vector<double> &near_null, int64_t k, int64_t candidate_dimension,
+                                           int smoothing_steps) {
+    const int64_t n = fine.nrows();
+    GalerkinCoarse g;
+    g.coarse_nn.assign((size_t)(partition.naggs() * candidate_dimension * k), 0.0);
+    famg_csr *p0 = nullptr, *p = nullptr, *r = nullptr, *ac = nullptr;
+    check(famg_tentative_p(ctx.raw(), n, block_size, k, candidate_dimension, near_null.data(), n, partition.naggs(),
+                           partition.agg_ptr.data(), partition.agg_nodes.data(), &p0, g.coarse_nn.data()));
+    SparseRowMat tentative(p0);
+    check(famg_galerkin(fine.raw(), p0, smoothing_steps, 0.66, &p, &r, &ac));  // interpolation/mod.rs:811-828
+    g.interpolation = std::make_shared<SparseRowMat>(p);
+    g.restriction = std::make_shared<SparseRowMat>(r);
+    g.coarse_mat = std::make_shared<SparseRowMat>(ac);
+    g.partition = std::move(partition);
+    return g;
+}
+
+// hierarchy.rs HierarchyConfig / Hierarchy: the coarsen loop (:190-248) over the ABI.  The
+// partitioner is a callback (level, fine operator) -> Partition, because the reference's
+// PartitionerConfig is host-side graph logic outside the GPU path.
+struct HierarchyConfig {
+    int64_t coarsest_dim = 1000;          // hierarchy.rs:31
+    int64_t max_levels = INT64_MAX;
+    int smoothing_steps = 1;              // AggregationConfig, interpolation/mod.rs:72-79
+    int64_t candidate_dimension = 1;
+};
+
+class Hierarchy {
+public:
+    template <class Partitioner>
+    Hierarchy(const Context &ctx, std::shared_ptr<SparseRowMat> fine, std::vector<double> near_null, int64_t k, const HierarchyConfig &cfg,
+              Partitioner &&partitioner)
+        : config(cfg) {
+        operators.push_back(std::move(fine));
+        near_nulls.push_back(std::move(near_null));
+        int64_t level = 1, coarse_dim = INT64_MAX;
+        while (coarse_dim > cfg.coarsest_dim && level < cfg.max_levels) {                         // hierarchy.rs:199
+            const SparseRowMat &a = *operators.back();
+            GalerkinCoarse g = smoothed_aggregation(ctx, a, partitioner(level - 1, a), 1, near_nulls.back(), k, cfg.candidate_dimension,
+                                                    cfg.smoothing_steps);
+            coarse_dim = g.coarse_mat->nrows();
+            // coarse near-null: 3-step L1 stationary iteration on the device (:217-226), thin QR (:228)
+            auto l1 = new_l1(*g.coarse_mat);
+            DeviceMat nn(ctx, coarse_dim, k);
+            nn.upload(g.coarse_nn.data(), coarse_dim);
+            check(famg_stationary_iteration_dev(g.coarse_mat->raw(), l1->raw(), 3, nn.raw()));
+            nn.download(g.coarse_nn.data(), coarse_dim);
+            check(famg_thin_q(coarse_dim, k, g.coarse_nn.data(), coarse_dim));
+            add_level(std::move(g));
+            ++level;
+        }
+    }
+    // hierarchy.rs:250-271 (same shape asserts)
+    void add_level(GalerkinCoarse g) {
+        if (g.interpolation->nrows() != g.restriction->ncols() || g.interpolation->nrows() != operators.back()->nrows() ||
+            g.interpolation->ncols() != g.restriction->nrows() || g.interpolation->ncols() != g.coarse_mat->ncols())
+            throw Error(FAMG_ERR_INVALID, "add_level: interpolation / restriction do not match the operators");
+        operators.push_back(g.coarse_mat);
+        interpolations.push_back(g.interpolation);
+        restrictions.push_back(g.restriction);
+        partitions.push_back(std::move(g.partition));
+        near_nulls.push_back(std::move(g.coarse_nn));
+    }
+    size_t levels() const { return operators.size(); }
+    double op_complexity() const {  // hierarchy.rs:352-360
+        double total = 0;
+        for (auto &m : operators) total += (double)m->compute_nnz();
+        return total / (double)operators[0]->compute_nnz();
+    }
+    double grid_complexity() const {  // hierarchy.rs:346-350
+        double total = 0;
+        for (auto &m : operators) total += (double)m->nrows();
+        return total / (double)operators[0]->nrows();
+    }
+    std::vector<std::shared_ptr<SparseRowMat>> operators, interpolations, restrictions;
+    std::vector<Partition> partitions;
+    std::vector<std::vector<double>> near_nulls;
+    HierarchyConfig config;
+};
+
+// multigrid.rs MultigridConfig::build (:52-164) with a diagonal smoother on every level but the
+// coarsest (exact Cholesky solve), the wiring the reference does by hand in simple_geometric.rs.
+struct MultigridConfig {
+    int mu = 1, smoothing_steps = 1;
+    int smoother_kind = FAMG_DIAG_L1;
+    double omega = 0.66;
+    std::unique_ptr<Multigrid> build(const Hierarchy &h, std::vector<std::shared_ptr<Smoother>> &keep) const {
+        auto make = [&](const SparseRowMat &m, bool coarsest) {
+            famg_smoother *s = nullptr;
+            if (coarsest) check(famg_smoother_cholesky(m.raw(), &s));
+            else check(famg_smoother_diag(m.raw(), smoother_kind, omega, &s));
+            keep.push_back(std::make_shared<Smoother>(s));
+            return keep.back();
+        };
+        const size_t nl = h.levels();
+        auto s0 = make(*h.operators[0], nl == 1 ? false : false);
+        auto mg = std::make_unique<Multigrid>(*h.operators[0], *s0);
+        for (size_t l = 1; l < nl; ++l) {
+            auto s = make(*h.operators[l], l + 1 == nl);
+            mg->add_level(*h.operators[l], *s, *h.restrictions[l - 1], *h.interpolations[l - 1]);
+        }
+        mg->with_cycle_type(mu).with_smoothing_steps(smoothing_steps);
+        return mg;
+    }
 };
 
 struct CgParams { double abs_tolerance = 0.0, rel_tolerance = 1e-12; int64_t max_iters = 1000; bool zero_guess = true; };

@@ -1,5 +1,6 @@
 // Compiles and links the C++ mirror against libfamg.so; run on a GPU it solves a 1-D Poisson
 // problem with a two-level multigrid, without a GPU it must fail loudly (no CPU fallback).
+#include <cmath>
 #include <cstdio>
 #include <vector>
 
@@ -26,8 +27,36 @@ int main() {
         std::vector<double> b(n, 1.0), x(n, 0.0);
         famg::CgParams prm; prm.rel_tolerance = 1e-10;
         famg_cg_info info = famg::conjugate_gradient(x.data(), mg, *a, b.data(), prm);
-        std::printf("mirror ok: %lld iterations, rel residual %.2e\n", (long long)info.iter_count, info.rel_residual);
-        return info.rel_residual < 1e-10 ? 0 : 1;
+        if (!(info.rel_residual < 1e-10)) return 1;
+        std::printf("two-level 1-D: %lld iterations, rel residual %.2e\n", (long long)info.iter_count, info.rel_residual);
+
+        // the examples/amg call stack in C++: SparseMatOp -> HierarchyConfig::build (smoothed
+        // aggregation, GPU RAP) -> MultigridConfig::build -> conjugate_gradient, 3-D Poisson 32^3
+        const int64_t N = 32, dims0[3] = {N, N, N}, block[3] = {2, 2, 2};
+        famg_csr *raw = nullptr;
+        famg::check(famg_gallery_g7(ctx.raw(), N, N, N, &raw));
+        auto a3 = std::make_shared<famg::SparseRowMat>(raw);
+        famg::SparseMatOp op(a3, 1);
+        const int64_t rows = a3->nrows();
+        std::vector<double> nn((size_t)rows, 1.0 / std::sqrt((double)rows));
+        std::vector<std::vector<int64_t>> level_dims{{N, N, N}};
+        famg::HierarchyConfig hc;
+        famg::Hierarchy h(ctx, op.arc_mat(), nn, 1, hc, [&](int64_t level, const famg::SparseRowMat &) {
+            int64_t d[3] = {level_dims[(size_t)level][0], level_dims[(size_t)level][1], level_dims[(size_t)level][2]}, c[3];
+            famg::Partition part = famg::geometric_partition(d, block, c);
+            if ((int64_t)level_dims.size() == level + 1) level_dims.push_back({c[0], c[1], c[2]});
+            return part;
+        });
+        (void)dims0;
+        std::vector<std::shared_ptr<famg::Smoother>> keep;
+        auto mg3 = famg::MultigridConfig{}.build(h, keep);
+        std::vector<double> b3((size_t)rows, 1.0), x3((size_t)rows, 0.0);
+        famg::CgParams p3; p3.rel_tolerance = 1e-8;
+        famg_cg_info i3 = famg::conjugate_gradient(x3.data(), *mg3, *a3, b3.data(), p3);
+        std::printf("mirror ok: 32^3 hierarchy %zu levels, op complexity %.3f, %lld PCG iterations, rel residual %.2e\n", h.levels(),
+                    h.op_complexity(), (long long)i3.iter_count, i3.rel_residual);
+        // the oracle's count for this case is 15 (tests/golden/oracle_golden.json g7_32_l1)
+        return (i3.rel_residual < 1e-8 && i3.iter_count >= 14 && i3.iter_count <= 16 && h.levels() == 3) ? 0 : 1;
     } catch (const famg::Error &e) {
         std::printf("famg::Error %d: %s\n", e.status, e.what());
         return e.status == FAMG_ERR_CUDA ? 3 : 1;
