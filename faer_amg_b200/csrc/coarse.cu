@@ -30,6 +30,8 @@ famg_status dense_inverse_from_csr(const famg_csr *a, double **d_inv) {
         double *cj = &l[(size_t)j * n];
         cj[j] = d;
         for (int64_t i = j + 1; i < n; ++i) cj[i] /= d;
+        // trailing update: columns are independent (same arithmetic per entry in any thread count)
+#pragma omp parallel for schedule(static) if (n - j > 128)
         for (int64_t k = j + 1; k < n; ++k) {
             const double f = cj[k];
             if (f == 0.0) continue;
@@ -39,6 +41,7 @@ famg_status dense_inverse_from_csr(const famg_csr *a, double **d_inv) {
     }
     // inverse: solve L L^T X = I column by column (forward solve starts at the unit row)
     std::vector<double> inv((size_t)n * n, 0.0);
+#pragma omp parallel for schedule(dynamic, 8)
     for (int64_t c = 0; c < n; ++c) {
         double *x = &inv[(size_t)c * n];
         x[c] = 1.0;

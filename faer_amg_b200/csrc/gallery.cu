@@ -206,25 +206,34 @@ famg_status famg_tentative_p(famg_ctx *ctx, int64_t n_fine, int64_t block_size, 
         // scalar problems with one near-null vector (every BASELINE config): the thin SVD of an
         // m x 1 block is u = local/||local||, s = ||local||, v = 1 -- same operations, same bits as
         // the general path, without the per-aggregate temporaries
+        int bad = 0;
+        // aggregates are independent; each node is written by exactly one aggregate of a valid partition
+#pragma omp parallel for schedule(static) reduction(| : bad)
         for (int64_t g = 0; g < n_aggs; ++g) {
             const uint64_t b0 = agg_ptr[g], b1 = agg_ptr[g + 1];
-            if (b1 <= b0) FAMG_FAIL(FAMG_ERR_INVALID, "Agg size of 0 cannot support near-null dimension of 1");
+            if (b1 <= b0) { bad |= 1; continue; }
             double nn = 0.0;
+            bool ok = true;
             for (uint64_t t = b0; t < b1; ++t) {
                 const uint64_t node = agg_nodes[t];
-                if (node >= (uint64_t)n_fine || seen[(size_t)node]) FAMG_FAIL(FAMG_ERR_INVALID, "invalid partition");
-                seen[(size_t)node] = 1;
+                if (node >= (uint64_t)n_fine) { ok = false; break; }
                 const double x = near_null[node];
                 nn += x * x;
             }
+            if (!ok) { bad |= 2; continue; }
             const double sv = sqrt(nn);
             coarse_nn[g] = sv * 1.0;
             for (uint64_t t = b0; t < b1; ++t) {
                 const uint64_t node = agg_nodes[t];
                 ci[(size_t)node] = (int)g;
                 cv[(size_t)node] = sv > 0 ? near_null[node] / sv : 0.0;
+                seen[(size_t)node] += 1;  // one writer per node unless the partition is invalid (checked below)
             }
         }
+        if (bad & 1) FAMG_FAIL(FAMG_ERR_INVALID, "Agg size of 0 cannot support near-null dimension of 1");
+        if (bad & 2) FAMG_FAIL(FAMG_ERR_INVALID, "invalid partition");
+        for (int64_t i = 0; i < n_fine; ++i)
+            if (seen[(size_t)i] != 1) FAMG_FAIL(FAMG_ERR_INVALID, "invalid partition");
         return csr_from_host_i32(ctx, n_fine, nc, rp.data(), ci.data(), cv.data(), p);
     }
     for (int64_t g = 0; g < n_aggs; ++g) {
