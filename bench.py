@@ -188,12 +188,17 @@ def run_ours(args):
     t_gen = time.perf_counter() - t0
     rows = a.nrows
     nn = np.full((rows, 1), 1.0 / np.sqrt(rows))
-    t0 = time.perf_counter()
-    gp = F.GeometricPartitioner((n, n, n), tuple(int(v) for v in args.block.split(",")))
-    h = F.HierarchyConfig(1000, F.AggregationConfig(1, 1, gp)).build(F.SparseMatOp(a), nn)
-    mg = F.MultigridConfig(smoother="l1").build(h)
-    ctx.sync()
-    t_setup = time.perf_counter() - t0
+    def build_hierarchy():
+        t0 = time.perf_counter()
+        gp = F.GeometricPartitioner((n, n, n), tuple(int(v) for v in args.block.split(",")))
+        h = F.HierarchyConfig(1000, F.AggregationConfig(1, 1, gp)).build(F.SparseMatOp(a), nn)
+        mg = F.MultigridConfig(smoother="l1").build(h)
+        ctx.sync()
+        return gp, h, mg, time.perf_counter() - t0
+    # first build pays CUDA's lazy module loading of every setup kernel; the second is steady state
+    gp, h, mg, t_setup_cold = build_hierarchy()
+    del h, mg
+    gp, h, mg, t_setup = build_hierarchy()
     params = F.CgParams(0.0, REL_TOL, 1000)
 
     if world > 1:
@@ -279,7 +284,7 @@ def run_ours(args):
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": False, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args),
                 "pcg_iterations": iters, "rel_residual": infos[0].rel_residual, "levels": h.levels(),
-                "op_complexity": h.op_complexity(), "setup_ms": {"generate": t_gen * 1e3, "hierarchy_rap": t_setup * 1e3},
+                "op_complexity": h.op_complexity(), "setup_ms": {"generate": t_gen * 1e3, "hierarchy_rap": t_setup * 1e3, "hierarchy_rap_first_call": t_setup_cold * 1e3},
                 "mdof_per_s": rows / (ms_dev * 1e-3) / 1e6,
                 "e2e": {"value": ms_e2e, "unit": "ms", "h2d_bytes_per_step": 8 * nloc, "d2h_bytes_per_step": 8 * nloc,
                         "api": "famg_pcg_solve (host pointers, pinned)" if not dmg else "famg_dist_pcg_solve (host pointers, pinned)",
