@@ -409,8 +409,12 @@ def test_full_size_properties_128(ctx, F):
     u, v = rng.standard_normal(n), rng.standard_normal(n)
     au, av = a.apply(u).ravel(), a.apply(v).ravel()
     assert abs(v @ au - u @ av) <= 1e-12 * abs(v @ au)                             # symmetry
-    assert np.array_equal(a.apply(u + v).ravel() - au - av != 0, np.zeros(n, bool)) or \
-        np.max(np.abs(a.apply(u + v).ravel() - au - av)) <= 1e-12 * np.max(np.abs(au))  # linearity
+    assert np.max(np.abs(a.apply(u + v).ravel() - au - av)) <= 1e-12 * np.max(np.abs(au))   # linearity
+    x_int = np.zeros((n1, n1, n1)); x_int[1:-1, 1:-1, 1:-1] = rng.standard_normal((n1 - 2,) * 3)
+    lap = a.apply(x_int.ravel()).reshape(n1, n1, n1)[2:-2, 2:-2, 2:-2]                  # 7-point stencil, checked with numpy
+    ref = 6 * x_int[2:-2, 2:-2, 2:-2] - x_int[1:-3, 2:-2, 2:-2] - x_int[3:-1, 2:-2, 2:-2] - x_int[2:-2, 1:-3, 2:-2] \
+        - x_int[2:-2, 3:-1, 2:-2] - x_int[2:-2, 2:-2, 1:-3] - x_int[2:-2, 2:-2, 3:-1]
+    assert np.max(np.abs(lap - ref)) <= 1e-12 * np.max(np.abs(ref))
     nn = np.full((n, 1), 1.0 / np.sqrt(n))
     h = F.HierarchyConfig(1000, F.AggregationConfig(1, 1, F.GeometricPartitioner((n1,) * 3))).build(F.SparseMatOp(a), nn)
     assert [op.mat_ref().nrows for op in h.operators()] == [n, n // 8, n // 64, n // 512, n // 4096]
