@@ -96,6 +96,29 @@ struct P2PPlanDev {
     int *err;                                 // set on spin timeout
 };
 
+// Small collectives over the same arenas: sum-all-reduce of <= 4 doubles (PCG dot products) and the
+// all-gather of the restricted residual at the replicated-level transition.  Every rank stores its
+// contribution into every peer's slot, publishes the epoch, waits for all peers, then reduces in
+// rank order -- every rank forms bit-identical sums.
+constexpr int P2P_AR_WIDTH = 4;
+struct P2PCollDev {
+    int nranks, rank;
+    // all-reduce
+    double *ar_rslots[2][P2P_MAX_NB + 1];            // peer p's slot array (parity), indexed [rank*W + w]
+    unsigned long long *ar_rflag[P2P_MAX_NB + 1];    // my flag slot on peer p
+    const unsigned long long *ar_lflag;              // my flag array (one per peer)
+    const double *ar_lslots[2];
+    unsigned long long *ar_epoch;
+    // all-gather
+    double *ag_rbuf[2][P2P_MAX_NB + 1];              // peer p's gather buffer (parity)
+    unsigned long long *ag_rflag[P2P_MAX_NB + 1];
+    const unsigned long long *ag_lflag;
+    const double *ag_lbuf[2];
+    unsigned long long *ag_epoch;
+    unsigned int *ag_done;
+    int *err;
+};
+
 struct HaloPlan {
     bool p2p = false;
     P2PPlanDev dev{};
@@ -141,6 +164,8 @@ struct famg_dist_mg {
     std::vector<void *> peer_arena;  // IPC-mapped arenas of the other ranks
     int *d_p2p_err = nullptr;
     bool p2p = false;
+    famg::P2PCollDev coll{};
+    bool p2p_coll = false;
     // the distributed cycle (kernels on two streams + NCCL point-to-point / broadcast calls) is
     // captured into one CUDA graph per (out, rhs) pair and replayed; disabled on the first failure
     std::map<std::pair<const void *, const void *>, GraphEntry> graphs;
@@ -354,6 +379,64 @@ __global__ void __launch_bounds__(256) p2p_wait_kernel(const P2PPlanDev pl, doub
         ghost_tail[j] = __ldcg(src + j);  // bypass L1 (peer-written)
 }
 
+// sum-all-reduce of `count` (<= 4) doubles in scalars[first..]: one CTA of 32 threads per rank
+__global__ void __launch_bounds__(32) p2p_allreduce_kernel(const P2PCollDev c, double *__restrict__ scalars, int first, int count) {
+    const int lane = threadIdx.x;
+    const unsigned long long e = *c.ar_epoch + 1ull;
+    const int par = (int)(e & 1ull);
+    __syncwarp();
+    if (lane < c.nranks) {
+        double *dst = c.ar_rslots[par][lane] + c.rank * P2P_AR_WIDTH;  // lane == rank: my own arena
+        for (int w = 0; w < count; ++w) dst[w] = scalars[first + w];
+        __threadfence_system();
+        st_release_sys(c.ar_rflag[lane], e);
+        const unsigned long long t0 = global_timer_ns();
+        while (ld_acquire_sys(c.ar_lflag + lane) < e) {
+            if (global_timer_ns() - t0 > 2000000000ull) { atomicExch(c.err, 1); break; }
+        }
+    }
+    __syncwarp();
+    if (lane < count) {
+        const double *src = c.ar_lslots[par];
+        double sum = 0.0;
+        for (int r = 0; r < c.nranks; ++r) sum += __ldcg(src + r * P2P_AR_WIDTH + lane);  // rank order: same bits everywhere
+        scalars[first + lane] = sum;
+    }
+    if (lane == 0) *c.ar_epoch = e;
+}
+
+// all-gather: every rank stores its `cnt` entries at offset `off` of every rank's gather buffer
+__global__ void __launch_bounds__(256) p2p_allgather_push_kernel(const P2PCollDev c, const double *__restrict__ local, int off, int cnt) {
+    __shared__ bool s_last;
+    const unsigned long long e = *c.ag_epoch + 1ull;
+    const int par = (int)(e & 1ull);
+    for (int p = 0; p < c.nranks; ++p) {
+        double *dst = c.ag_rbuf[par][p] + off;
+        for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < cnt; j += gridDim.x * blockDim.x) dst[j] = local[j];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(c.ag_done, 1u) + 1u == gridDim.x;
+    __syncthreads();
+    if (s_last) {
+        __threadfence_system();
+        if (threadIdx.x < c.nranks) st_release_sys(c.ag_rflag[threadIdx.x], e);
+        if (threadIdx.x == 0) { *c.ag_done = 0u; *c.ag_epoch = e; }
+    }
+}
+__global__ void __launch_bounds__(256) p2p_allgather_wait_kernel(const P2PCollDev c, double *__restrict__ global, int n) {
+    const unsigned long long e = *c.ag_epoch;
+    if (threadIdx.x < c.nranks) {
+        const unsigned long long t0 = global_timer_ns();
+        while (ld_acquire_sys(c.ag_lflag + threadIdx.x) < e) {
+            if (global_timer_ns() - t0 > 2000000000ull) { atomicExch(c.err, 1); break; }
+        }
+    }
+    __syncthreads();
+    const double *src = c.ag_lbuf[e & 1ull];
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) global[j] = __ldcg(src + j);
+}
+
 static famg_status p2p_begin(famg_comm *cm, const HaloPlan &h, const double *x_ext) {
     const int grid = std::max(1, std::min(64, (h.total_send + 1023) / 1024));
     p2p_pack_kernel<<<grid, 256, 0, cm->ctx->stream>>>(h.dev, x_ext, h.d_send_idx);
@@ -464,10 +547,30 @@ static famg_status allreduce_slots(famg_comm *cm, int first, int count) {
     return FAMG_OK;
 }
 
+static famg_status dist_allreduce(famg_dist_mg *dm, int first, int count) {
+    famg_comm *cm = dm->comm;
+    if (cm->nranks == 1) return FAMG_OK;
+    if (dm->p2p_coll && count <= P2P_AR_WIDTH) {
+        p2p_allreduce_kernel<<<1, 32, 0, cm->ctx->stream>>>(dm->coll, cm->ctx->d_scalars, first, count);
+        count_launch(cm->ctx);
+        KERNEL_CHECK();
+        return FAMG_OK;
+    }
+    return allreduce_slots(cm, first, count);
+}
+
 // gather the owned pieces of a level vector into a replicated one
 static famg_status allgather_rows(famg_dist_mg *dm, int level, const double *local, double *global) {
     famg_comm *cm = dm->comm;
     const auto &sp = dm->splits[level];
+    if (dm->p2p_coll && cm->nranks > 1 && level == dm->lrep) {
+        const int cnt = (int)(sp[cm->rank + 1] - sp[cm->rank]), n = (int)sp[cm->nranks];
+        p2p_allgather_push_kernel<<<std::max(1, std::min(32, (cnt + 1023) / 1024)), 256, 0, cm->ctx->stream>>>(dm->coll, local, (int)sp[cm->rank], cnt);
+        p2p_allgather_wait_kernel<<<std::max(1, std::min(32, (n + 1023) / 1024)), 256, 0, cm->ctx->stream>>>(dm->coll, global, n);
+        count_launch(cm->ctx, 2);
+        KERNEL_CHECK();
+        return FAMG_OK;
+    }
     if (cm->nranks == 1) {
         CUDA_TRY(cudaMemcpyAsync(global, local, sizeof(double) * (sp[1] - sp[0]), cudaMemcpyDeviceToDevice, cm->ctx->stream));
         return FAMG_OK;
@@ -554,6 +657,15 @@ static famg_status p2p_setup(famg_dist_mg *d) {
         h->arena_flags = off; off = align(off + sizeof(unsigned long long) * (nr + 2));
         for (int b = 0; b < 2; ++b) { h->arena_recv[b] = off; off = align(off + sizeof(double) * (size_t)std::max(h->nghost, 1)); }
     }
+    // collective regions: all-reduce [flags nr | epoch | pad][slots0][slots1], all-gather [flags nr | epoch | done][buf0][buf1]
+    const size_t n_rep = (size_t)d->global->lv[d->lrep].a->nrows;
+    size_t coll_off[6];
+    coll_off[0] = off; off = align(off + sizeof(unsigned long long) * (nr + 2));
+    coll_off[1] = off; off = align(off + sizeof(double) * (size_t)nr * P2P_AR_WIDTH);
+    coll_off[2] = off; off = align(off + sizeof(double) * (size_t)nr * P2P_AR_WIDTH);
+    coll_off[3] = off; off = align(off + sizeof(unsigned long long) * (nr + 2));
+    coll_off[4] = off; off = align(off + sizeof(double) * (n_rep + 2));
+    coll_off[5] = off; off = align(off + sizeof(double) * (n_rep + 2));
     d->arena_bytes = off;
     FAMG_TRY(dev_alloc(&d->arena, (int64_t)off));
     CUDA_TRY(cudaMemset(d->arena, 0, off));
@@ -561,14 +673,15 @@ static famg_status p2p_setup(famg_dist_mg *d) {
     CUDA_TRY(cudaMemset(d->d_p2p_err, 0, sizeof(int)));
     // exchange IPC handles and layouts through NCCL all-gathers of raw bytes
     const int rec = (int)sizeof(cudaIpcMemHandle_t);
-    const int lay = (int)(sizeof(long long) * (size_t)np * (3 + nr));
+    const int lay = (int)(sizeof(long long) * ((size_t)np * (3 + nr) + 8));  // plan rows + 8-word header (collective offsets)
     unsigned char *dbuf = nullptr;
     FAMG_TRY(dev_alloc(&dbuf, (int64_t)(rec + lay) * (nr + 1)));
     std::vector<unsigned char> mine((size_t)(rec + lay));
     cudaIpcMemHandle_t hnd;
     CUDA_TRY(cudaIpcGetMemHandle(&hnd, d->arena));
     memcpy(mine.data(), &hnd, rec);
-    long long *tab = reinterpret_cast<long long *>(mine.data() + rec);
+    long long *tab = reinterpret_cast<long long *>(mine.data() + rec) + 8;
+    for (int w = 0; w < 6; ++w) tab[w - 8] = (long long)coll_off[w];
     for (int i = 0; i < np; ++i) {
         long long *row = tab + (size_t)i * (3 + nr);
         row[0] = (long long)plans[i]->arena_flags; row[1] = (long long)plans[i]->arena_recv[0]; row[2] = (long long)plans[i]->arena_recv[1];
@@ -602,7 +715,7 @@ static famg_status p2p_setup(famg_dist_mg *d) {
         v.err = d->d_p2p_err;
         for (int p = 0; p < nr; ++p) {
             if (p == me || (h->send_cnt[p] == 0 && h->recv_cnt[p] == 0)) continue;
-            const long long *prow = reinterpret_cast<const long long *>(all.data() + (size_t)(rec + lay) * p + rec) + (size_t)i * (3 + nr);
+            const long long *prow = reinterpret_cast<const long long *>(all.data() + (size_t)(rec + lay) * p + rec) + 8 + (size_t)i * (3 + nr);
             unsigned char *pa = static_cast<unsigned char *>(d->peer_arena[p]);
             const int nb = v.nnb++;
             v.rdst[0][nb] = reinterpret_cast<double *>(pa + prow[1]) + prow[3 + me];
@@ -612,6 +725,31 @@ static famg_status p2p_setup(famg_dist_mg *d) {
             v.soff[nb] = h->send_off[p]; v.scnt[nb] = h->send_cnt[p];
         }
         h->p2p = h->any && v.nnb > 0;
+    }
+    {   // collective descriptors
+        P2PCollDev &c = d->coll;
+        c = P2PCollDev{};
+        c.nranks = nr; c.rank = me; c.err = d->d_p2p_err;
+        for (int p = 0; p < nr; ++p) {
+            const long long *hdr = reinterpret_cast<const long long *>(all.data() + (size_t)(rec + lay) * p + rec);
+            unsigned char *pa = static_cast<unsigned char *>(d->peer_arena[p]);
+            c.ar_rslots[0][p] = reinterpret_cast<double *>(pa + hdr[1]);
+            c.ar_rslots[1][p] = reinterpret_cast<double *>(pa + hdr[2]);
+            c.ar_rflag[p] = reinterpret_cast<unsigned long long *>(pa + hdr[0]) + me;
+            c.ag_rbuf[0][p] = reinterpret_cast<double *>(pa + hdr[4]);
+            c.ag_rbuf[1][p] = reinterpret_cast<double *>(pa + hdr[5]);
+            c.ag_rflag[p] = reinterpret_cast<unsigned long long *>(pa + hdr[3]) + me;
+        }
+        c.ar_lflag = reinterpret_cast<const unsigned long long *>(d->arena + coll_off[0]);
+        c.ar_epoch = reinterpret_cast<unsigned long long *>(d->arena + coll_off[0]) + nr;
+        c.ar_lslots[0] = reinterpret_cast<const double *>(d->arena + coll_off[1]);
+        c.ar_lslots[1] = reinterpret_cast<const double *>(d->arena + coll_off[2]);
+        c.ag_lflag = reinterpret_cast<const unsigned long long *>(d->arena + coll_off[3]);
+        c.ag_epoch = reinterpret_cast<unsigned long long *>(d->arena + coll_off[3]) + nr;
+        c.ag_done = reinterpret_cast<unsigned int *>(reinterpret_cast<unsigned long long *>(d->arena + coll_off[3]) + nr + 1);
+        c.ag_lbuf[0] = reinterpret_cast<const double *>(d->arena + coll_off[4]);
+        c.ag_lbuf[1] = reinterpret_cast<const double *>(d->arena + coll_off[5]);
+        d->p2p_coll = getenv("FAMG_P2P_COLL") ? atoi(getenv("FAMG_P2P_COLL")) != 0 : true;
     }
     d->p2p = true;
     return FAMG_OK;
@@ -773,7 +911,7 @@ famg_status famg_dist_mg_create(famg_comm *c, famg_mg *gm, const int64_t *const 
             }
             if (all_ok != 1.0) {  // somebody could not map a peer: everyone stays on NCCL send/recv
                 for (auto &L : d->lv) { L.A.halo.p2p = false; L.R.halo.p2p = false; L.P.halo.p2p = false; }
-                d->p2p = false;
+                d->p2p = false; d->p2p_coll = false;
             }
         }
     }
@@ -868,7 +1006,7 @@ famg_status famg_dist_pcg_solve_dev(famg_dist_mg *d, famg_vec *x, const famg_vec
     enum { S_BB = 0, S_RR = 1, S_PTQ = 2, S_RTZ_A = 3, S_RTZ_B = 4 };
     double h[8];
     FAMG_TRY(vec_dot(ctx, b->p, b->p, n, S_BB));
-    FAMG_TRY(allreduce_slots(cm, S_BB, 1));
+    FAMG_TRY(dist_allreduce(d, S_BB, 1));
     FAMG_TRY(read_scalars(ctx, S_BB, 1, h));
     const double b_norm = sqrt(h[0]);
     if (b_norm == 0.0) return famg_vec_fill(x, 0.0);
@@ -881,7 +1019,7 @@ famg_status famg_dist_pcg_solve_dev(famg_dist_mg *d, famg_vec *x, const famg_vec
         FAMG_TRY(dist_apply(cm, A, EPI_RESID, xe, r, b->p, nullptr, nullptr, nullptr));
     }
     FAMG_TRY(vec_dot(ctx, r, r, n, S_RR));
-    FAMG_TRY(allreduce_slots(cm, S_RR, 1));
+    FAMG_TRY(dist_allreduce(d, S_RR, 1));
     FAMG_TRY(read_scalars(ctx, S_RR, 1, h));
     double rn = sqrt(h[0]);
     bool converged = rn < thr;
@@ -890,15 +1028,15 @@ famg_status famg_dist_pcg_solve_dev(famg_dist_mg *d, famg_vec *x, const famg_vec
         FAMG_TRY(dist_precond(d, z, r));
         FAMG_TRY(vec_copy(ctx, p, ld, z, ld, n, 1));
         FAMG_TRY(vec_dot(ctx, r, z, n, slot_rtz));
-        FAMG_TRY(allreduce_slots(cm, slot_rtz, 1));
+        FAMG_TRY(dist_allreduce(d, slot_rtz, 1));
         for (int64_t it = 0; it < max_iters; ++it) {
             FAMG_TRY(ensure_partials(ctx, n + 8));
             int np = 0;
             FAMG_TRY(dist_apply(cm, A, EPI_SPMV, p, q, nullptr, nullptr, ctx->d_partials, &np));
             FAMG_TRY(reduce_partials(ctx, ctx->d_partials, np, S_PTQ));
-            FAMG_TRY(allreduce_slots(cm, S_PTQ, 1));
+            FAMG_TRY(dist_allreduce(d, S_PTQ, 1));
             FAMG_TRY(pcg_update_xr(ctx, x->p, r, p, q, n, slot_rtz, S_PTQ, S_RR));
-            FAMG_TRY(allreduce_slots(cm, S_RR, 1));
+            FAMG_TRY(dist_allreduce(d, S_RR, 1));
             FAMG_TRY(read_scalars(ctx, S_RR, 4, h));
             const double ptq = h[S_PTQ - S_RR], rtz = h[slot_rtz - S_RR];
             if (!(ptq > 0.0) || !(rtz > 0.0))
@@ -908,7 +1046,7 @@ famg_status famg_dist_pcg_solve_dev(famg_dist_mg *d, famg_vec *x, const famg_vec
             if (rn < thr) { converged = true; break; }
             FAMG_TRY(dist_precond(d, z, r));
             FAMG_TRY(vec_dot(ctx, r, z, n, slot_rtz_new));
-            FAMG_TRY(allreduce_slots(cm, slot_rtz_new, 1));
+            FAMG_TRY(dist_allreduce(d, slot_rtz_new, 1));
             FAMG_TRY(pcg_update_p(ctx, p, z, n, slot_rtz_new, slot_rtz));
             std::swap(slot_rtz, slot_rtz_new);
         }
