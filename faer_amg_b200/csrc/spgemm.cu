@@ -113,19 +113,33 @@ __device__ void sg_row_fill(int i, int lane, const SgMat &a, const SgMat &b, int
     for (int t = lane; t < n; t += GROUP) vals[t] = 0.0;
     group_sync<GROUP>();
     // numeric: ascending k, lanes over the entries of B_k (each j unique within one k => no races)
+    // The loop is latency-bound (a.col[q] -> b.rp[k] -> b.col[p] are dependent loads and every k ends
+    // in a group barrier), so the next k's row bounds and this lane's first entry of B_k are fetched
+    // one iteration ahead.
     const int a0 = a.rp[i], a1 = a.rp[i + 1];
+    int k_n = 0, b0_n = 0, b1_n = 0, j_n = 0;
+    double av_n = 0.0, bv_n = 0.0;
+    if (a0 < a1) {
+        k_n = a.col[a0]; av_n = a.val[a0]; b0_n = b.rp[k_n]; b1_n = b.rp[k_n + 1];
+        if (b0_n + lane < b1_n) { j_n = b.col[b0_n + lane]; bv_n = b.val[b0_n + lane]; }
+    }
     for (int q = a0; q < a1; ++q) {
-        const int k = a.col[q];
-        const double av = a.val[q];
-        const int b1 = b.rp[k + 1];
-        for (int p = b.rp[k] + lane; p < b1; p += GROUP) {
-            const int j = b.col[p];
+        const double av = av_n;
+        const int b0 = b0_n, b1 = b1_n;
+        int j = j_n;
+        double bv = bv_n;
+        if (q + 1 < a1) {  // prefetch iteration q+1
+            k_n = a.col[q + 1]; av_n = a.val[q + 1]; b0_n = b.rp[k_n]; b1_n = b.rp[k_n + 1];
+            if (b0_n + lane < b1_n) { j_n = b.col[b0_n + lane]; bv_n = b.val[b0_n + lane]; }
+        }
+        for (int p = b0 + lane; p < b1; p += GROUP) {
+            if (p != b0 + lane) { j = b.col[p]; bv = b.val[p]; }
             int lo = 0, hi = n;
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
                 if (list[mid] < j) lo = mid + 1; else hi = mid;
             }
-            vals[lo] = vals[lo] + av * b.val[p];
+            vals[lo] = vals[lo] + av * bv;
         }
         group_sync<GROUP>();
     }
@@ -170,6 +184,7 @@ __device__ void sg_row_fill(int i, int lane, const SgMat &a, const SgMat &b, int
 
 // ---- kernels ------------------------------------------------------------------------------
 constexpr int SG_NCLS = 8;   // size classes per pass (see sg_plan)
+constexpr int SG_TINY = 32;  // rows with at most this many products: one thread per row
 constexpr int SG_WARPS = 4;  // rows per CTA in the warp-per-row classes
 
 // ub_i = number of products of row i (work); size_i = min(ub_i, ncols(B)) bounds the distinct columns
@@ -180,7 +195,8 @@ __global__ void sg_ub_kernel(SgMat a, SgMat b, int m, int ncols_b, int *__restri
     for (int q = a.rp[i]; q < a.rp[i + 1]; ++q) { const int k = a.col[q]; s += b.rp[k + 1] - b.rp[k]; }
     const int u = s > 0x3fffffff ? 0x3fffffff : (int)s;
     ub[i] = u;
-    size[i] = min(u, ncols_b);
+    // rows with a lot of products get a whole CTA in the count pass even when B is narrow
+    size[i] = u > 3072 ? max(min(u, ncols_b), 3073) : min(u, ncols_b);
 }
 
 // pass-2 size: the exact row length, raised for rows with a lot of work per output entry so that
@@ -188,7 +204,8 @@ __global__ void sg_ub_kernel(SgMat a, SgMat b, int m, int ncols_b, int *__restri
 __global__ void sg_size2_kernel(const int *__restrict__ row_nnz, const int *__restrict__ ub, int m, int *__restrict__ size) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
-    size[i] = max(row_nnz[i], min(ub[i] >> 4, 2048));
+    // ub <= SG_TINY: scalar class (size 0); otherwise at least 1 so that the row lands in a table class
+    size[i] = ub[i] <= SG_TINY ? 0 : max(max(row_nnz[i], 1), min(ub[i] >> 4, 2048));
 }
 
 struct SgBounds { int limit[SG_NCLS]; };  // class c holds rows with size <= limit[c] (ascending; last = INT_MAX)
@@ -230,6 +247,58 @@ struct SgArgs {
     SgEpilogue ep;
     int *g_table; int *g_list;    // global-table class scratch (per CTA slices)
 };
+
+// ---- tiny rows (ub <= SG_TINY): one THREAD per row.  A warp-per-row walk of a 7-product row is a
+// chain of dependent loads with one lane busy; here 32 rows are in flight per warp.  The sorted key
+// list lives in local memory; products are inserted / accumulated in ascending k, so pattern and
+// values are the same as in the table kernels.
+template <bool FILL>
+__global__ void __launch_bounds__(128) sg_scalar_kernel(SgArgs s) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= s.count) return;
+    const int i = s.perm[idx];
+    int keys[SG_TINY];
+    double vals[FILL ? SG_TINY : 1];
+    int n = 0;
+    const int a0 = s.a.rp[i], a1 = s.a.rp[i + 1];
+    for (int q = a0; q < a1; ++q) {
+        const int k = s.a.col[q];
+        const double av = FILL ? s.a.val[q] : 0.0;
+        const int b1 = s.b.rp[k + 1];
+        for (int p = s.b.rp[k]; p < b1; ++p) {
+            const int j = s.b.col[p];
+            int pos = 0;
+            while (pos < n && keys[pos] < j) ++pos;
+            if (pos < n && keys[pos] == j) {
+                if (FILL) vals[pos] = vals[pos] + av * s.b.val[p];
+            } else {
+                for (int t = n; t > pos; --t) { keys[t] = keys[t - 1]; if (FILL) vals[t] = vals[t - 1]; }
+                keys[pos] = j;
+                if (FILL) vals[pos] = 0.0 + av * s.b.val[p];
+                ++n;
+            }
+        }
+    }
+    if (!FILL) { s.row_nnz[i] = n; return; }
+    const int base = s.c_rp[i];
+    if (!s.ep.enabled) {
+        for (int t = 0; t < n; ++t) { s.c_col[base + t] = keys[t]; s.c_val[base + t] = vals[t]; }
+        return;
+    }
+    double dv = 0.0; bool found = false;
+    for (int q = a0; q < a1; ++q) if (s.a.col[q] == i) { dv = s.a.val[q]; found = true; break; }
+    if (!found || !(dv > 1e-6)) atomicMax(s.ep.error_flag, 1);
+    const double scalar = s.ep.omega * (1.0 / dv);
+    const int p0 = s.ep.p.rp[i], p1 = s.ep.p.rp[i + 1];
+    int matched = 0, pp = p0;
+    for (int t = 0; t < n; ++t) {
+        double v = vals[t] * -scalar;
+        while (pp < p1 && s.ep.p.col[pp] < keys[t]) ++pp;
+        if (pp < p1 && s.ep.p.col[pp] == keys[t]) { v = v + s.ep.p.val[pp]; ++matched; }
+        s.c_col[base + t] = keys[t]; s.c_val[base + t] = v;
+    }
+    if (matched != p1 - p0) atomicMax(s.ep.error_flag, 2);
+}
 
 // one warp per row; dynamic shared memory: per warp (hmask+1) ints (+ half as many for the list)
 template <bool FILL>
@@ -307,9 +376,9 @@ __global__ void __launch_bounds__(256) sg_global_kernel(SgArgs s) {
 struct SgClass { int limit, h, kind; };
 // Only the last class is open-ended (it alone tracks the maximum row size for its table); unused
 // slots repeat the previous limit so that nothing falls into them.
-static const SgClass SG_PASS1[SG_NCLS] = {{48, 64, 0},       {192, 256, 0},     {768, 1024, 0},    {3072, 4096, 0},
+static const SgClass SG_PASS1[SG_NCLS] = {{SG_TINY, 0, 3},  {192, 256, 0},     {768, 1024, 0},    {3072, 4096, 0},
                                           {12288, 16384, 1}, {12288, 16384, 1}, {12288, 16384, 1}, {0x7fffffff, 0, 2}};
-static const SgClass SG_PASS2[SG_NCLS] = {{32, 64, 0},       {128, 256, 0},     {512, 1024, 0},    {2048, 4096, 1},
+static const SgClass SG_PASS2[SG_NCLS] = {{0, 0, 3},        {128, 256, 0},     {512, 1024, 0},    {2048, 4096, 1},
                                           {16384, 32768, 1}, {16384, 32768, 1}, {16384, 32768, 1}, {0x7fffffff, 0, 2}};
 
 template <bool FILL>
@@ -352,6 +421,12 @@ static famg_status sg_run_pass(famg_ctx *ctx, SgArgs base, const int *d_size, in
             continue;
         }
         if (plan[c].kind == 2) { if (global_off < 0) global_off = my_off; global_count += cnt; continue; }
+        if (plan[c].kind == 3) {  // tiny rows: one thread per row
+            sg_scalar_kernel<FILL><<<(unsigned)ceil_div(cnt, 128), 128, 0, ctx->stream>>>(s);
+            count_launch(ctx);
+            KERNEL_CHECK();
+            continue;
+        }
         s.hmask = plan[c].h - 1;
         const size_t per_row = (size_t)(FILL ? plan[c].h + plan[c].h / 2 : plan[c].h) * sizeof(int);
         if (plan[c].kind == 0) {
