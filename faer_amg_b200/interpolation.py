@@ -32,8 +32,9 @@ def tentative_prolongator(ctx, n_fine: int, partition: Partition, near_null, can
     """interpolation/mod.rs:747-809: per-aggregate thin SVD of the near-null block (host, tiny),
     P uploaded as device CSR.  Returns (P, coarse_near_null)."""
     nn = as_colmajor(near_null)
-    ap = np.ascontiguousarray(partition.agg_ptr, dtype=np.uint64)
-    an = np.ascontiguousarray(partition.agg_nodes, dtype=np.uint64)
+    # Partition keeps non-negative int64 arrays: same bits as the ABI's usize, passed without a copy
+    ap = np.ascontiguousarray(partition.agg_ptr, dtype=np.int64)
+    an = np.ascontiguousarray(partition.agg_nodes, dtype=np.int64)
     coarse_nn = np.zeros((partition.naggs() * candidate_dimension, nn.shape[1]), order="F")
     h = vp()
     call("famg_tentative_p", ctx._h, n_fine, block_size, nn.shape[1], candidate_dimension, _f(nn), max(nn.shape[0], 1),

@@ -20,8 +20,8 @@ class BlockSmoother(Smoother):
     def new(cls, op: SparseMatOp, partition: Partition) -> "BlockSmoother":
         if op.block_size() != 1:
             raise NotImplementedError("vector block size > 1 (diagonally_compensate_vector) is not built yet")
-        ap = np.ascontiguousarray(partition.agg_ptr, dtype=np.uint64)
-        an = np.ascontiguousarray(partition.agg_nodes, dtype=np.uint64)
+        ap = np.ascontiguousarray(partition.agg_ptr, dtype=np.int64)   # same bits as usize, no copy
+        an = np.ascontiguousarray(partition.agg_nodes, dtype=np.int64)
         h = vp()
         call("famg_smoother_block", op.mat_ref()._h, partition.naggs(), ap.ctypes.data_as(u64p), an.ctypes.data_as(u64p), C.byref(h))
         s = cls(op.mat_ref().ctx, h)
