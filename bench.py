@@ -337,7 +337,7 @@ def main():
     ap.add_argument("--grid", "--n", dest="n", type=int, default=256,
                     help="grid points per dimension (use --grid under torchrun: its parser treats --n as an abbreviation)")
     ap.add_argument("--sample-iters", type=int, default=2, help="PCG iterations per CPU sample")
-    ap.add_argument("--replicate-below", type=int, default=32768, help="rows per rank under which a level is replicated")
+    ap.add_argument("--replicate-below", type=int, default=4096, help="rows per rank under which a level is replicated")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--stencil", type=int, default=7, choices=[7, 27], help="7-point Poisson (headline) or 27-point anisotropic diffusion")
     ap.add_argument("--block", default="2,2,2", help="geometric aggregate box")

@@ -437,6 +437,50 @@ __global__ void __launch_bounds__(256) p2p_allgather_wait_kernel(const P2PCollDe
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) global[j] = __ldcg(src + j);
 }
 
+// Unsplit applies: pack and wait+copy in ONE launch (<= 64 co-resident CTAs).  Every CTA stores
+// its slice into the neighbours' buffers; the last one to finish publishes the epoch; then every CTA
+// acquire-spins on this rank's own flags and moves its slice of the ghosts into the vector tail.
+__global__ void __launch_bounds__(256) p2p_exchange_kernel(const P2PPlanDev pl, double *__restrict__ x_ext, int nloc,
+                                                           const int *__restrict__ send_idx) {
+    __shared__ bool s_last;
+    const unsigned long long e = *pl.epoch + 1ull;
+    const int par = (int)(e & 1ull);
+    const int stride = gridDim.x * blockDim.x;
+    for (int nb = 0; nb < pl.nnb; ++nb) {
+        double *dst = pl.rdst[par][nb];
+        const int *idx = send_idx + pl.soff[nb];
+        for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < pl.scnt[nb]; j += stride) dst[j] = x_ext[idx[j]];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(pl.done, 1u) + 1u == gridDim.x;
+    __syncthreads();
+    if (s_last) {
+        __threadfence_system();
+        if (threadIdx.x < pl.nnb) st_release_sys(pl.rflag[threadIdx.x], e);
+        if (threadIdx.x == 0) { *pl.done = 0u; *pl.epoch = e; }
+    }
+    if (threadIdx.x < pl.nnb) {
+        const unsigned long long t0 = global_timer_ns();
+        while (ld_acquire_sys(pl.lflag[threadIdx.x]) < e) {
+            if (global_timer_ns() - t0 > 2000000000ull) { atomicExch(pl.err, 1); break; }
+        }
+    }
+    __syncthreads();
+    const double *src = pl.lrecv[par];
+    double *tail = x_ext + nloc;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < pl.nghost; j += stride) tail[j] = __ldcg(src + j);
+}
+
+static famg_status p2p_exchange(famg_comm *cm, const HaloPlan &h, double *x_ext) {
+    const int work = std::max(h.total_send, h.nghost);
+    const int grid = std::max(1, std::min(64, (work + 1023) / 1024));
+    p2p_exchange_kernel<<<grid, 256, 0, cm->ctx->stream>>>(h.dev, x_ext, h.nloc, h.d_send_idx);
+    count_launch(cm->ctx);
+    KERNEL_CHECK();
+    return FAMG_OK;
+}
+
 static famg_status p2p_begin(famg_comm *cm, const HaloPlan &h, const double *x_ext) {
     const int grid = std::max(1, std::min(64, (h.total_send + 1023) / 1024));
     p2p_pack_kernel<<<grid, 256, 0, cm->ctx->stream>>>(h.dev, x_ext, h.d_send_idx);
@@ -495,19 +539,19 @@ static famg_status dist_apply(famg_comm *cm, const DistOp &op, int epi, double *
     if (op.halo.p2p) {
         // pack -> interior rows -> wait+copy ghosts -> boundary rows, all on the compute stream: the
         // neighbours' stores land in this rank's arena while the interior kernel runs
-        FAMG_TRY(p2p_begin(cm, op.halo, x_ext));
         // Measured on 2 and 8 B200 (scripts/dist_bench.py): with peer-memory stores the ghosts arrive
         // within a few microseconds, less than what splitting the apply into interior + boundary
         // launches costs (persistent-kernel ramp/tail twice, one more dependency) -- even for the
         // finest level.  The split is kept for operators above FAMG_SPLIT_MIN_ROWS (default: never).
         static const int split_min_rows = getenv("FAMG_SPLIT_MIN_ROWS") ? atoi(getenv("FAMG_SPLIT_MIN_ROWS")) : 0x7fffffff;
         if (nrows < split_min_rows) {
-            FAMG_TRY(p2p_end(cm, op.halo, x_ext));
+            FAMG_TRY(p2p_exchange(cm, op.halo, x_ext));
             g.dot_partials = dot_partials;
             FAMG_TRY(spmv_launch(g, &n));
             if (num_partials) *num_partials = n;
             return FAMG_OK;
         }
+        FAMG_TRY(p2p_begin(cm, op.halo, x_ext));
         if (op.ie > op.ib) {
             g.row_begin = op.ib; g.row_end = op.ie; g.dot_partials = dot_partials ? dot_partials + total : nullptr;
             FAMG_TRY(spmv_launch(g, &n)); total += n;

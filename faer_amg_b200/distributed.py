@@ -107,7 +107,7 @@ class Comm:
 class DistMultigrid:
     """Row-partitioned Multigrid + PCG built from a replicated global :class:`Multigrid`."""
 
-    def __init__(self, comm: Comm, global_mg, row_splits: Sequence[np.ndarray], replicate_below: int = 32768):
+    def __init__(self, comm: Comm, global_mg, row_splits: Sequence[np.ndarray], replicate_below: int = 4096):
         self._splits = [np.ascontiguousarray(s, dtype=np.int64) for s in row_splits]
         arr = (i64p * len(self._splits))(*[s.ctypes.data_as(i64p) for s in self._splits])
         h = vp()
