@@ -79,7 +79,7 @@ namespace famg {
 // "arena" exported with CUDA IPC; per plan it holds one flag per peer, an epoch counter and two
 // receive buffers (parity = epoch & 1).  A pack kernel stores this rank's boundary entries straight
 // into its neighbours' receive buffers, fences, and publishes the epoch in their flag slots; the
-// consumer spins on its own flag slots (acquire, with a timeout) and moves the ghosts into the
+// consumer spins on its own flag slots (acquire, with a 20 s timeout) and moves the ghosts into the
 // vector's tail.  Epochs live in device memory, so the sequence replays inside CUDA graphs.
 constexpr int P2P_MAX_NB = 8;
 struct P2PPlanDev {
@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(256) p2p_wait_kernel(const P2PPlanDev pl, doub
     if (threadIdx.x < pl.nnb) {
         const unsigned long long t0 = global_timer_ns();
         while (ld_acquire_sys(pl.lflag[threadIdx.x]) < e) {
-            if (global_timer_ns() - t0 > 2000000000ull) { atomicExch(pl.err, 1); break; }  // 2 s: peer died
+            if (global_timer_ns() - t0 > 20000000000ull) { atomicExch(pl.err, 1); break; }  // 20 s: peer died
         }
     }
     __syncthreads();
@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(32) p2p_allreduce_kernel(const P2PCollDev c, d
         st_release_sys(c.ar_rflag[lane], e);
         const unsigned long long t0 = global_timer_ns();
         while (ld_acquire_sys(c.ar_lflag + lane) < e) {
-            if (global_timer_ns() - t0 > 2000000000ull) { atomicExch(c.err, 1); break; }
+            if (global_timer_ns() - t0 > 20000000000ull) { atomicExch(c.err, 1); break; }
         }
     }
     __syncwarp();
@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(256) p2p_allgather_wait_kernel(const P2PCollDe
     if (threadIdx.x < c.nranks) {
         const unsigned long long t0 = global_timer_ns();
         while (ld_acquire_sys(c.ag_lflag + threadIdx.x) < e) {
-            if (global_timer_ns() - t0 > 2000000000ull) { atomicExch(c.err, 1); break; }
+            if (global_timer_ns() - t0 > 20000000000ull) { atomicExch(c.err, 1); break; }
         }
     }
     __syncthreads();
@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(256) p2p_exchange_kernel(const P2PPlanDev pl, 
     if (threadIdx.x < pl.nnb) {
         const unsigned long long t0 = global_timer_ns();
         while (ld_acquire_sys(pl.lflag[threadIdx.x]) < e) {
-            if (global_timer_ns() - t0 > 2000000000ull) { atomicExch(pl.err, 1); break; }
+            if (global_timer_ns() - t0 > 20000000000ull) { atomicExch(pl.err, 1); break; }
         }
     }
     __syncthreads();
