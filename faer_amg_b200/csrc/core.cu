@@ -379,17 +379,29 @@ famg_status famg_csr_create(famg_ctx *ctx, int64_t nrows, int64_t ncols, const u
     if (nnz && (!col_idx || !val)) FAMG_FAIL(FAMG_ERR_INVALID, "null col_idx/val");
     std::vector<int> rp((size_t)nrows + 1), ci((size_t)nnz);
     for (int64_t i = 0; i <= nrows; ++i) {
-        if (i > 0 && row_ptr[i] < row_ptr[i - 1]) FAMG_FAIL(FAMG_ERR_INVALID, "row_ptr not monotone at row %lld", (long long)i);
+        if (i > 0 && (row_ptr[i] < row_ptr[i - 1] || row_ptr[i] > nnz))
+            FAMG_FAIL(FAMG_ERR_INVALID, "row_ptr not monotone at row %lld", (long long)i);
         rp[(size_t)i] = (int)row_ptr[i];
     }
+    // usize -> i32 narrowing + validation of the faer CSR invariants, rows in parallel
+    int64_t bad_range = -1, bad_order = -1;
+#pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < nrows; ++i)
         for (uint64_t q = row_ptr[i]; q < row_ptr[i + 1]; ++q) {
-            uint64_t c = col_idx[q];
-            if (c >= (uint64_t)ncols) FAMG_FAIL(FAMG_ERR_INVALID, "column index %llu out of range in row %lld", (unsigned long long)c, (long long)i);
-            if (q > row_ptr[i] && col_idx[q - 1] >= c)
-                FAMG_FAIL(FAMG_ERR_INVALID, "columns of row %lld are not sorted and unique", (long long)i);
+            const uint64_t c = col_idx[q];
+            if (c >= (uint64_t)ncols) {
+#pragma omp atomic write
+                bad_range = i;
+                continue;
+            }
+            if (q > row_ptr[i] && col_idx[q - 1] >= c) {
+#pragma omp atomic write
+                bad_order = i;
+            }
             ci[(size_t)q] = (int)c;
         }
+    if (bad_range >= 0) FAMG_FAIL(FAMG_ERR_INVALID, "column index out of range in row %lld", (long long)bad_range);
+    if (bad_order >= 0) FAMG_FAIL(FAMG_ERR_INVALID, "columns of row %lld are not sorted and unique", (long long)bad_order);
     return csr_from_host_i32(ctx, nrows, ncols, rp.data(), ci.data(), val, out);
 }
 
