@@ -177,7 +177,6 @@ famg_status pcg_update_xr(famg_ctx *ctx, double *x, double *r, const double *p, 
                           int slot_num, int slot_den, int slot_rr);
 // p = z + beta p with beta = s[num]/s[den]
 famg_status pcg_update_p(famg_ctx *ctx, double *p, const double *z, int64_t n, int slot_num, int slot_den);
-famg_status vec_axpby_sub(famg_ctx *ctx, double *out, const double *a, const double *b, int64_t n);  // out = a - b
 famg_status vec_add_inplace(famg_ctx *ctx, double *x, const double *y, int64_t n);  // x += y
 famg_status read_scalars(famg_ctx *ctx, int first, int count, double *host);  // sync D2H
 famg_status vec_axpby(famg_ctx *ctx, double *y, int64_t ldy, const double *x, int64_t ldx, int64_t n, int k, double alpha, double beta);

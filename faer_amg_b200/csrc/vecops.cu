@@ -134,18 +134,6 @@ famg_status pcg_update_p(famg_ctx *ctx, double *p, const double *z, int64_t n, i
     return FAMG_OK;
 }
 
-__global__ void __launch_bounds__(VT) sub_kernel(double *__restrict__ out, const double *__restrict__ a, const double *__restrict__ b,
-                                                 long long n) {
-    for (long long i = (long long)blockIdx.x * VT + threadIdx.x; i < n; i += (long long)gridDim.x * VT) out[i] = a[i] - b[i];
-}
-famg_status vec_axpby_sub(famg_ctx *ctx, double *out, const double *a, const double *b, int64_t n) {
-    if (n == 0) return FAMG_OK;
-    sub_kernel<<<vec_grid(ctx, n), VT, 0, ctx->stream>>>(out, a, b, n);
-    count_launch(ctx);
-    KERNEL_CHECK();
-    return FAMG_OK;
-}
-
 __global__ void __launch_bounds__(VT) add_inplace_kernel(double *__restrict__ x, const double *__restrict__ y, long long n) {
     for (long long i = (long long)blockIdx.x * VT + threadIdx.x; i < n; i += (long long)gridDim.x * VT) x[i] = x[i] + y[i];
 }

@@ -91,3 +91,18 @@ def test_world_size_2_plumbing_over_gloo():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True, True), (1, True, True)]
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    """`bench.py --impl reference` is the CPU arm of the contract: it must run without a GPU and
+    print one JSON line with the reference keys."""
+    import json
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--grid", "16", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "ms" and line["higher_is_better"] is False
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["value"] > 0
+    assert line["config"]["grid"] == [16, 16, 16]
