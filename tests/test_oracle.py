@@ -187,3 +187,66 @@ def test_block_smoother_matches_dense_blocks():
                 if j not in nodes:
                     blk[li, li] += 0.5 * np.sqrt(d[i] / d[j]) * abs(A[i, j])
         assert np.allclose(out[nodes], np.linalg.solve(blk, r[nodes]), rtol=1e-12)
+
+
+# ---------------------------------------------------------------------- second, independent restatement
+def _numpy_cycle(levels, mu, nu, v, f, lvl):
+    """multigrid.rs:269-380 written directly in dense numpy (no shared code with the C oracle)."""
+    A, minv, R, P = levels[lvl]
+    if lvl == len(levels) - 1:
+        return minv(f)
+    for _ in range(nu):
+        v = v + minv(f - A @ v)
+    fc = R @ (f - A @ v)
+    vc = np.zeros((levels[lvl + 1][0].shape[0], f.shape[1]))
+    for _ in range(mu):
+        vc = _numpy_cycle(levels, mu, nu, vc, fc, lvl + 1)
+    v = v + P @ vc
+    for _ in range(nu):
+        v = v + minv(f - A @ v)
+    return v
+
+
+@pytest.mark.parametrize("mu,nu", [(1, 1), (2, 1), (1, 3)])
+def test_cycle_against_dense_numpy_restatement(mu, nu):
+    dims = (8, 8, 4)
+    a = O.gen_g7(*dims)
+    n = a.nrows
+    h = O.build_hierarchy(a, np.full((n, 1), 1 / np.sqrt(n)), dims, coarsest_dim=20)
+    assert h.levels == 3
+    mg = O.multigrid_from_hierarchy(h, "l1", mu=mu, nu=nu)
+    levels = []
+    for lvl, op in enumerate(h.operators):
+        A = op.to_scipy().toarray()
+        if lvl == h.levels - 1:
+            minv = (lambda Ad: (lambda r: np.linalg.solve(Ad, r)))(A)
+        else:
+            d = 1.0 / np.abs(A).sum(axis=1)
+            minv = (lambda dd: (lambda r: dd[:, None] * r))(d)
+        R = h.restrictions[lvl - 1].to_scipy().toarray() if lvl else None
+        P = h.interpolations[lvl - 1].to_scipy().toarray() if lvl else None
+        levels.append((A, minv, R, P))
+    f = np.random.default_rng(17).standard_normal((n, 2))
+    want = _numpy_cycle(levels, mu, nu, np.zeros_like(f), f, 0)
+    got = mg.apply(f)
+    assert np.max(np.abs(got - want)) <= 1e-13 * np.max(np.abs(want))
+
+
+def test_pcg_against_numpy_restatement():
+    """Textbook PCG with faer's stopping rule, re-written in numpy: same iteration count and iterates."""
+    a = O.gen_g27(6, 5, 4)
+    A = a.to_scipy().tocsr()
+    d = O.new_jacobi(a, 1.0)
+    b = np.random.default_rng(3).standard_normal(a.nrows)
+    x = np.zeros_like(b); r = b.copy(); thr = 1e-10 * np.linalg.norm(b)
+    z = d * r; p = z.copy(); rtz = r @ z; it = 0
+    while True:
+        q = A @ p
+        alpha = rtz / (p @ q)
+        x += alpha * p; r -= alpha * q; it += 1
+        if np.linalg.norm(r) < thr or it >= 1000:
+            break
+        z = d * r; rtz_new = r @ z; p = z + (rtz_new / rtz) * p; rtz = rtz_new
+    xo, info = O.pcg(a, b, d, rel_tol=1e-10, abs_tol=0.0, max_iters=1000)
+    assert info.status == 0 and info.iters == it
+    assert np.linalg.norm(xo - x) <= 1e-12 * np.linalg.norm(x)
