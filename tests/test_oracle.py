@@ -192,9 +192,10 @@ def test_block_smoother_matches_dense_blocks():
 # ---------------------------------------------------------------------- second, independent restatement
 def _numpy_cycle(levels, mu, nu, v, f, lvl):
     """multigrid.rs:269-380 written directly in dense numpy (no shared code with the C oracle)."""
-    A, minv, R, P = levels[lvl]
+    A, minv = levels[lvl][0], levels[lvl][1]
     if lvl == len(levels) - 1:
         return minv(f)
+    R, P = levels[lvl + 1][2], levels[lvl + 1][3]  # transfer operators are stored with the coarse level
     for _ in range(nu):
         v = v + minv(f - A @ v)
     fc = R @ (f - A @ v)
