@@ -11,7 +11,9 @@ from .core import Context, DeviceMat, ParSpmmOp, SparseMatOp, SparseRowMat, PAR_
 from .hierarchy import Hierarchy, HierarchyConfig  # noqa: F401
 from .interpolation import (AggregationConfig, GalerkinCoarse, InterpolationConfig, galerkin_product,  # noqa: F401
                             smooth_interpolation, smoothed_aggregation, tentative_prolongator)
-from .partitioners import GeometricPartitioner, Partition, geometric_partition  # noqa: F401
+from .partitioners import (GeometricPartitioner, Partition, PartitionerConfig, StrengthGraph,  # noqa: F401
+                           geometric_partition)
+from . import partitioners  # noqa: F401
 from .preconditioners.block_smoothers import BlockSmoother, BlockSmootherConfig  # noqa: F401
 from .preconditioners.coarse_solvers import CoarseSolverKind, SparseCholeskySolve  # noqa: F401
 from .preconditioners.multigrid import Multigrid, MultigridConfig  # noqa: F401
@@ -19,7 +21,8 @@ from .preconditioners.smoothers import (Diag, SmootherKind, StationaryIteration,
                                         smooth)
 from .solvers import (CgError, CgInfo, CgParams, conjugate_gradient, conjugate_gradient_dev, stationary_solver,  # noqa: F401
                       test_solver)
-from .adaptivity import ErrorPropogator  # noqa: F401
+from .adaptivity import ErrorPropogator, create_weights, find_near_null, smooth_vector, smooth_vector_dev  # noqa: F401
+from . import adaptivity  # noqa: F401
 from . import gallery  # noqa: F401
 
 __version__ = "0.1.0"

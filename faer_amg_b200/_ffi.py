@@ -96,6 +96,16 @@ SIGNATURES = {
     "famg_galerkin": [vp, vp, cint, f64, vpp, vpp, vpp],
     "famg_tentative_p": [vp, i64, i64, i64, i64, f64p, i64, i64, u64p, u64p, vpp, f64p],
     "famg_thin_q": [i64, i64, f64p, i64],
+    "famg_thin_q_dev": [vp],
+    "famg_error_propagator_dev": [vp, vp, vp, vp],
+    "famg_smooth_vector_dev": [vp, vp, i64, vp, f64p],
+    "famg_vec_coldot": [vp, vp, f64p],
+    "famg_strength_graph_create": [i64, u64p, u64p, f64p, i64, i64, f64p, i64, vpp],
+    "famg_graph_create": [i64, u64p, u64p, f64p, vpp],
+    "famg_graph_dims": [vp, i64p, i64p],
+    "famg_graph_download": [vp, u64p, u64p, f64p],
+    "famg_graph_destroy": [vp],
+    "famg_partition_modularity": [vp, f64, f64, i64, u64p, i64p],
     "famg_pcg_solve": [vp, cint, vp, f64p, f64p, f64, f64, i64, cint, C.POINTER(CgInfoStruct)],
     "famg_pcg_solve_dev": [vp, cint, vp, vp, vp, f64, f64, i64, cint, C.POINTER(CgInfoStruct)],
     "famg_stationary_solve": [vp, cint, vp, f64p, f64p, f64, i64, i64p],

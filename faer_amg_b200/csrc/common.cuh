@@ -146,14 +146,14 @@ inline void count_launch(famg_ctx *ctx, int n = 1) { ctx->launches.fetch_add(n, 
 famg_status exclusive_scan_i32(famg_ctx *ctx, const int *in, int *out, int64_t n);
 
 // ---------------------------------------------------------------- SpMV family (spmv.cu)
-enum Epi { EPI_SPMV = 0, EPI_RESID = 1, EPI_SMOOTH = 2, EPI_ADD = 3, EPI_SI = 4 };
+enum Epi { EPI_SPMV = 0, EPI_RESID = 1, EPI_SMOOTH = 2, EPI_ADD = 3, EPI_SI = 4, EPI_EPROP = 5 };
 struct SpmvArgs {
     const famg_csr *a = nullptr;
     int epi = EPI_SPMV;
     const double *x = nullptr; int64_t ldx = 0;  // gather source (ncols rows)
     double *y = nullptr;       int64_t ldy = 0;  // output (nrows rows)
     const double *b = nullptr; int64_t ldb = 0;  // rhs (RESID, SMOOTH)
-    const double *d = nullptr;                   // diagonal (SMOOTH, SI)
+    const double *d = nullptr;                   // diagonal (SMOOTH, SI, EPROP)
     int k = 1;
     double *dot_partials = nullptr;              // k == 1: per-CTA partial of sum_i x[i]*(A x)[i]
     int row_begin = 0, row_end = -1;             // row range (distributed interior/boundary split)

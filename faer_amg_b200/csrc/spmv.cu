@@ -75,8 +75,8 @@ __device__ __forceinline__ EpiOps epi_prefetch(const SpmvKernelParams &p, const 
         // b, d and y are touched once per sweep: streaming (evict-first) so they do not push the
         // x lines that the gathers reuse out of L1/L2
         if (EPI == EPI_RESID || EPI == EPI_SMOOTH) o.b = __ldcs(p.b + (long long)c * p.ldb + row);
-        if (EPI == EPI_SMOOTH || EPI == EPI_SI) o.d = __ldcs(p.d + row);
-        if (EPI == EPI_SMOOTH || EPI == EPI_SI || DOT) o.x = xc[row];
+        if (EPI == EPI_SMOOTH || EPI == EPI_SI || EPI == EPI_EPROP) o.d = __ldcs(p.d + row);
+        if (EPI == EPI_SMOOTH || EPI == EPI_SI || EPI == EPI_EPROP || DOT) o.x = xc[row];
         if (EPI == EPI_ADD) o.y = __ldcs(yc + row);
     }
     return o;
@@ -93,6 +93,8 @@ __device__ __forceinline__ void epi_store(double *yc, int row, double s, const E
         yc[row] = o.x + o.d * r;
     } else if (EPI == EPI_ADD) {
         yc[row] = o.y + s;                       // multigrid.rs:349-350
+    } else if (EPI == EPI_EPROP) {
+        yc[row] = o.x - o.d * s;                 // ErrorPropogator: out = x - M^-1 (A x)   (adaptivity.rs:191-198)
     } else {
         yc[row] = o.x + o.d * (o.x - s);         // EPI_SI: x' = x + d .* (x - A x)   (smoothers.rs:153-156, literal)
     }
@@ -424,6 +426,7 @@ static famg_status launch_tpr(const SpmvKernelParams &kp, int epi, bool dot, int
         case EPI_RESID: return launch_one<TPR, EPI_RESID, false>(kp, variant, nrows, nrows2, sms, reserve, st, grid);
         case EPI_SMOOTH: return launch_one<TPR, EPI_SMOOTH, false>(kp, variant, nrows, nrows2, sms, reserve, st, grid);
         case EPI_ADD: return launch_one<TPR, EPI_ADD, false>(kp, variant, nrows, nrows2, sms, reserve, st, grid);
+        case EPI_EPROP: return launch_one<TPR, EPI_EPROP, false>(kp, variant, nrows, nrows2, sms, reserve, st, grid);
         default: return launch_one<TPR, EPI_SI, false>(kp, variant, nrows, nrows2, sms, reserve, st, grid);
     }
 }
@@ -438,7 +441,7 @@ famg_status spmv_launch(const SpmvArgs &args, int *num_ctas) {
     if ((row_end <= row_begin && args.row2_end <= args.row2_begin) || args.k <= 0) return FAMG_OK;
     if (row_end < row_begin) row_end = row_begin;
     if ((args.epi == EPI_RESID || args.epi == EPI_SMOOTH) && !args.b) FAMG_FAIL(FAMG_ERR_INVALID, "spmv: missing rhs");
-    if ((args.epi == EPI_SMOOTH || args.epi == EPI_SI) && (!args.d || args.y == args.x))
+    if ((args.epi == EPI_SMOOTH || args.epi == EPI_SI || args.epi == EPI_EPROP) && (!args.d || args.y == args.x))
         FAMG_FAIL(FAMG_ERR_INVALID, "spmv: smoother sweep needs a diagonal and distinct in/out vectors");
     if (args.dot_partials && (args.k != 1 || args.epi != EPI_SPMV)) FAMG_FAIL(FAMG_ERR_INVALID, "spmv: dot needs k == 1");
     SpmvKernelParams kp;

@@ -20,6 +20,11 @@ def thin_q(m) -> np.ndarray:
     return m
 
 
+def thin_q_dev(x: DeviceMat):
+    """Device-resident thin Q (CholeskyQR2, k <= 64), in place."""
+    call("famg_thin_q_dev", x._h)
+
+
 class HierarchyConfig:
     """hierarchy.rs:22-53."""
 

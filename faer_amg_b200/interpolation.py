@@ -12,7 +12,7 @@ import numpy as np
 
 from ._ffi import call, u64p, vp
 from .core import SparseMatOp, SparseRowMat, _f, as_colmajor
-from .partitioners import Partition
+from .partitioners import Partition, PartitionerConfig
 
 JACOBI_WEIGHT = 0.66  # interpolation/mod.rs:814
 
@@ -69,8 +69,9 @@ def smoothed_aggregation(fine_mat: SparseRowMat, partition: Partition, block_siz
 
 
 class AggregationConfig:
-    """interpolation/mod.rs:62-157.  ``partitioner``: callable (level, op, near_null) -> Partition
-    (the reference's PartitionerConfig lives on the host and is out of the GPU path)."""
+    """interpolation/mod.rs:62-157.  ``partitioner``: a :class:`PartitionerConfig` (the reference's
+    ``partitioner_config`` field; host-side algebraic aggregation) or a callable
+    ``(level, op, near_null) -> Partition`` (e.g. :class:`GeometricPartitioner`)."""
 
     def __init__(self, smoothing_steps: int = 1, candidate_dimension: int = 4,
                  partitioner: Optional[Callable] = None):
@@ -84,8 +85,15 @@ class AggregationConfig:
 
     def build(self, op: SparseMatOp, near_null, nn_weights=None, level: int = 0) -> GalerkinCoarse:
         if self.partitioner is None:
-            raise ValueError("AggregationConfig needs a partitioner callable")
-        partition = self.partitioner(level, op, near_null)
+            raise ValueError("AggregationConfig needs a partitioner (PartitionerConfig or callable)")
+        if isinstance(self.partitioner, PartitionerConfig):
+            # interpolation/mod.rs:135-138
+            ratio = self.candidate_dimension / op.block_size()
+            if nn_weights is None:
+                raise ValueError("the algebraic partitioner needs nn_weights (one per near-null vector)")
+            partition = self.partitioner.scaled(ratio).build_partition(op, near_null, nn_weights)
+        else:
+            partition = self.partitioner(level, op, near_null)
         coarse_nn, r, p, ac, partition = smoothed_aggregation(op.mat_ref(), partition, op.block_size(), near_null,
                                                               self.candidate_dimension, self.smoothing_steps)
         return GalerkinCoarse(p, r, ac, coarse_nn, partition)

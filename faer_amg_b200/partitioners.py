@@ -1,14 +1,17 @@
-"""``Partition`` container + deterministic geometric aggregation.
+"""``Partition`` container, deterministic geometric aggregation and the algebraic partitioner.
 
 The reference's algebraic partitioner (``src/partitioners/``) is host-side graph work that the
 north-star keeps out of the GPU path; it is also non-deterministic.  The hot path only
-consumes its *output*, a ``Partition`` (``partitioners/mod.rs:23-27``: node_to_agg + agg_to_node),
-so that is what this module provides, plus the structured-grid aggregates used by the benchmark
-configurations.
+consumes its *output*, a ``Partition`` (``partitioners/mod.rs:23-27``: node_to_agg + agg_to_node).
+This module provides that container, the structured-grid aggregates used by the benchmark
+configurations, and ``PartitionerConfig`` -- the host restatement of
+``PartitionerConfig::build_partition`` (least-squares strength graph, greedy modularity matching,
+node-swap refinement; ``csrc/partition.cu``, host-only C++) with documented tie-breaking.
 """
 from __future__ import annotations
 
-from typing import Sequence, Tuple
+import ctypes as C
+from typing import Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -89,3 +92,110 @@ class GeometricPartitioner:
         if len(self.dims) == level + 1:
             self.dims.append(coarse)
         return part
+
+
+class StrengthGraph:
+    """``AdjacencyList`` (partitioners/mod.rs:331-334), host-resident."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    @classmethod
+    def new_ls_strength_graph(cls, mat, near_null, weights, max_depth: int = 3) -> "StrengthGraph":
+        """partitioners/mod.rs:337-393.  ``mat``: device ``SparseRowMat`` (pattern downloaded) or a
+        ``(row_ptr, col_idx)`` pair of host arrays."""
+        from ._ffi import call, f64p, u64p, vp
+        from .core import as_colmajor
+
+        if isinstance(mat, tuple):
+            rp, ci = mat
+        else:
+            rp, ci, _ = mat.to_host()
+        rp = np.ascontiguousarray(rp, dtype=np.uint64)
+        ci = np.ascontiguousarray(ci, dtype=np.uint64)
+        nn = as_colmajor(near_null)
+        n = len(rp) - 1
+        if nn.shape[0] != n:
+            raise ValueError("near_null rows must match the matrix")  # mod.rs:284
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        if len(w) < nn.shape[1]:
+            raise ValueError("one weight per near-null vector is required")
+        h = vp()
+        call("famg_strength_graph_create", n, rp.ctypes.data_as(u64p), ci.ctypes.data_as(u64p), nn.ctypes.data_as(f64p),
+             max(nn.shape[0], 1), nn.shape[1], w.ctypes.data_as(f64p), max_depth, C.byref(h))
+        return cls(h)
+
+    @classmethod
+    def from_csr(cls, row_ptr, col_idx, w) -> "StrengthGraph":
+        from ._ffi import call, f64p, u64p, vp
+
+        rp = np.ascontiguousarray(row_ptr, dtype=np.uint64)
+        ci = np.ascontiguousarray(col_idx, dtype=np.uint64)
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        h = vp()
+        call("famg_graph_create", len(rp) - 1, rp.ctypes.data_as(u64p), ci.ctypes.data_as(u64p), w.ctypes.data_as(f64p), C.byref(h))
+        return cls(h)
+
+    def dims(self) -> Tuple[int, int]:
+        from ._ffi import call
+
+        n, nnz = C.c_int64(), C.c_int64()
+        call("famg_graph_dims", self._h, C.byref(n), C.byref(nnz))
+        return n.value, nnz.value
+
+    def to_csr(self):
+        """(row_ptr, neighbour ids, weights) -- neighbour lists ascending by id."""
+        from ._ffi import call, f64p, u64p
+
+        n, nnz = self.dims()
+        rp = np.empty(n + 1, dtype=np.uint64)
+        ci = np.empty(max(nnz, 1), dtype=np.uint64)
+        w = np.empty(max(nnz, 1))
+        call("famg_graph_download", self._h, rp.ctypes.data_as(u64p), ci.ctypes.data_as(u64p), w.ctypes.data_as(f64p))
+        return rp.astype(np.int64), ci[:nnz].astype(np.int64), w[:nnz]
+
+    def __del__(self):
+        try:
+            from . import _ffi
+
+            _ffi.lib().famg_graph_destroy(self._h)
+        except Exception:
+            pass
+
+
+class PartitionerConfig:
+    """partitioners/mod.rs:249-329 (``callback`` is a visualisation hook and is not mirrored).
+    Also usable as the ``partitioner`` callable of :class:`AggregationConfig`; there the
+    coarsening factor is scaled by ``candidate_dimension / block_size`` exactly as
+    ``AggregationConfig::build`` does (interpolation/mod.rs:135-137)."""
+
+    def __init__(self, coarsening_factor: float = 8.0, agg_size_penalty: float = 1.0, max_improvement_iters: int = 100):
+        self.coarsening_factor = float(coarsening_factor)
+        self.agg_size_penalty = float(agg_size_penalty)
+        self.max_improvement_iters = int(max_improvement_iters)
+
+    def build_from_strength(self, strength: StrengthGraph) -> Partition:
+        from ._ffi import call, u64p
+
+        n, _ = strength.dims()
+        node_to_agg = np.zeros(n, dtype=np.uint64)
+        naggs = C.c_int64()
+        call("famg_partition_modularity", strength._h, self.coarsening_factor, self.agg_size_penalty, self.max_improvement_iters,
+             node_to_agg.ctypes.data_as(u64p), C.byref(naggs))
+        part = Partition.from_node_to_agg(node_to_agg.astype(np.int64))
+        assert part.naggs() == naggs.value
+        return part
+
+    def build_partition(self, mat, near_null, weights) -> Partition:
+        """partitioners/mod.rs:319-328.  ``mat``: ``SparseMatOp`` (block size 1) or ``SparseRowMat``."""
+        block_size = mat.block_size() if hasattr(mat, "block_size") else 1
+        if block_size != 1:
+            raise NotImplementedError("block_size > 1 (strength.aggregate(block_reduce), mod.rs:293-300) is not built yet")
+        m = mat.mat_ref() if hasattr(mat, "mat_ref") else mat
+        if m.nrows != m.ncols:
+            raise ValueError("square matrix expected")  # mod.rs:283
+        strength = StrengthGraph.new_ls_strength_graph(m, near_null, weights, 3)
+        return self.build_from_strength(strength)
+
+    def scaled(self, ratio: float) -> "PartitionerConfig":
+        return PartitionerConfig(self.coarsening_factor * ratio, self.agg_size_penalty, self.max_improvement_iters)

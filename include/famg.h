@@ -189,6 +189,43 @@ famg_status famg_tentative_p(famg_ctx *ctx, int64_t n_fine, int64_t block_size, 
                              double *coarse_nn);
 /* coarse_nn.qr().compute_thin_Q() (hierarchy.rs:228); host, in place, R with positive diagonal */
 famg_status famg_thin_q(int64_t n, int64_t k, double *a, int64_t lda);
+/* the same on a device-resident block (k <= 64): CholeskyQR2 -- Gram matrix by a deterministic
+ * reduction, k x k Cholesky on the host, X <- X R^-1, twice.  Keeps the near-null search loop
+ * (adaptivity.rs:331-354: one thin QR per error-propagation step on an n x k block) in HBM. */
+famg_status famg_thin_q_dev(famg_vec *x);
+
+/* ---- near-null search kept on the device -------------------------------------- */
+/* ErrorPropogator::apply (adaptivity.rs:191-198): out = x - M^-1 (A x) on an n x k block.  With a
+ * Diag preconditioner this is one fused SpMM launch (A and x read once). */
+famg_status famg_error_propagator_dev(const famg_csr *a, const famg_smoother *s, famg_vec *out, const famg_vec *x);
+/* smooth_vector (adaptivity.rs:307-390) from the caller's random block x (n x k, k <= 64), in place:
+ * x = thinQ(thinQ(x)); iterations x { x = E x; x = thinQ(x) }   (:331, :346, :351-354)
+ * cfs (k doubles, may be NULL): ||E w||_A / ||w||_A per column (:365-384).  The reference draws x
+ * from an unseeded StandardNormal stream (:321-329); the caller supplies it here. */
+famg_status famg_smooth_vector_dev(const famg_csr *a, const famg_smoother *s, int64_t iterations, famg_vec *x, double *cfs);
+/* out[c] = x[:,c] . y[:,c] (deterministic two-stage reduction) */
+famg_status famg_vec_coldot(const famg_vec *x, const famg_vec *y, double *out);
+
+/* ---- host partitioner: PartitionerConfig::build_partition, partitioners/mod.rs:273-329 -
+ * Host-only (no device work, no ctx): the north-star keeps aggregation on the host.  A Rust build keeps
+ * using the crate's own partitioner; these entry points give the non-Rust harness algebraic aggregates.
+ * Tie-breaking where the reference is unspecified is documented in csrc/partition.cu. */
+typedef struct famg_graph famg_graph; /* AdjacencyList (partitioners/mod.rs:331-334) */
+/* AdjacencyList::new_ls_strength_graph (partitioners/mod.rs:337-393); the reference uses max_depth 3 (:290).
+ * CSR pattern of the square matrix (values are not used), near_null n x k column-major, k weights. */
+famg_status famg_strength_graph_create(int64_t n, const uint64_t *row_ptr, const uint64_t *col_idx,
+                                       const double *near_null, int64_t ldn, int64_t k, const double *weights,
+                                       int64_t max_depth, famg_graph **out);
+/* an explicit weighted adjacency list (PartitionerConfig::build_from_strength, partitioners/mod.rs:310-317) */
+famg_status famg_graph_create(int64_t n, const uint64_t *row_ptr, const uint64_t *col_idx, const double *w,
+                              famg_graph **out);
+famg_status famg_graph_dims(const famg_graph *g, int64_t *n, int64_t *nnz);
+famg_status famg_graph_download(const famg_graph *g, uint64_t *row_ptr, uint64_t *col_idx, double *w);
+famg_status famg_graph_destroy(famg_graph *g);
+/* Partitioner::new + initialize_partition + improve_partition (partitioners/modularity.rs:28-137, 179-192,
+ * 437-510) from the singleton partition; node_to_agg has n entries, aggregates are numbered 0..naggs-1. */
+famg_status famg_partition_modularity(const famg_graph *g, double coarsening_factor, double agg_size_penalty,
+                                      int64_t max_improvement_iters, uint64_t *node_to_agg, int64_t *naggs);
 
 /* ---- PCG: faer conjugate_gradient as driven by utils.rs:574-609 ----------------------------- */
 typedef struct {

@@ -339,6 +339,32 @@ def error_propagator(a: Csr, precond_apply, x) -> np.ndarray:
     return x - precond_apply(spmm_csr(a, x))
 
 
+def smooth_vector(a: Csr, precond_apply, x0, iterations: int):
+    """smooth_vector (adaptivity.rs:307-390) from a given start block x0 (the reference draws it from
+    an unseeded StandardNormal stream, :321-329): x = thinQ(thinQ(x0)); iterations x { x = E x;
+    x = thinQ(x) } with the Householder thin Q of ``orc_thin_q``; then per column
+    cf = ||E w||_A / ||w||_A (:365-384).  Returns (x, cfs)."""
+    x = thin_q(thin_q(_fcol(x0)))
+    for _ in range(iterations):
+        x = thin_q(error_propagator(a, precond_apply, x))
+    cfs = []
+    for c in range(x.shape[1]):
+        w = x[:, c:c + 1]
+        aw = spmm_csr(a, w)
+        w_a = np.sqrt(float(w[:, 0] @ aw[:, 0]))
+        ev = w - precond_apply(aw)
+        aev = spmm_csr(a, ev)
+        cfs.append(np.sqrt(float(ev[:, 0] @ aev[:, 0])) / w_a)
+    return x, cfs
+
+
+def create_weights(a: Csr, nn_basis) -> list:
+    """create_weights (adaptivity.rs:434-443): 1 / (v^T A v) per column."""
+    v = _fcol(nn_basis)
+    av = spmm_csr(a, v)
+    return [1.0 / float(v[:, c] @ av[:, c]) for c in range(v.shape[1])]
+
+
 # ----------------------------------------------------------------------------- multigrid
 SM_DIAG, SM_LLT, SM_BLOCK = 0, 1, 2
 PC_NONE, PC_DIAG, PC_MG = 0, 1, 2
@@ -475,9 +501,11 @@ class Hierarchy:
 
 def build_hierarchy(a: Csr, near_null, dims: Sequence[int], coarsest_dim: int = 1000,
                     max_levels: Optional[int] = None, cand: int = 1, smoothing_steps: int = 1,
-                    block: Sequence[int] = (2, 2, 2)) -> Hierarchy:
+                    block: Sequence[int] = (2, 2, 2), partitioner=None) -> Hierarchy:
     """Hierarchy::coarsen (hierarchy.rs:190-248) with the partitioner replaced by deterministic
-    geometric aggregates (the reference partitioner is non-deterministic).  Per level:
+    geometric aggregates (the reference partitioner is non-deterministic) -- or by
+    ``partitioner(level, fine, near_null) -> node_to_agg`` (e.g. the restated algebraic partitioner
+    of ``oracle/partitioner.py`` with its documented tie-breaking).  Per level:
     GalerkinCoarse; coarse near-null smoothed by a 3-step L1 StationaryIteration (:217-226) and
     re-orthonormalised by thin QR (:228)."""
     h = Hierarchy([a], [], [], [], [_fcol(near_null)], [tuple(dims)])
@@ -486,7 +514,13 @@ def build_hierarchy(a: Csr, near_null, dims: Sequence[int], coarsest_dim: int = 
     while coarse_dim > coarsest_dim and level < max_levels:
         fine = h.operators[-1]
         dims_f = h.grid_dims[-1]
-        agg_ptr, agg_nodes, dims_c = geometric_aggregates(dims_f, block)
+        if partitioner is None:
+            agg_ptr, agg_nodes, dims_c = geometric_aggregates(dims_f, block)
+        else:
+            n2a = np.asarray(partitioner(level - 1, fine, h.near_nulls[-1]), dtype=np.int64)
+            agg_nodes = np.argsort(n2a, kind="stable").astype(np.int64)
+            agg_ptr = np.concatenate([[0], np.cumsum(np.bincount(n2a))]).astype(np.int64)
+            dims_c = None
         g = smoothed_aggregation(fine, agg_ptr, agg_nodes, h.near_nulls[-1], cand, smoothing_steps)
         coarse_dim = g.coarse_mat.nrows
         nn = stationary_iteration(g.coarse_mat, new_l1(g.coarse_mat), 3, g.coarse_nn)
