@@ -77,11 +77,106 @@ __device__ void sg_row_count(int i, int lane, const SgMat &a, const SgMat &b, in
     group_sync<GROUP>();
 }
 
+// ---- staged accumulation for rows that own a whole CTA ------------------------------------------
+// The plain k loop of sg_row_fill costs one chain of dependent global loads (a.col -> b.rp -> b.col)
+// plus a CTA barrier per k: ~1 us per k whatever the length of B_k, which is what made the
+// coarse-level products (hundreds to thousands of k per row) the slowest part of a hierarchy build.
+// Here the entries of a batch of k's (up to SG_SK segments / SG_SE entries) are brought in by all
+// 256 threads at once (the loads of a batch are independent), their output slots are found by a flat,
+// perfectly balanced binary-search pass, and only the short in-order accumulation
+// vals[slot] += a_ik * b_kj  runs k after k out of shared memory -- by one warp with __syncwarp
+// between k's when the segments are short, by the whole CTA when they are long.  The order of
+// the adds per output entry is still ascending k: same bits as before.
+constexpr int SG_SK = 64;    // segments (k's) per batch
+constexpr int SG_SE = 2048;  // entries per batch
+
+struct SgStage {
+    double bv[SG_SE];
+    double av[SG_SK];
+    int slot[SG_SE];
+    int b0[SG_SK], len[SG_SK], off[SG_SK + 1];
+    int nk, partial;
+};
+
+// DENSE: `vals` is indexed by the column itself (ncols(B) accumulators), `touched` records the
+// structural pattern; no search pass.
+template <bool DENSE>
+__device__ void sg_accumulate_staged(int tid, const SgMat &a, const SgMat &b, int a0, int a1, const int *list, int n, double *vals,
+                                     SgStage &st, unsigned char *touched = nullptr) {
+    const int warp = tid >> 5, lane = tid & 31;
+    int q = a0, poff = 0;  // next k of the row; entries of that k already consumed (a B_k longer than one batch)
+    while (q < a1) {
+        if (tid < SG_SK) {
+            int len = 0, b0 = 0;
+            double av = 0.0;
+            if (q + tid < a1) {
+                const int k = a.col[q + tid];
+                av = a.val[q + tid];
+                b0 = b.rp[k];
+                len = b.rp[k + 1] - b0;
+                if (tid == 0) { b0 += poff; len -= poff; }
+            }
+            st.av[tid] = av; st.b0[tid] = b0; st.len[tid] = len;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const int avail = min(SG_SK, a1 - q);
+            int acc = 0, nk = 0, partial = 0;
+            while (nk < avail && acc + st.len[nk] <= SG_SE) { st.off[nk] = acc; acc += st.len[nk]; ++nk; }
+            if (nk == 0) { st.off[0] = 0; st.len[0] = SG_SE; acc = SG_SE; nk = 1; partial = 1; }  // B_k longer than a batch
+            st.off[nk] = acc; st.nk = nk; st.partial = partial;
+        }
+        __syncthreads();
+        const int nk = st.nk, total = st.off[nk];
+        for (int kk = warp; kk < nk; kk += 8) {  // one warp per segment: coalesced, independent loads
+            const int b0 = st.b0[kk], len = st.len[kk], off = st.off[kk];
+            for (int p = lane; p < len; p += 32) {
+                const int j = b.col[b0 + p];
+                st.slot[off + p] = j; st.bv[off + p] = b.val[b0 + p];
+                if (DENSE) touched[j] = 1;  // same value from every writer
+            }
+        }
+        __syncthreads();
+        if (!DENSE) {
+            for (int t = tid; t < total; t += 256) {  // column -> output slot
+                const int j = st.slot[t];
+                int lo = 0, hi = n;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (list[mid] < j) lo = mid + 1; else hi = mid;
+                }
+                st.slot[t] = lo;
+            }
+            __syncthreads();
+        }
+        if (total > 64 * nk) {  // long segments: the whole CTA takes one k at a time
+            for (int kk = 0; kk < nk; ++kk) {
+                const double av = st.av[kk];
+                const int len = st.len[kk], off = st.off[kk];
+                for (int p = tid; p < len; p += 256) { const int sl = st.slot[off + p]; vals[sl] = vals[sl] + av * st.bv[off + p]; }
+                __syncthreads();
+            }
+        } else {
+            if (warp == 0) {
+                for (int kk = 0; kk < nk; ++kk) {
+                    const double av = st.av[kk];
+                    const int len = st.len[kk], off = st.off[kk];
+                    for (int p = lane; p < len; p += 32) { const int sl = st.slot[off + p]; vals[sl] = vals[sl] + av * st.bv[off + p]; }
+                    __syncwarp();
+                }
+            }
+            __syncthreads();
+        }
+        if (st.partial) poff += SG_SE; else { q += nk; poff = 0; }
+        __syncthreads();  // st.partial / st.nk are rewritten by the next round
+    }
+}
+
 // Pass 2 for one row.  table: H = hmask+1 ints (8-byte aligned; reused as the H/2 f64 accumulators
 // once the keys have been compacted), list: H/2 ints.  The row has n <= H/2 distinct columns.
 template <int GROUP>
 __device__ void sg_row_fill(int i, int lane, const SgMat &a, const SgMat &b, int *table, int *list, int hmask, int *cnt,
-                            const int *c_rp, int *c_col, double *c_val, const SgEpilogue &ep) {
+                            const int *c_rp, int *c_col, double *c_val, const SgEpilogue &ep, SgStage *stage = nullptr) {
     const int n = sg_row_insert<GROUP>(i, lane, a, b, table, hmask, cnt);
     const int half = (hmask + 1) >> 1;
     // compact the distinct columns, pad with INT_MAX up to the sort width (power of two >= n)
@@ -112,11 +207,14 @@ __device__ void sg_row_fill(int i, int lane, const SgMat &a, const SgMat &b, int
     (void)half;
     for (int t = lane; t < n; t += GROUP) vals[t] = 0.0;
     group_sync<GROUP>();
+    const int a0 = a.rp[i], a1 = a.rp[i + 1];
+    if (GROUP == 256 && stage != nullptr) {
+        sg_accumulate_staged<false>(lane, a, b, a0, a1, list, n, vals, *stage);
+    } else {
     // numeric: ascending k, lanes over the entries of B_k (each j unique within one k => no races)
     // The loop is latency-bound (a.col[q] -> b.rp[k] -> b.col[p] are dependent loads and every k ends
     // in a group barrier), so the next k's row bounds and this lane's first entry of B_k are fetched
     // one iteration ahead.
-    const int a0 = a.rp[i], a1 = a.rp[i + 1];
     int k_n = 0, b0_n = 0, b1_n = 0, j_n = 0;
     double av_n = 0.0, bv_n = 0.0;
     if (a0 < a1) {
@@ -142,6 +240,7 @@ __device__ void sg_row_fill(int i, int lane, const SgMat &a, const SgMat &b, int
             vals[lo] = vals[lo] + av * bv;
         }
         group_sync<GROUP>();
+    }
     }
     const int base = c_rp[i];
     if (!ep.enabled) {
@@ -210,32 +309,85 @@ __global__ void sg_size2_kernel(const int *__restrict__ row_nnz, const int *__re
 
 struct SgBounds { int limit[SG_NCLS]; };  // class c holds rows with size <= limit[c] (ascending; last = INT_MAX)
 
-__global__ void sg_classify_kernel(const int *__restrict__ size, int m, SgBounds bnd, int *__restrict__ cls,
-                                   int *__restrict__ class_count, int *__restrict__ max_size) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m) return;
-    const int u = size[i];
-    int c = 0;
-    while (c < SG_NCLS - 1 && u > bnd.limit[c]) ++c;
-    cls[i] = c;
-    // one atomic per (warp, class) instead of one per row
-    const unsigned active = __activemask();
-    const unsigned peers = __match_any_sync(active, c);
-    if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&class_count[c], __popc(peers));
-    if (c == SG_NCLS - 1) atomicMax(max_size, u);
+// Rows -> size classes -> `perm` (rows of each class contiguous, ascending inside a class: the
+// permutation is deterministic).  Every CTA owns one contiguous chunk of rows; class counts are
+// accumulated in shared memory (one global atomic per CTA and class -- a per-warp global atomic on 8
+// addresses serialised 500 k atomics for a 16 M-row operator and cost 11 ms per kernel), the per-CTA
+// counts are kept so that the binning pass can compute exact per-CTA offsets without atomics.
+constexpr int SG_BIN_THREADS = 256;
+
+__global__ void __launch_bounds__(SG_BIN_THREADS) sg_classify_kernel(const int *__restrict__ size, int m, int chunk, SgBounds bnd,
+                                                                     int *__restrict__ cls, int *__restrict__ block_count,
+                                                                     int *__restrict__ class_count, int *__restrict__ max_size) {
+    __shared__ int s_count[SG_NCLS];
+    __shared__ int s_max;
+    if (threadIdx.x < SG_NCLS) s_count[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_max = 0;
+    __syncthreads();
+    const int r0 = blockIdx.x * chunk, r1 = min(r0 + chunk, m);
+    for (int i = r0 + threadIdx.x; i < r1; i += SG_BIN_THREADS) {
+        const int u = size[i];
+        int c = 0;
+        while (c < SG_NCLS - 1 && u > bnd.limit[c]) ++c;
+        cls[i] = c;
+        const unsigned peers = __match_any_sync(__activemask(), c);
+        if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&s_count[c], __popc(peers));
+        if (c == SG_NCLS - 1) atomicMax(&s_max, u);
+    }
+    __syncthreads();
+    if (threadIdx.x < SG_NCLS) {
+        const int v = s_count[threadIdx.x];
+        block_count[blockIdx.x * SG_NCLS + threadIdx.x] = v;
+        if (v) atomicAdd(&class_count[threadIdx.x], v);
+    }
+    if (threadIdx.x == 0 && s_max) atomicMax(max_size, s_max);
 }
 
-__global__ void sg_bin_kernel(const int *__restrict__ cls, int m, int *__restrict__ cursor, int *__restrict__ perm) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m) return;
-    const int c = cls[i];
-    const unsigned active = __activemask();
-    const unsigned peers = __match_any_sync(active, c);
-    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
-    int base = 0;
-    if (lane == leader) base = atomicAdd(&cursor[c], __popc(peers));
-    base = __shfl_sync(peers, base, leader);
-    perm[base + __popc(peers & ((1u << lane) - 1u))] = i;  // rows of a warp stay in ascending order
+// block_count[b][c] -> first slot of CTA b's rows of class c: class start + counts of the CTAs before it
+__global__ void sg_block_offsets_kernel(int *__restrict__ block_count, int nblocks, const int *__restrict__ class_start) {
+    const int c = threadIdx.x;
+    if (c >= SG_NCLS) return;
+    int acc = class_start[c];
+    for (int b = 0; b < nblocks; ++b) {
+        const int v = block_count[b * SG_NCLS + c];
+        block_count[b * SG_NCLS + c] = acc;
+        acc += v;
+    }
+}
+
+__global__ void __launch_bounds__(SG_BIN_THREADS) sg_bin_kernel(const int *__restrict__ cls, int m, int chunk,
+                                                                const int *__restrict__ block_base, int *__restrict__ perm) {
+    constexpr int NW = SG_BIN_THREADS / 32;
+    __shared__ int s_cursor[SG_NCLS];
+    __shared__ int s_wcount[NW][SG_NCLS];
+    if (threadIdx.x < SG_NCLS) s_cursor[threadIdx.x] = block_base[blockIdx.x * SG_NCLS + threadIdx.x];
+    const int r0 = blockIdx.x * chunk, r1 = min(r0 + chunk, m);
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int base = r0; base < r1; base += SG_BIN_THREADS) {
+        if (threadIdx.x < NW * SG_NCLS) (&s_wcount[0][0])[threadIdx.x] = 0;
+        __syncthreads();
+        const int i = base + threadIdx.x;
+        int c = -1, rank = 0;
+        if (i < r1) {
+            c = cls[i];
+            const unsigned peers = __match_any_sync(__activemask(), c);
+            rank = __popc(peers & ((1u << lane) - 1u));
+            if (lane == __ffs(peers) - 1) s_wcount[w][c] = __popc(peers);
+        }
+        __syncthreads();
+        if (c >= 0) {
+            int off = s_cursor[c];
+            for (int v = 0; v < w; ++v) off += s_wcount[v][c];
+            perm[off + rank] = i;
+        }
+        __syncthreads();
+        if (threadIdx.x < SG_NCLS) {
+            int t = 0;
+            for (int v = 0; v < NW; ++v) t += s_wcount[v][threadIdx.x];
+            s_cursor[threadIdx.x] += t;
+        }
+        __syncthreads();  // the counts are cleared at the top of the next round
+    }
 }
 
 struct SgArgs {
@@ -322,8 +474,74 @@ __global__ void __launch_bounds__(256) sg_cta_kernel(SgArgs s) {
     __shared__ int s_cnt;
     const int h = s.hmask + 1;
     const int i = s.perm[blockIdx.x];
-    if (FILL) sg_row_fill<256>(i, threadIdx.x, s.a, s.b, sg_smem, sg_smem + h, s.hmask, &s_cnt, s.c_rp, s.c_col, s.c_val, s.ep);
-    else sg_row_count<256>(i, threadIdx.x, s.a, s.b, sg_smem, s.hmask, &s_cnt, s.row_nnz);
+    if (FILL) {
+        SgStage *stage = reinterpret_cast<SgStage *>(sg_smem + h + (h >> 1));  // 8-byte aligned: h is a multiple of 4
+        sg_row_fill<256>(i, threadIdx.x, s.a, s.b, sg_smem, sg_smem + h, s.hmask, &s_cnt, s.c_rp, s.c_col, s.c_val, s.ep, stage);
+    } else sg_row_count<256>(i, threadIdx.x, s.a, s.b, sg_smem, s.hmask, &s_cnt, s.row_nnz);
+}
+
+// Pass 2 for CTA-class rows when B is narrow (ncols(B) <= SG_DENSE_MAX): one f64 accumulator per
+// column of B in shared memory, so a product costs a load and a read-modify-write -- no hash table, no
+// sort, no slot search (the binary search was 45 % of the instructions of the table kernel on the
+// coarse-level products, ncu source view).  The structural pattern is recorded as one byte per
+// column and compacted in column order at the end: sorted output, explicit zeros kept.
+constexpr int SG_DENSE_MAX = 8192;
+
+__global__ void __launch_bounds__(256) sg_dense_kernel(SgArgs s, int ncols_b) {
+    extern __shared__ __align__(16) int sg_smem[];
+    __shared__ int s_warp_tot[8];
+    __shared__ int s_matched;
+    double *acc = reinterpret_cast<double *>(sg_smem);
+    SgStage *stage = reinterpret_cast<SgStage *>(acc + ncols_b);
+    unsigned char *touched = reinterpret_cast<unsigned char *>(stage + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int i = s.perm[blockIdx.x];
+    for (int t = tid; t < ncols_b; t += 256) { acc[t] = 0.0; touched[t] = 0; }
+    if (tid == 0) s_matched = 0;
+    __syncthreads();
+    const int a0 = s.a.rp[i], a1 = s.a.rp[i + 1];
+    sg_accumulate_staged<true>(tid, s.a, s.b, a0, a1, nullptr, 0, acc, *stage, touched);
+    __syncthreads();
+    // ordered compaction: thread t owns the columns [t*per, (t+1)*per)
+    const int per = (ncols_b + 255) / 256;
+    const int j0 = min(tid * per, ncols_b), j1 = min(j0 + per, ncols_b);
+    int mine = 0;
+    for (int j = j0; j < j1; ++j) mine += touched[j];
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) s_warp_tot[warp] = incl;
+    __syncthreads();
+    int before = incl - mine;
+    for (int w = 0; w < warp; ++w) before += s_warp_tot[w];
+    int pos = s.c_rp[i] + before;
+    if (!s.ep.enabled) {
+        for (int j = j0; j < j1; ++j)
+            if (touched[j]) { s.c_col[pos] = j; s.c_val[pos] = acc[j]; ++pos; }
+        return;
+    }
+    // smooth_interpolation epilogue (see sg_row_fill)
+    double dv = 0.0; bool found = false;
+    {
+        int lo = a0, hi = a1;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (s.a.col[mid] < i) lo = mid + 1; else hi = mid; }
+        if (lo < a1 && s.a.col[lo] == i) { dv = s.a.val[lo]; found = true; }
+    }
+    if (tid == 0 && (!found || !(dv > 1e-6))) atomicMax(s.ep.error_flag, 1);
+    const double scalar = s.ep.omega * (1.0 / dv);
+    const int p0 = s.ep.p.rp[i], p1 = s.ep.p.rp[i + 1];
+    int matched = 0;
+    for (int j = j0; j < j1; ++j) {
+        if (!touched[j]) continue;
+        double v = acc[j] * -scalar;
+        int lo = p0, hi = p1;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (s.ep.p.col[mid] < j) lo = mid + 1; else hi = mid; }
+        if (lo < p1 && s.ep.p.col[lo] == j) { v = v + s.ep.p.val[lo]; ++matched; }
+        s.c_col[pos] = j; s.c_val[pos] = v; ++pos;
+    }
+    if (matched) atomicAdd(&s_matched, matched);
+    __syncthreads();
+    if (tid == 0 && s_matched != p1 - p0) atomicMax(s.ep.error_flag, 2);
 }
 
 // Pass 1 for rows with many candidates when B is not too wide: distinct columns counted with a
@@ -389,16 +607,27 @@ static famg_status sg_run_pass(famg_ctx *ctx, SgArgs base, const int *d_size, in
     for (int c = 0; c < SG_NCLS; ++c) bnd.limit[c] = plan[c].limit;
     int h_counters[16] = {0};
     cudaMemsetAsync(d_counters, 0, sizeof(int) * 16, ctx->stream);
-    sg_classify_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, ctx->stream>>>(d_size, m, bnd, d_cls, d_counters, d_counters + 8);
+    // contiguous chunks of rows per CTA (multiples of the CTA width so warps stay full)
+    const int nblocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(m, SG_BIN_THREADS * 4), 8 * (int64_t)ctx->num_sms));
+    const int chunk = (int)(ceil_div(ceil_div(m, nblocks), SG_BIN_THREADS) * SG_BIN_THREADS);
+    int *d_block = nullptr;
+    const size_t block_bytes = sizeof(int) * (size_t)nblocks * SG_NCLS;
+    FAMG_TRY(pool_alloc(ctx, block_bytes, (void **)&d_block));
+    sg_classify_kernel<<<nblocks, SG_BIN_THREADS, 0, ctx->stream>>>(d_size, m, chunk, bnd, d_cls, d_block, d_counters, d_counters + 8);
     count_launch(ctx);
-    CUDA_TRY(cudaMemcpyAsync(h_counters, d_counters, sizeof(int) * 16, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    cudaError_t ce = cudaMemcpyAsync(h_counters, d_counters, sizeof(int) * 16, cudaMemcpyDeviceToHost, ctx->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
     int h_cursor[SG_NCLS], acc = 0;
     for (int c = 0; c < SG_NCLS; ++c) { h_cursor[c] = acc; acc += h_counters[c]; }
-    CUDA_TRY(cudaMemcpyAsync(d_counters, h_cursor, sizeof(int) * SG_NCLS, cudaMemcpyHostToDevice, ctx->stream));
-    sg_bin_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, ctx->stream>>>(d_cls, m, d_counters, d_perm);
-    count_launch(ctx);
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // h_cursor is a stack buffer
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_counters, h_cursor, sizeof(int) * SG_NCLS, cudaMemcpyHostToDevice, ctx->stream);
+    if (ce == cudaSuccess) {
+        sg_block_offsets_kernel<<<1, 32, 0, ctx->stream>>>(d_block, nblocks, d_counters);
+        sg_bin_kernel<<<nblocks, SG_BIN_THREADS, 0, ctx->stream>>>(d_cls, m, chunk, d_block, d_perm);
+        count_launch(ctx, 2);
+        ce = cudaStreamSynchronize(ctx->stream);  // h_cursor is a stack buffer
+    }
+    pool_free(ctx, d_block, block_bytes);
+    if (ce != cudaSuccess) FAMG_FAIL(FAMG_ERR_CUDA, "spgemm binning failed: %s", cudaGetErrorString(ce));
     const int max_size = h_counters[8];
     int off = 0;
     // merge the open-ended global classes into one launch
@@ -420,6 +649,14 @@ static famg_status sg_run_pass(famg_ctx *ctx, SgArgs base, const int *d_size, in
             KERNEL_CHECK();
             continue;
         }
+        if (FILL && plan[c].kind >= 1 && ncols_b <= SG_DENSE_MAX) {
+            const size_t smem = (size_t)ncols_b * 8 + sizeof(SgStage) + (((size_t)ncols_b + 15) & ~(size_t)15);
+            if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(sg_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+            sg_dense_kernel<<<(unsigned)cnt, 256, smem, ctx->stream>>>(s, ncols_b);
+            count_launch(ctx);
+            KERNEL_CHECK();
+            continue;
+        }
         if (plan[c].kind == 2) { if (global_off < 0) global_off = my_off; global_count += cnt; continue; }
         if (plan[c].kind == 3) {  // tiny rows: one thread per row
             sg_scalar_kernel<FILL><<<(unsigned)ceil_div(cnt, 128), 128, 0, ctx->stream>>>(s);
@@ -434,8 +671,9 @@ static famg_status sg_run_pass(famg_ctx *ctx, SgArgs base, const int *d_size, in
             if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(sg_warp_kernel<FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
             sg_warp_kernel<FILL><<<(unsigned)ceil_div(cnt, SG_WARPS), SG_WARPS * 32, smem, ctx->stream>>>(s);
         } else {
-            if (per_row > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(sg_cta_kernel<FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            sg_cta_kernel<FILL><<<(unsigned)cnt, 256, per_row, ctx->stream>>>(s);
+            const size_t cta_smem = per_row + (FILL ? sizeof(SgStage) : 0);
+            if (cta_smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(sg_cta_kernel<FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));  // 227 KB opt-in limit minus the static s_cnt
+            sg_cta_kernel<FILL><<<(unsigned)cnt, 256, cta_smem, ctx->stream>>>(s);
         }
         count_launch(ctx);
         KERNEL_CHECK();

@@ -41,38 +41,39 @@ __device__ __forceinline__ void qr_load_tile(double (*tile)[QR_LDT], const doubl
     }
 }
 
-// partial Gram matrices, one per CTA: partials[blockIdx][i + j*k].  Thread (ti, tj) of a 16 x 16
-// grid owns the 4 x 4 entries {ti + 16a} x {tj + 16b}: per tile row 8 shared loads (consecutive ti
-// -> consecutive words; tj is warp-uniform up to 2 values -> broadcast) feed 16 FMAs.
+// partial Gram matrices, one per CTA: partials[blockIdx][i + j*k].  KB = ceil(k / 16).  Thread (ti, tj)
+// of a 16 x 16 grid owns the KB x KB entries {ti + 16a} x {tj + 16b}: per tile row 2 KB shared loads
+// (consecutive ti -> consecutive words; tj takes 2 values per warp -> broadcast) feed KB^2 FMAs.
+template <int KB>
 __global__ void __launch_bounds__(QR_THREADS) gram_partial_kernel(const double *__restrict__ x, long long ld, long long n, int k,
                                                                   double *__restrict__ partials) {
     __shared__ double tile[QR_TILE][QR_LDT];
     for (int t = threadIdx.x; t < QR_TILE * QR_LDT; t += QR_THREADS) (&tile[0][0])[t] = 0.0;  // columns >= k stay zero
     const int ti = threadIdx.x & 15, tj = threadIdx.x >> 4;
-    double acc[4][4];
+    double acc[KB][KB];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < KB; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+        for (int b = 0; b < KB; ++b) acc[a][b] = 0.0;
     for (long long r0 = (long long)blockIdx.x * QR_TILE; r0 < n; r0 += (long long)gridDim.x * QR_TILE) {
         __syncthreads();
         qr_load_tile(tile, x, ld, n, r0, k);
         __syncthreads();
 #pragma unroll 4
         for (int r = 0; r < QR_TILE; ++r) {
-            double xi[4], xj[4];
+            double xi[KB], xj[KB];
 #pragma unroll
-            for (int a = 0; a < 4; ++a) { xi[a] = tile[r][ti + 16 * a]; xj[a] = tile[r][tj + 16 * a]; }
+            for (int a = 0; a < KB; ++a) { xi[a] = tile[r][ti + 16 * a]; xj[a] = tile[r][tj + 16 * a]; }
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
+            for (int a = 0; a < KB; ++a)
 #pragma unroll
-                for (int b = 0; b < 4; ++b) acc[a][b] = fma(xi[a], xj[b], acc[a][b]);
+                for (int b = 0; b < KB; ++b) acc[a][b] = fma(xi[a], xj[b], acc[a][b]);
         }
     }
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < KB; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
+        for (int b = 0; b < KB; ++b) {
             const int i = ti + 16 * a, j = tj + 16 * b;
             if (i < k && j < k) partials[(long long)blockIdx.x * k * k + i + j * k] = acc[a][b];
         }
@@ -88,38 +89,58 @@ __global__ void sum_partials_kernel(const double *__restrict__ partials, int npa
 }
 
 // X <- X * Rinv (upper triangular; passed ROW-major and zero-padded to QR_MAXK columns), in place.
-// Thread (r = tid % 64, g = tid / 64) owns row r and the 16 columns [16g, 16g + 16): per inner index
-// one tile load and 16 warp-uniform (broadcast) coefficient loads feed 16 FMAs.
+// Thread (r = tid % 64, g = tid / 64) owns row r and the CPT = 4 KB columns [g CPT, (g + 1) CPT): per
+// inner index one tile load and CPT warp-uniform (broadcast) coefficient loads feed CPT FMAs.
+template <int KB>
 __global__ void __launch_bounds__(QR_THREADS) apply_rinv_kernel(double *__restrict__ x, long long ld, long long n, int k,
                                                                 const double *__restrict__ rinv_rm) {
+    constexpr int CPT = 4 * KB;
     extern __shared__ __align__(16) double qr_smem[];  // tile, then Rinv (k x QR_MAXK)
     double (*tile)[QR_LDT] = reinterpret_cast<double (*)[QR_LDT]>(qr_smem);
     double *rs = qr_smem + QR_TILE * QR_LDT;
     for (int t = threadIdx.x; t < k * QR_MAXK; t += QR_THREADS) rs[t] = rinv_rm[t];
     const int r = threadIdx.x % QR_TILE, g = threadIdx.x / QR_TILE;
-    const int j0 = g * 16;
-    const int iend = min(k, j0 + 16);  // Rinv[i][j] = 0 for i > j
+    const int j0 = g * CPT;
+    const int iend = min(k, j0 + CPT);  // Rinv[i][j] = 0 for i > j
     for (long long r0 = (long long)blockIdx.x * QR_TILE; r0 < n; r0 += (long long)gridDim.x * QR_TILE) {
         __syncthreads();
         qr_load_tile(tile, x, ld, n, r0, k);
         __syncthreads();
         if (j0 < k) {
-            double acc[16];
+            double acc[CPT];
 #pragma unroll
-            for (int b = 0; b < 16; ++b) acc[b] = 0.0;
+            for (int b = 0; b < CPT; ++b) acc[b] = 0.0;
             for (int i = 0; i < iend; ++i) {
                 const double xv = tile[r][i];
                 const double *c = rs + i * QR_MAXK + j0;
 #pragma unroll
-                for (int b = 0; b < 16; ++b) acc[b] = fma(xv, c[b], acc[b]);
+                for (int b = 0; b < CPT; ++b) acc[b] = fma(xv, c[b], acc[b]);
             }
             if (r0 + r < n) {
 #pragma unroll
-                for (int b = 0; b < 16; ++b)
+                for (int b = 0; b < CPT; ++b)
                     if (j0 + b < k) x[(long long)(j0 + b) * ld + r0 + r] = acc[b];
             }
         }
     }
+}
+
+template <int KB>
+static famg_status launch_gram(cudaStream_t st, int grid, const double *x, int64_t ld, int64_t n, int k, double *partials) {
+    gram_partial_kernel<KB><<<grid, QR_THREADS, 0, st>>>(x, ld, n, k, partials);
+    return FAMG_OK;
+}
+template <int KB>
+static famg_status launch_rinv(cudaStream_t st, int grid, double *x, int64_t ld, int64_t n, int k, const double *d_rinv) {
+    constexpr int SMEM_MAX = (int)(sizeof(double) * (QR_TILE * QR_LDT + QR_MAXK * QR_MAXK));
+    static bool configured = false;  // per template instance
+    if (!configured) {
+        CUDA_TRY(cudaFuncSetAttribute(apply_rinv_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+        configured = true;
+    }
+    const size_t smem = sizeof(double) * ((size_t)QR_TILE * QR_LDT + (size_t)k * QR_MAXK);
+    apply_rinv_kernel<KB><<<grid, QR_THREADS, smem, st>>>(x, ld, n, k, d_rinv);
+    return FAMG_OK;
 }
 
 // per-column dot products: grid (nblk, k); partials[c * nblk + blk]
@@ -157,7 +178,13 @@ static inline int qr_grid(famg_ctx *ctx, int64_t n) {
 static famg_status cholqr_pass(famg_ctx *ctx, double *x, int64_t ld, int64_t n, int k, double *d_work, int grid) {
     const int kk = k * k;
     double *partials = d_work, *d_g = d_work + (size_t)grid * kk, *d_rinv = d_g + kk;
-    gram_partial_kernel<<<grid, QR_THREADS, 0, ctx->stream>>>(x, ld, n, k, partials);
+    const int kb = (k + 15) / 16;
+    switch (kb) {
+        case 1: FAMG_TRY(launch_gram<1>(ctx->stream, grid, x, ld, n, k, partials)); break;
+        case 2: FAMG_TRY(launch_gram<2>(ctx->stream, grid, x, ld, n, k, partials)); break;
+        case 3: FAMG_TRY(launch_gram<3>(ctx->stream, grid, x, ld, n, k, partials)); break;
+        default: FAMG_TRY(launch_gram<4>(ctx->stream, grid, x, ld, n, k, partials)); break;
+    }
     sum_partials_kernel<<<(kk + 255) / 256, 256, 0, ctx->stream>>>(partials, grid, kk, d_g);
     count_launch(ctx, 2);
     KERNEL_CHECK();
@@ -188,14 +215,12 @@ static famg_status cholqr_pass(famg_ctx *ctx, double *x, int64_t ld, int64_t n, 
     for (int i = 0; i < k; ++i)
         for (int j = i; j < k; ++j) rinv[(size_t)i * QR_MAXK + j] = linv[(size_t)j + (size_t)i * k];
     CUDA_TRY(cudaMemcpyAsync(d_rinv, rinv.data(), sizeof(double) * k * QR_MAXK, cudaMemcpyHostToDevice, ctx->stream));
-    constexpr int SMEM_MAX = (int)(sizeof(double) * (QR_TILE * QR_LDT + QR_MAXK * QR_MAXK));
-    static bool configured = false;
-    if (!configured) {
-        CUDA_TRY(cudaFuncSetAttribute(apply_rinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
-        configured = true;
+    switch (kb) {
+        case 1: FAMG_TRY(launch_rinv<1>(ctx->stream, grid, x, ld, n, k, d_rinv)); break;
+        case 2: FAMG_TRY(launch_rinv<2>(ctx->stream, grid, x, ld, n, k, d_rinv)); break;
+        case 3: FAMG_TRY(launch_rinv<3>(ctx->stream, grid, x, ld, n, k, d_rinv)); break;
+        default: FAMG_TRY(launch_rinv<4>(ctx->stream, grid, x, ld, n, k, d_rinv)); break;
     }
-    const size_t smem = sizeof(double) * ((size_t)QR_TILE * QR_LDT + (size_t)k * QR_MAXK);
-    apply_rinv_kernel<<<grid, QR_THREADS, smem, ctx->stream>>>(x, ld, n, k, d_rinv);
     count_launch(ctx);
     KERNEL_CHECK();
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // rinv is a host temporary

@@ -184,6 +184,51 @@ inline Partition geometric_partition(const int64_t dims[3], const int64_t block[
     return p;
 }
 
+// partitioners/mod.rs PartitionerConfig (:249-329): the algebraic partitioner (least-squares strength
+// graph -> greedy modularity matching -> node-swap refinement), host-only, with the documented
+// tie-breaking of csrc/partition.cu.  `build_partition` takes the host CSR pattern of the operator.
+struct PartitionerConfig {
+    double coarsening_factor = 8.0, agg_size_penalty = 1.0;  // :257-266
+    int64_t max_improvement_iters = 100;
+    Partition build_partition(int64_t n, const uint64_t *row_ptr, const uint64_t *col_idx, const std::vector<double> &near_null, int64_t k,
+                              const std::vector<double> &weights) const {
+        famg_graph *g = nullptr;
+        check(famg_strength_graph_create(n, row_ptr, col_idx, near_null.data(), n, k, weights.data(), 3, &g));  // depth 3, :290
+        std::vector<uint64_t> node_to_agg((size_t)n);
+        int64_t naggs = 0;
+        famg_status st = famg_partition_modularity(g, coarsening_factor, agg_size_penalty, max_improvement_iters, node_to_agg.data(), &naggs);
+        famg_graph_destroy(g);
+        check(st);
+        Partition p;  // Partition::from_node_to_agg (:86-93)
+        p.agg_ptr.assign((size_t)naggs + 1, 0);
+        for (uint64_t a : node_to_agg) ++p.agg_ptr[(size_t)a + 1];
+        for (int64_t a = 0; a < naggs; ++a) p.agg_ptr[(size_t)a + 1] += p.agg_ptr[(size_t)a];
+        p.agg_nodes.resize((size_t)n);
+        std::vector<uint64_t> fill(p.agg_ptr.begin(), p.agg_ptr.end() - 1);
+        for (int64_t i = 0; i < n; ++i) p.agg_nodes[(size_t)fill[(size_t)node_to_agg[(size_t)i]]++] = (uint64_t)i;
+        return p;
+    }
+    Partition build_partition(const SparseRowMat &mat, const std::vector<double> &near_null, int64_t k, const std::vector<double> &weights) const {
+        std::vector<uint64_t> rp((size_t)mat.nrows() + 1), ci((size_t)std::max<int64_t>(mat.compute_nnz(), 1));
+        std::vector<double> v(ci.size());
+        check(famg_csr_download(mat.raw(), rp.data(), ci.data(), v.data()));
+        return build_partition(mat.nrows(), rp.data(), ci.data(), near_null, k, weights);
+    }
+};
+
+// adaptivity.rs ErrorPropogator (:168-198) and smooth_vector (:307-390), device-resident.
+struct ErrorPropogator {
+    const SparseRowMat &op;
+    const Smoother &pc;
+    void apply(DeviceMat &out, const DeviceMat &x) const { check(famg_error_propagator_dev(op.raw(), pc.raw(), out.raw(), x.raw())); }
+};
+// x: the caller's random start block (n x k, k <= 64), replaced by the smooth basis; returns ||E w||_A / ||w||_A per column
+inline std::vector<double> smooth_vector(const SparseRowMat &mat, const Smoother &pc, int64_t iterations, DeviceMat &x) {
+    std::vector<double> cfs((size_t)x.ncols());
+    check(famg_smooth_vector_dev(mat.raw(), pc.raw(), iterations, x.raw(), cfs.data()));
+    return cfs;
+}
+
 // interpolation/mod.rs GalerkinCoarse (:34-40)
 struct GalerkinCoarse {
     std::shared_ptr<SparseRowMat> interpolation, restriction, coarse_mat;

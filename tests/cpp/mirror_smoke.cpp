@@ -8,6 +8,21 @@
 
 int main() {
     try {
+        {   // host-only: the algebraic partitioner (PartitionerConfig::build_partition) needs no device
+            const int64_t n = 64;
+            std::vector<uint64_t> rp{0}, ci;
+            for (int64_t i = 0; i < n; ++i) {
+                if (i > 0) ci.push_back((uint64_t)(i - 1));
+                ci.push_back((uint64_t)i);
+                if (i + 1 < n) ci.push_back((uint64_t)(i + 1));
+                rp.push_back((uint64_t)ci.size());
+            }
+            std::vector<double> nn((size_t)n, 0.125), w{1.0};
+            famg::PartitionerConfig pc; pc.coarsening_factor = 4.0; pc.max_improvement_iters = 10;
+            famg::Partition part = pc.build_partition(n, rp.data(), ci.data(), nn, 1, w);
+            if (part.nnodes() != n || part.naggs() < 8 || part.naggs() > 20) return 1;
+            std::printf("partitioner ok: %lld nodes -> %lld aggregates\n", (long long)n, (long long)part.naggs());
+        }
         famg::Context ctx(0);
         const int64_t n = 63, nc = 31;
         std::vector<uint64_t> r, c; std::vector<double> v;

@@ -73,3 +73,4 @@ def test_cpp_mirror_links_and_fails_loudly_without_gpu():
         assert out.returncode == 0 and "mirror ok" in out.stdout, out.stdout + out.stderr
     else:
         assert out.returncode == 3 and "no CPU fallback" in out.stdout
+    assert "partitioner ok" in out.stdout  # the host-only partitioner runs with or without a device

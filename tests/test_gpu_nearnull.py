@@ -62,7 +62,8 @@ def test_coldot_and_create_weights(ctx, F):
     rng = np.random.default_rng(2)
     x, y = rng.standard_normal((50001, 7)), rng.standard_normal((50001, 7))
     out = np.zeros(7)
-    call("famg_vec_coldot", F.DeviceMat.from_host(ctx, x)._h, F.DeviceMat.from_host(ctx, y)._h, _f(out))
+    dx, dy = F.DeviceMat.from_host(ctx, x), F.DeviceMat.from_host(ctx, y)  # keep the handles alive across the call
+    call("famg_vec_coldot", dx._h, dy._h, _f(out))
     want = np.einsum("ij,ij->j", x, y)
     assert np.max(np.abs(out - want) / np.einsum("ij,ij->j", np.abs(x), np.abs(y))) < 1e-14
     o = O.gen_g7(9, 8, 7)

@@ -208,6 +208,15 @@ def test_spgemm_bit_exact_all_size_classes(ctx, F):
     _check_product(ctx, F, random_csr(rng, 40, 400, rng.integers(60, 90, 40)), random_csr(rng, 400, 3000, rng.integers(40, 90, 400)))
     a = random_csr(rng, 12, 500, rng.integers(150, 200, 12))
     _check_product(ctx, F, a, random_csr(rng, 500, 6000, rng.integers(60, 110, 500)))
+    # staged CTA-per-row accumulation: B rows longer than one staging batch (2048 entries: split
+    # segments, whole-CTA accumulation), and thousands of short B rows per output row (64-segment
+    # batches, single-warp accumulation)
+    _check_product(ctx, F, random_csr(rng, 6, 300, rng.integers(100, 200, 6)), random_csr(rng, 300, 6000, rng.integers(1800, 5000, 300)))
+    _check_product(ctx, F, random_csr(rng, 9, 4000, rng.integers(1000, 2500, 9)), random_csr(rng, 4000, 3000, rng.integers(0, 14, 4000)))
+    # the same two shapes with B wider than the dense-accumulator limit (8192 columns): hash table,
+    # sort and slot search, staged accumulation
+    _check_product(ctx, F, random_csr(rng, 5, 300, rng.integers(100, 200, 5)), random_csr(rng, 300, 12000, rng.integers(300, 3000, 300)))
+    _check_product(ctx, F, random_csr(rng, 7, 4000, rng.integers(1000, 2500, 7)), random_csr(rng, 4000, 12000, rng.integers(0, 14, 4000)))
     # explicit zeros are kept (cancellation must not prune)
     z = O.Csr.from_triplets(2, 2, [0, 0, 1], [0, 1, 1], [1.0, -1.0, 1.0])
     w = O.Csr.from_triplets(2, 1, [0, 1], [0, 0], [1.0, 1.0])
