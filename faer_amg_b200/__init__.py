@@ -9,8 +9,8 @@ from . import _ffi  # noqa: F401
 from ._ffi import FamgError  # noqa: F401
 from .core import Context, DeviceMat, ParSpmmOp, SparseMatOp, SparseRowMat, PAR_BLOCK_SIZE  # noqa: F401
 from .hierarchy import Hierarchy, HierarchyConfig  # noqa: F401
-from .interpolation import (AggregationConfig, GalerkinCoarse, InterpolationConfig, galerkin_product,  # noqa: F401
-                            smooth_interpolation, smoothed_aggregation, tentative_prolongator)
+from .interpolation import (AggregationConfig, GalerkinCoarse, InterpolationConfig, block_jacobi, galerkin_product,  # noqa: F401
+                            smooth_interpolation, smooth_p, smoothed_aggregation, tentative_prolongator)
 from .partitioners import (GeometricPartitioner, Partition, PartitionerConfig, StrengthGraph,  # noqa: F401
                            geometric_partition)
 from . import partitioners  # noqa: F401

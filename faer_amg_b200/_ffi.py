@@ -74,6 +74,7 @@ SIGNATURES = {
     "famg_smoother_diag_from_host": [vp, i64, f64p, vpp],
     "famg_smoother_cholesky": [vp, vpp],
     "famg_smoother_block": [vp, i64, u64p, u64p, vpp],
+    "famg_smoother_block_vector": [vp, i64, i64, u64p, u64p, vpp],
     "famg_smoother_retain": [vp],
     "famg_smoother_destroy": [vp],
     "famg_smoother_dim": [vp, i64p],
@@ -94,6 +95,9 @@ SIGNATURES = {
     "famg_transpose": [vp, vpp],
     "famg_smooth_interpolation": [vp, vp, f64, vpp],
     "famg_galerkin": [vp, vp, cint, f64, vpp, vpp, vpp],
+    "famg_galerkin_block": [vp, vp, i64, cint, f64, vpp, vpp, vpp],
+    "famg_block_jacobi": [vp, i64, vp, vpp],
+    "famg_smooth_p": [vp, vp, vp, vpp],
     "famg_tentative_p": [vp, i64, i64, i64, i64, f64p, i64, i64, u64p, u64p, vpp, f64p],
     "famg_thin_q": [i64, i64, f64p, i64],
     "famg_thin_q_dev": [vp],
@@ -102,6 +106,7 @@ SIGNATURES = {
     "famg_vec_coldot": [vp, vp, f64p],
     "famg_strength_graph_create": [i64, u64p, u64p, f64p, i64, i64, f64p, i64, vpp],
     "famg_graph_create": [i64, u64p, u64p, f64p, vpp],
+    "famg_graph_block_reduce": [vp, i64],
     "famg_graph_dims": [vp, i64p, i64p],
     "famg_graph_download": [vp, u64p, u64p, f64p],
     "famg_graph_destroy": [vp],

@@ -190,6 +190,9 @@ famg_status dense_gemv(famg_ctx *ctx, const double *inv, int64_t n, const double
 famg_status smoother_apply_dev(const famg_smoother *s, const double *in, int64_t ldi, double *out, int64_t ldo,
                                int k, cudaStream_t st = nullptr);
 
+// one-sided Jacobi thin SVD of an m x k column-major block held in u (in: A, out: U); gallery.cu
+void host_thin_svd(int64_t m, int64_t k, std::vector<double> &u, std::vector<double> &s, std::vector<double> &v);
+
 // host copies of a device CSR (setup-time helpers)
 struct HostCsr {
     int64_t nrows = 0, ncols = 0;

@@ -109,7 +109,7 @@ static famg_status gallery_build(famg_ctx *ctx, int64_t nx, int64_t ny, int64_t 
 // One-sided Jacobi thin SVD of an m x k column-major block (k is the near-null width: tiny).
 // Stands in for faer thin_svd (interpolation/mod.rs:770), whose column signs are not knowable
 // here; convention: singular values descending, largest-magnitude entry of each v_j positive.
-static void host_thin_svd(int64_t m, int64_t k, std::vector<double> &u, std::vector<double> &s, std::vector<double> &v) {
+void host_thin_svd(int64_t m, int64_t k, std::vector<double> &u, std::vector<double> &s, std::vector<double> &v) {
     v.assign((size_t)(k * k), 0.0);
     s.assign((size_t)k, 0.0);
     for (int64_t i = 0; i < k; ++i) v[(size_t)(i + i * k)] = 1.0;

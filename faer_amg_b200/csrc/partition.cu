@@ -27,7 +27,9 @@
 //   TIE-BREAK 5  swaps sorted descending by gain: stable over ascending node id
 // Reference bug F10c (`pairwise_merge_rowsums` writes the unmatched row sums at `new_idx` instead of
 // `new_idx + pairs.len()`, modularity.rs:299-301) is fixed: the evident intent is implemented.
-// block_size > 1 (`strength.aggregate(&block_reduce)`, mod.rs:293-300) is not built.
+//   TIE-BREAK 6  AdjacencyList::aggregate (block_size > 1, mod.rs:293-300, 465-496, 588-656): the k-way merge
+//                pops a BinaryHeap keyed by neighbour id only; equal ids are summed here in ascending
+//                (member of the aggregate, position in its list) order
 #include <cmath>
 #include <queue>
 
@@ -395,6 +397,49 @@ famg_status famg_graph_create(int64_t n, const uint64_t *row_ptr, const uint64_t
             g->nodes[(size_t)i].emplace_back((int64_t)col_idx[q], w[q]);
         }
     *out = g;
+    return FAMG_OK;
+}
+
+// strength.aggregate(&block_reduce); strength.filter_diag()  (partitioners/mod.rs:293-300): dofs -> nodes of
+// `block_size` consecutive dofs.  aggregate (:465-496): neighbour ids mapped to node ids, the lists of a
+// node's dofs merged with equal ids summed (merge_agg, :588-656), every weight divided by the largest
+// merged weight of the whole graph (self loops included, as the reference does); then self loops dropped.
+famg_status famg_graph_block_reduce(famg_graph *g, int64_t block_size) {
+    if (!g || block_size < 1) FAMG_FAIL(FAMG_ERR_INVALID, "graph: bad argument");
+    const int64_t n = (int64_t)g->nodes.size();
+    if (n % block_size != 0) FAMG_FAIL(FAMG_ERR_INVALID, "graph: size is not a multiple of the block size");
+    if (block_size == 1) return FAMG_OK;
+    const int64_t nb = n / block_size;
+    std::vector<std::vector<std::pair<int64_t, double>>> merged((size_t)nb);
+    std::vector<double> local_max((size_t)nb, 0.0);
+    bool empty = false;
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int64_t b = 0; b < nb; ++b) {
+        std::vector<std::pair<int64_t, double>> all;
+        for (int64_t o = 0; o < block_size; ++o) {
+            const auto &nbrs = g->nodes[(size_t)(b * block_size + o)];
+            if (nbrs.empty()) empty = true;
+            for (const auto &e : nbrs) all.emplace_back(e.first / block_size, e.second);
+        }
+        std::stable_sort(all.begin(), all.end(), [](const std::pair<int64_t, double> &x, const std::pair<int64_t, double> &y) { return x.first < y.first; });  // TIE-BREAK 2 + 6
+        auto &out = merged[(size_t)b];
+        for (const auto &e : all) {
+            if (!out.empty() && out.back().first == e.first) out.back().second += e.second;
+            else out.push_back(e);
+        }
+        double mx = out.empty() ? 0.0 : out[0].second;
+        for (const auto &e : out) mx = std::max(mx, e.second);
+        local_max[(size_t)b] = mx;
+    }
+    if (empty) FAMG_FAIL(FAMG_ERR_INVALID, "empty neighborhood means graph is disconnected");
+    double mx = local_max.empty() ? 1.0 : local_max[0];
+    for (double v : local_max) mx = std::max(mx, v);
+    for (int64_t b = 0; b < nb; ++b) {
+        auto &row = merged[(size_t)b];
+        for (auto &e : row) e.second /= mx;
+        row.erase(std::remove_if(row.begin(), row.end(), [b](const std::pair<int64_t, double> &e) { return e.first == b; }), row.end());  // filter_diag (:498-502)
+    }
+    g->nodes.swap(merged);
     return FAMG_OK;
 }
 

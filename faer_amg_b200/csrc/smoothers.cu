@@ -266,6 +266,115 @@ famg_status famg_smoother_block(const famg_csr *a, int64_t n_aggs, const uint64_
     return FAMG_OK;
 }
 
+// BlockSmoother::new for vdim > 1 (block_smoothers.rs:88-123 with diagonally_compensate_vector, :326-400):
+// the partition is over *nodes* of vdim dofs each.  Per aggregate: couplings to nodes of the aggregate are
+// kept; every coupling block A_IJ to a node J outside is lumped into node I's diagonal block as
+// 0.5 * U S U^T with -A_IJ = U S V^T (the symmetric polar factor; independent of the SVD's sign choices).
+// The reference walks a HashSet of the blocks to lump (arbitrary order); here they are added in ascending
+// (I, J) order.  The block is solved exactly (Cholesky) and materialised as rows of the block-diagonal M^-1.
+famg_status famg_smoother_block_vector(const famg_csr *a, int64_t vdim, int64_t n_aggs, const uint64_t *agg_ptr,
+                                       const uint64_t *agg_nodes, famg_smoother **out) {
+    if (!a || !out || !agg_ptr || !agg_nodes || n_aggs < 0 || vdim < 1 || vdim > 64) FAMG_FAIL(FAMG_ERR_INVALID, "bad argument");
+    if (vdim == 1) return famg_smoother_block(a, n_aggs, agg_ptr, agg_nodes, out);  // block_smoothers.rs:98-102
+    *out = nullptr;
+    if (a->nrows != a->ncols || a->nrows % vdim != 0) FAMG_FAIL(FAMG_ERR_INVALID, "block smoother needs a square matrix of vdim-sized nodes");
+    const int64_t n = a->nrows, nnodes = n / vdim;
+    if ((int64_t)agg_ptr[n_aggs] != nnodes) FAMG_FAIL(FAMG_ERR_INVALID, "partition does not cover the matrix");  // block_smoothers.rs:91
+    CUDA_TRY(cudaSetDevice(a->ctx->device));
+    HostCsr h;
+    FAMG_TRY(csr_to_host(a, &h));
+    std::vector<int64_t> node_agg((size_t)nnodes, -1), node_local((size_t)nnodes, 0);
+    for (int64_t g = 0; g < n_aggs; ++g)
+        for (uint64_t u = agg_ptr[g]; u < agg_ptr[g + 1]; ++u) {
+            const uint64_t node = agg_nodes[u];
+            if (node >= (uint64_t)nnodes || node_agg[(size_t)node] != -1) FAMG_FAIL(FAMG_ERR_INVALID, "invalid partition");
+            if (u > agg_ptr[g] && agg_nodes[u - 1] >= node) FAMG_FAIL(FAMG_ERR_INVALID, "aggregate nodes must ascend");
+            node_agg[(size_t)node] = g; node_local[(size_t)node] = (int64_t)(u - agg_ptr[g]);
+        }
+    std::vector<int> rp((size_t)n + 1, 0);
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t g = node_agg[(size_t)(i / vdim)];
+        rp[(size_t)i + 1] = rp[(size_t)i] + (int)((agg_ptr[g + 1] - agg_ptr[g]) * (uint64_t)vdim);
+    }
+    std::vector<int> ci((size_t)rp[(size_t)n]);
+    std::vector<double> cv((size_t)rp[(size_t)n]);
+    const int vd = (int)vdim;
+    int failed = 0;
+#pragma omp parallel
+    {
+        std::vector<double> blk, diag, u, sv, vv, usut((size_t)vd * vd);
+        std::vector<int64_t> outside;
+#pragma omp for schedule(dynamic, 16)
+        for (int64_t g = 0; g < n_aggs; ++g) {
+            const int na = (int)(agg_ptr[g + 1] - agg_ptr[g]);
+            const int bd = na * vd;
+            const uint64_t *nodes = agg_nodes + agg_ptr[g];
+            blk.assign((size_t)bd * bd, 0.0);
+            diag.assign((size_t)na * vd * vd, 0.0);  // per node, row-major vd x vd
+            for (int li = 0; li < na; ++li) {
+                const int64_t bi = (int64_t)nodes[li];
+                outside.clear();
+                for (int oi = 0; oi < vd; ++oi) {
+                    const int64_t i = bi * vd + oi;
+                    for (int q = h.row_ptr[(size_t)i]; q < h.row_ptr[(size_t)i + 1]; ++q) {
+                        const int64_t j = h.col[(size_t)q], bj = j / vd;
+                        const int oj = (int)(j % vd);
+                        if (bj == bi) diag[((size_t)li * vd + oi) * vd + oj] = h.val[(size_t)q];
+                        else if (node_agg[(size_t)bj] == g) blk[(size_t)(li * vd + oi) + (size_t)(node_local[(size_t)bj] * vd + oj) * bd] = h.val[(size_t)q];
+                        else outside.push_back(bj);
+                    }
+                }
+                std::sort(outside.begin(), outside.end());
+                outside.erase(std::unique(outside.begin(), outside.end()), outside.end());
+                for (int64_t bj : outside) {
+                    u.assign((size_t)vd * vd, 0.0);  // -A_IJ, column-major
+                    for (int oi = 0; oi < vd; ++oi) {
+                        const int64_t i = bi * vd + oi;
+                        for (int q = h.row_ptr[(size_t)i]; q < h.row_ptr[(size_t)i + 1]; ++q) {
+                            const int64_t j = h.col[(size_t)q];
+                            if (j / vd == bj) u[(size_t)oi + (size_t)(j % vd) * vd] -= h.val[(size_t)q];
+                        }
+                    }
+                    host_thin_svd(vd, vd, u, sv, vv);
+                    for (int r = 0; r < vd; ++r)
+                        for (int c = 0; c < vd; ++c) {
+                            double t = 0.0;
+                            for (int e = 0; e < vd; ++e) t += u[(size_t)r + (size_t)e * vd] * (sv[(size_t)e] * u[(size_t)c + (size_t)e * vd]);
+                            usut[(size_t)r * vd + c] = t;
+                        }
+                    for (int e = 0; e < vd * vd; ++e) diag[(size_t)li * vd * vd + e] += 0.5 * usut[(size_t)e];
+                }
+                for (int oi = 0; oi < vd; ++oi)
+                    for (int oj = 0; oj < vd; ++oj) blk[(size_t)(li * vd + oi) + (size_t)(li * vd + oj) * bd] = diag[((size_t)li * vd + oi) * vd + oj];
+            }
+            // the reference factorises the upper side of the transpose == lower triangle of the block
+            for (int c = 0; c < bd; ++c)
+                for (int r = 0; r < c; ++r) blk[(size_t)r + (size_t)c * bd] = blk[(size_t)c + (size_t)r * bd];
+            if (!host_spd_inverse(bd, blk)) {
+#pragma omp atomic write
+                failed = 1;
+                continue;
+            }
+            for (int li = 0; li < na; ++li)
+                for (int oi = 0; oi < vd; ++oi) {
+                    const int64_t i = (int64_t)nodes[li] * vd + oi;
+                    for (int lj = 0; lj < na; ++lj)
+                        for (int oj = 0; oj < vd; ++oj) {
+                            ci[(size_t)rp[(size_t)i] + lj * vd + oj] = (int)((int64_t)nodes[lj] * vd + oj);
+                            cv[(size_t)rp[(size_t)i] + lj * vd + oj] = blk[(size_t)(li * vd + oi) + (size_t)(lj * vd + oj) * bd];
+                        }
+                }
+        }
+    }
+    if (failed) FAMG_FAIL(FAMG_ERR_NUMERIC, "an aggregate block is not positive definite");
+    famg_smoother *s = new famg_smoother();
+    s->ctx = a->ctx; s->kind = SM_SPARSE_INV; s->n = n;
+    famg_status st = csr_from_host_i32(a->ctx, n, n, rp.data(), ci.data(), cv.data(), &s->minv);
+    if (st != FAMG_OK) { smoother_release(s); return st; }
+    *out = s;
+    return FAMG_OK;
+}
+
 famg_status famg_smoother_retain(famg_smoother *s) {
     if (!s) FAMG_FAIL(FAMG_ERR_INVALID, "null smoother");
     s->refs.fetch_add(1);

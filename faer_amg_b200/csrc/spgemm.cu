@@ -25,14 +25,23 @@
 
 namespace famg {
 
+constexpr double JACOBI_WEIGHT_BLOCK = 0.66;  // hard-coded in block_jacobi (interpolation/mod.rs:1009)
+
 struct SgMat { const int *rp; const int *col; const double *val; };
 
 struct SgEpilogue {
-    int enabled;          // smooth_interpolation
+    int enabled;          // 0 none | 1 S_i <- -(w/a_ii) S_i + P_i (smooth_interpolation) | 2 S_i <- S_i + P_i (block_jacobi)
+                          // | 3 S_i <- -S_i + P_i (smooth_p)
     double omega;
     SgMat p;              // P (same rows as C)
     int *error_flag;      // 1: missing / tiny diagonal, 2: pattern(P) not in pattern(A P)
 };
+
+// epilogue scaling of one accumulated value (see SgEpilogue::enabled); negation is exact, so kind 3
+// equals the reference's `m_inv * (-(A P))` bit for bit
+__device__ __forceinline__ double sg_epi_scale(int kind, double v, double scalar) {
+    return kind == 1 ? v * -scalar : kind == 3 ? -v : v;
+}
 
 __device__ __forceinline__ unsigned sg_hash(int j, int hmask) { return ((unsigned)j * 2654435761u >> 8) & (unsigned)hmask; }
 
@@ -253,13 +262,13 @@ __device__ void sg_row_fill(int i, int lane, const SgMat &a, const SgMat &b, int
             while (lo < hi) { const int mid = (lo + hi) >> 1; if (a.col[mid] < i) lo = mid + 1; else hi = mid; }
             if (lo < a1 && a.col[lo] == i) { dv = a.val[lo]; found = true; }
         }
-        if (lane == 0 && (!found || !(dv > 1e-6))) atomicMax(ep.error_flag, 1);
+        if (lane == 0 && ep.enabled == 1 && (!found || !(dv > 1e-6))) atomicMax(ep.error_flag, 1);
         const double scalar = ep.omega * (1.0 / dv);
         const int p0 = ep.p.rp[i], p1 = ep.p.rp[i + 1];
         int matched = 0;
         for (int t = lane; t < n; t += GROUP) {
             const int j = list[t];
-            double v = vals[t] * -scalar;
+            double v = sg_epi_scale(ep.enabled, vals[t], scalar);
             int lo = p0, hi = p1;
             while (lo < hi) { const int mid = (lo + hi) >> 1; if (ep.p.col[mid] < j) lo = mid + 1; else hi = mid; }
             if (lo < p1 && ep.p.col[lo] == j) { v = v + ep.p.val[lo]; ++matched; }
@@ -439,12 +448,12 @@ __global__ void __launch_bounds__(128) sg_scalar_kernel(SgArgs s) {
     }
     double dv = 0.0; bool found = false;
     for (int q = a0; q < a1; ++q) if (s.a.col[q] == i) { dv = s.a.val[q]; found = true; break; }
-    if (!found || !(dv > 1e-6)) atomicMax(s.ep.error_flag, 1);
+    if (s.ep.enabled == 1 && (!found || !(dv > 1e-6))) atomicMax(s.ep.error_flag, 1);
     const double scalar = s.ep.omega * (1.0 / dv);
     const int p0 = s.ep.p.rp[i], p1 = s.ep.p.rp[i + 1];
     int matched = 0, pp = p0;
     for (int t = 0; t < n; ++t) {
-        double v = vals[t] * -scalar;
+        double v = sg_epi_scale(s.ep.enabled, vals[t], scalar);
         while (pp < p1 && s.ep.p.col[pp] < keys[t]) ++pp;
         if (pp < p1 && s.ep.p.col[pp] == keys[t]) { v = v + s.ep.p.val[pp]; ++matched; }
         s.c_col[base + t] = keys[t]; s.c_val[base + t] = v;
@@ -527,13 +536,13 @@ __global__ void __launch_bounds__(256) sg_dense_kernel(SgArgs s, int ncols_b) {
         while (lo < hi) { const int mid = (lo + hi) >> 1; if (s.a.col[mid] < i) lo = mid + 1; else hi = mid; }
         if (lo < a1 && s.a.col[lo] == i) { dv = s.a.val[lo]; found = true; }
     }
-    if (tid == 0 && (!found || !(dv > 1e-6))) atomicMax(s.ep.error_flag, 1);
+    if (tid == 0 && s.ep.enabled == 1 && (!found || !(dv > 1e-6))) atomicMax(s.ep.error_flag, 1);
     const double scalar = s.ep.omega * (1.0 / dv);
     const int p0 = s.ep.p.rp[i], p1 = s.ep.p.rp[i + 1];
     int matched = 0;
     for (int j = j0; j < j1; ++j) {
         if (!touched[j]) continue;
-        double v = acc[j] * -scalar;
+        double v = sg_epi_scale(s.ep.enabled, acc[j], scalar);
         int lo = p0, hi = p1;
         while (lo < hi) { const int mid = (lo + hi) >> 1; if (s.ep.p.col[mid] < j) lo = mid + 1; else hi = mid; }
         if (lo < p1 && s.ep.p.col[lo] == j) { v = v + s.ep.p.val[lo]; ++matched; }
@@ -695,7 +704,7 @@ static famg_status sg_run_pass(famg_ctx *ctx, SgArgs base, const int *d_size, in
     return FAMG_OK;
 }
 
-famg_status spgemm_impl(const famg_csr *a, const famg_csr *b, const famg_csr *p_for_smoothing, double omega, famg_csr **out) {
+famg_status spgemm_impl(const famg_csr *a, const famg_csr *b, const famg_csr *p_for_smoothing, double omega, famg_csr **out, int epi_kind = 1) {
     *out = nullptr;
     if (a->ncols != b->nrows) FAMG_FAIL(FAMG_ERR_INVALID, "spgemm: inner dimensions differ (%lld vs %lld)", (long long)a->ncols, (long long)b->nrows);
     famg_ctx *ctx = a->ctx;
@@ -734,7 +743,7 @@ famg_status spgemm_impl(const famg_csr *a, const famg_csr *b, const famg_csr *p_
     int *err_flag = counters + 12;
     base.c_rp = c->row_ptr; base.c_col = c->col; base.c_val = c->val;
     if (p_for_smoothing) {
-        base.ep.enabled = 1; base.ep.omega = omega;
+        base.ep.enabled = epi_kind; base.ep.omega = omega;
         base.ep.p = SgMat{p_for_smoothing->row_ptr, p_for_smoothing->col, p_for_smoothing->val};
         base.ep.error_flag = err_flag;
     }
@@ -825,6 +834,127 @@ famg_status transpose_impl(const famg_csr *a, famg_csr **out) {
     return FAMG_OK;
 }
 
+// ---------------------------------------------------------------- block Jacobi prolongator smoothing
+// diagonal blocks of A (block_size x block_size, row-major per block, absent entries 0): one thread per row
+__global__ void block_diag_extract_kernel(const int *__restrict__ rp, const int *__restrict__ col, const double *__restrict__ val, int n,
+                                          int bs, double *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int start = (i / bs) * bs;
+    double *o = out + (size_t)i * bs;
+    for (int j = 0; j < bs; ++j) o[j] = 0.0;
+    for (int q = rp[i]; q < rp[i + 1]; ++q) {
+        const int j = col[q] - start;
+        if (j >= 0 && j < bs) o[j] = val[q];
+    }
+}
+
+// cyclic Jacobi eigen-decomposition of a small symmetric matrix (column-major, both triangles filled):
+// on return `m` holds the eigenvalues on its diagonal and `u` the eigenvectors in its columns
+static void host_sym_eig(int n, std::vector<double> &m, std::vector<double> &u) {
+    u.assign((size_t)n * n, 0.0);
+    for (int i = 0; i < n; ++i) u[(size_t)i + (size_t)i * n] = 1.0;
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0.0, diag = 0.0;
+        for (int p = 0; p < n; ++p) {
+            diag += m[(size_t)p + (size_t)p * n] * m[(size_t)p + (size_t)p * n];
+            for (int q = p + 1; q < n; ++q) off += m[(size_t)p + (size_t)q * n] * m[(size_t)p + (size_t)q * n];
+        }
+        if (off <= 1e-32 * diag || off == 0.0) break;
+        for (int p = 0; p < n - 1; ++p)
+            for (int q = p + 1; q < n; ++q) {
+                const double apq = m[(size_t)p + (size_t)q * n];
+                if (apq == 0.0) continue;
+                const double app = m[(size_t)p + (size_t)p * n], aqq = m[(size_t)q + (size_t)q * n];
+                const double zeta = (aqq - app) / (2.0 * apq);
+                const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+                for (int r = 0; r < n; ++r) {  // columns p, q
+                    const double mp = m[(size_t)r + (size_t)p * n], mq = m[(size_t)r + (size_t)q * n];
+                    m[(size_t)r + (size_t)p * n] = c * mp - sn * mq;
+                    m[(size_t)r + (size_t)q * n] = sn * mp + c * mq;
+                }
+                for (int r = 0; r < n; ++r) {  // rows p, q
+                    const double mp = m[(size_t)p + (size_t)r * n], mq = m[(size_t)q + (size_t)r * n];
+                    m[(size_t)p + (size_t)r * n] = c * mp - sn * mq;
+                    m[(size_t)q + (size_t)r * n] = sn * mp + c * mq;
+                }
+                for (int r = 0; r < n; ++r) {
+                    const double up = u[(size_t)r + (size_t)p * n], uq = u[(size_t)r + (size_t)q * n];
+                    u[(size_t)r + (size_t)p * n] = c * up - sn * uq;
+                    u[(size_t)r + (size_t)q * n] = sn * up + c * uq;
+                }
+            }
+    }
+}
+
+// D^-1 of interpolation/mod.rs:963-1015: scale * (U diag(1/s) U^T) of every diagonal block (lower side),
+// all block_size^2 entries kept (the reference pushes a triplet for each), as a device CSR
+static famg_status block_diag_inverse(const famg_csr *a, int bs, double scale, famg_csr **out) {
+    famg_ctx *ctx = a->ctx;
+    const int64_t n = a->nrows, nb = n / bs;
+    double *d_blocks = nullptr;
+    const size_t bytes = sizeof(double) * (size_t)n * bs;
+    FAMG_TRY(pool_alloc(ctx, bytes, (void **)&d_blocks));
+    if (n > 0) {
+        block_diag_extract_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, ctx->stream>>>(a->row_ptr, a->col, a->val, (int)n, bs, d_blocks);
+        count_launch(ctx);
+    }
+    std::vector<double> blocks((size_t)n * bs);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(blocks.data(), d_blocks, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    pool_free(ctx, d_blocks, bytes);
+    if (e != cudaSuccess) FAMG_FAIL(FAMG_ERR_CUDA, "block_jacobi: %s", cudaGetErrorString(e));
+    std::vector<int> rp((size_t)n + 1), ci((size_t)n * bs);
+    std::vector<double> cv((size_t)n * bs);
+    double worst = 1.0;
+    bool bad = false;
+#pragma omp parallel
+    {
+        std::vector<double> m, u;
+#pragma omp for schedule(static)
+        for (int64_t b = 0; b < nb; ++b) {
+            m.assign((size_t)bs * bs, 0.0);
+            for (int i = 0; i < bs; ++i)
+                for (int j = 0; j <= i; ++j) {  // Side::Lower
+                    const double v = blocks[((size_t)b * bs + i) * bs + j];
+                    m[(size_t)i + (size_t)j * bs] = v; m[(size_t)j + (size_t)i * bs] = v;
+                }
+            host_sym_eig(bs, m, u);
+            for (int c = 0; c < bs; ++c) {
+                const double ev = m[(size_t)c + (size_t)c * bs];
+                if (!(ev > 1e-6)) {
+#pragma omp critical
+                    { bad = true; worst = std::min(worst, ev); }
+                }
+            }
+            for (int i = 0; i < bs; ++i)
+                for (int j = 0; j < bs; ++j) {
+                    double sum = 0.0;
+                    for (int c = 0; c < bs; ++c) sum += u[(size_t)i + (size_t)c * bs] * (1.0 / m[(size_t)c + (size_t)c * bs]) * u[(size_t)j + (size_t)c * bs];
+                    const size_t row = (size_t)b * bs + i;
+                    ci[row * bs + j] = (int)(b * bs + j);
+                    cv[row * bs + j] = scale * sum;
+                }
+        }
+    }
+    if (bad) FAMG_FAIL(FAMG_ERR_NUMERIC, "block diagonal is nearly singular with eigval of: %.3e", worst);  // interpolation/mod.rs:994-998
+    for (int64_t i = 0; i <= n; ++i) rp[(size_t)i] = (int)(i * bs);
+    return csr_from_host_i32(ctx, n, n, rp.data(), ci.data(), cv.data(), out);
+}
+
+// block_jacobi (interpolation/mod.rs:963-1028): D^-1 = -0.66 (block diag of A)^-1; S = D^-1 (A P); S += P
+static famg_status block_jacobi_impl(const famg_csr *a, int bs, const famg_csr *p, famg_csr **out) {
+    famg_csr *dinv = nullptr, *ap = nullptr;
+    famg_status st = block_diag_inverse(a, bs, -JACOBI_WEIGHT_BLOCK, &dinv);
+    if (st == FAMG_OK) st = spgemm_impl(a, p, nullptr, 0.0, &ap);
+    if (st == FAMG_OK) st = spgemm_impl(dinv, ap, p, 0.0, out, 2);
+    if (dinv) csr_release(dinv);
+    if (ap) csr_release(ap);
+    return st;
+}
+
 }  // namespace famg
 
 using namespace famg;
@@ -850,18 +980,46 @@ famg_status famg_smooth_interpolation(const famg_csr *a, const famg_csr *p, doub
     return spgemm_impl(a, p, p, omega, out);
 }
 
+famg_status famg_block_jacobi(const famg_csr *a, int64_t block_size, const famg_csr *p, famg_csr **out) {
+    if (!a || !p || !out || block_size < 1) FAMG_FAIL(FAMG_ERR_INVALID, "bad argument");
+    if (a->nrows != a->ncols || p->nrows != a->nrows || a->nrows % block_size != 0 || block_size > 64)
+        FAMG_FAIL(FAMG_ERR_INVALID, "block_jacobi shape mismatch");
+    CUDA_TRY(cudaSetDevice(a->ctx->device));
+    *out = nullptr;
+    return block_jacobi_impl(a, (int)block_size, p, out);
+}
+
+famg_status famg_smooth_p(const famg_csr *a, const famg_csr *m_inv, const famg_csr *p, famg_csr **out) {
+    if (!a || !m_inv || !p || !out) FAMG_FAIL(FAMG_ERR_INVALID, "null argument");
+    if (a->nrows != a->ncols || m_inv->ncols != a->nrows || m_inv->nrows != p->nrows || p->nrows != a->nrows)
+        FAMG_FAIL(FAMG_ERR_INVALID, "smooth_p shape mismatch");
+    CUDA_TRY(cudaSetDevice(a->ctx->device));
+    *out = nullptr;
+    famg_csr *ap = nullptr;
+    famg_status st = spgemm_impl(a, p, nullptr, 0.0, &ap);
+    if (st == FAMG_OK) st = spgemm_impl(m_inv, ap, p, 0.0, out, 3);  // m_inv * (-(A P)) + P
+    if (ap) csr_release(ap);
+    return st;
+}
+
 famg_status famg_galerkin(const famg_csr *a, const famg_csr *p0, int smoothing_steps, double omega, famg_csr **p_out,
                           famg_csr **r_out, famg_csr **ac_out) {
-    if (!a || !p0 || !p_out || !r_out || !ac_out || smoothing_steps < 0) FAMG_FAIL(FAMG_ERR_INVALID, "bad argument");
+    return famg_galerkin_block(a, p0, 1, smoothing_steps, omega, p_out, r_out, ac_out);
+}
+
+famg_status famg_galerkin_block(const famg_csr *a, const famg_csr *p0, int64_t block_size, int smoothing_steps, double omega,
+                                famg_csr **p_out, famg_csr **r_out, famg_csr **ac_out) {
+    if (!a || !p0 || !p_out || !r_out || !ac_out || smoothing_steps < 0 || block_size < 1 || block_size > 64)
+        FAMG_FAIL(FAMG_ERR_INVALID, "bad argument");
     *p_out = *r_out = *ac_out = nullptr;
-    if (a->nrows != a->ncols || p0->nrows != a->nrows) FAMG_FAIL(FAMG_ERR_INVALID, "galerkin shape mismatch");
+    if (a->nrows != a->ncols || p0->nrows != a->nrows || a->nrows % block_size != 0) FAMG_FAIL(FAMG_ERR_INVALID, "galerkin shape mismatch");
     CUDA_TRY(cudaSetDevice(a->ctx->device));
     famg_csr *p = const_cast<famg_csr *>(p0);
     p->refs.fetch_add(1);
     famg_status st = FAMG_OK;
     for (int s = 0; s < smoothing_steps && st == FAMG_OK; ++s) {   // interpolation/mod.rs:812-818
         famg_csr *next = nullptr;
-        st = spgemm_impl(a, p, p, omega, &next);
+        st = block_size == 1 ? spgemm_impl(a, p, p, omega, &next) : block_jacobi_impl(a, (int)block_size, p, &next);
         if (st == FAMG_OK) { csr_release(p); p = next; }
     }
     famg_csr *r = nullptr, *ap = nullptr, *ac = nullptr;

@@ -49,22 +49,38 @@ def smooth_interpolation(mat: SparseRowMat, p: SparseRowMat, jacobi_weight: floa
     return SparseRowMat(mat.ctx, h)
 
 
-def galerkin_product(mat: SparseRowMat, p0: SparseRowMat, smoothing_steps: int = 1, jacobi_weight: float = JACOBI_WEIGHT):
-    """interpolation/mod.rs:811-828: P = smooth^steps(P0); R = P^T; A_c = R (A P).  Returns (P, R, A_c)."""
+def block_jacobi(mat: SparseRowMat, block_size: int, p: SparseRowMat) -> SparseRowMat:
+    """interpolation/mod.rs:963-1028: P - 0.66 D_b^-1 A P with D_b^-1 from the per-block symmetric
+    eigen-decomposition of A's block diagonal (two SpGEMMs, the ``+ P`` fused into the second)."""
+    h = vp()
+    call("famg_block_jacobi", mat._h, int(block_size), p._h, C.byref(h))
+    return SparseRowMat(mat.ctx, h)
+
+
+def smooth_p(mat: SparseRowMat, m_inv: SparseRowMat, p: SparseRowMat) -> SparseRowMat:
+    """interpolation/mod.rs:1030-1040: ``m_inv * (-(mat * p)) + p``."""
+    h = vp()
+    call("famg_smooth_p", mat._h, m_inv._h, p._h, C.byref(h))
+    return SparseRowMat(mat.ctx, h)
+
+
+def galerkin_product(mat: SparseRowMat, p0: SparseRowMat, smoothing_steps: int = 1, jacobi_weight: float = JACOBI_WEIGHT,
+                     block_size: int = 1):
+    """interpolation/mod.rs:811-828: P = smooth^steps(P0) (``smooth_interpolation`` for block_size 1,
+    ``block_jacobi`` otherwise); R = P^T; A_c = R (A P).  Returns (P, R, A_c)."""
     p, r, ac = vp(), vp(), vp()
-    call("famg_galerkin", mat._h, p0._h, smoothing_steps, float(jacobi_weight), C.byref(p), C.byref(r), C.byref(ac))
+    call("famg_galerkin_block", mat._h, p0._h, int(block_size), smoothing_steps, float(jacobi_weight), C.byref(p), C.byref(r),
+         C.byref(ac))
     return SparseRowMat(mat.ctx, p), SparseRowMat(mat.ctx, r), SparseRowMat(mat.ctx, ac)
 
 
 def smoothed_aggregation(fine_mat: SparseRowMat, partition: Partition, block_size: int, near_null,
                          candidate_dimension: int, smoothing_steps: int):
     """interpolation/mod.rs:730-836 -> (coarse_near_null, R, P, A_c, partition)."""
-    if block_size != 1 and smoothing_steps > 0:
-        raise NotImplementedError("block_jacobi prolongator smoothing (block_size > 1) is not built yet")
     n_fine = fine_mat.nrows
     assert n_fine % block_size == 0 and n_fine == partition.nnodes() * block_size  # :743-745
     p0, coarse_nn = tentative_prolongator(fine_mat.ctx, n_fine, partition, near_null, candidate_dimension, block_size)
-    p, r, ac = galerkin_product(fine_mat, p0, smoothing_steps)
+    p, r, ac = galerkin_product(fine_mat, p0, smoothing_steps, block_size=block_size)
     return coarse_nn, r, p, ac, partition
 
 

@@ -136,6 +136,12 @@ class StrengthGraph:
         call("famg_graph_create", len(rp) - 1, rp.ctypes.data_as(u64p), ci.ctypes.data_as(u64p), w.ctypes.data_as(f64p), C.byref(h))
         return cls(h)
 
+    def block_reduce(self, block_size: int):
+        """``strength.aggregate(&block_reduce); strength.filter_diag()`` (partitioners/mod.rs:293-300), in place."""
+        from ._ffi import call
+
+        call("famg_graph_block_reduce", self._h, int(block_size))
+
     def dims(self) -> Tuple[int, int]:
         from ._ffi import call
 
@@ -189,12 +195,12 @@ class PartitionerConfig:
     def build_partition(self, mat, near_null, weights) -> Partition:
         """partitioners/mod.rs:319-328.  ``mat``: ``SparseMatOp`` (block size 1) or ``SparseRowMat``."""
         block_size = mat.block_size() if hasattr(mat, "block_size") else 1
-        if block_size != 1:
-            raise NotImplementedError("block_size > 1 (strength.aggregate(block_reduce), mod.rs:293-300) is not built yet")
         m = mat.mat_ref() if hasattr(mat, "mat_ref") else mat
         if m.nrows != m.ncols:
             raise ValueError("square matrix expected")  # mod.rs:283
         strength = StrengthGraph.new_ls_strength_graph(m, near_null, weights, 3)
+        if block_size > 1:  # mod.rs:293-300: the partition is over nodes of block_size dofs
+            strength.block_reduce(block_size)
         return self.build_from_strength(strength)
 
     def scaled(self, ratio: float) -> "PartitionerConfig":

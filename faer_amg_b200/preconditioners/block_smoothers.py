@@ -18,12 +18,12 @@ class BlockSmoother(Smoother):
 
     @classmethod
     def new(cls, op: SparseMatOp, partition: Partition) -> "BlockSmoother":
-        if op.block_size() != 1:
-            raise NotImplementedError("vector block size > 1 (diagonally_compensate_vector) is not built yet")
         ap = np.ascontiguousarray(partition.agg_ptr, dtype=np.int64)   # same bits as usize, no copy
         an = np.ascontiguousarray(partition.agg_nodes, dtype=np.int64)
         h = vp()
-        call("famg_smoother_block", op.mat_ref()._h, partition.naggs(), ap.ctypes.data_as(u64p), an.ctypes.data_as(u64p), C.byref(h))
+        # vdim == 1: diagonally_compensate (:293-324); vdim > 1: diagonally_compensate_vector (:326-400)
+        call("famg_smoother_block_vector", op.mat_ref()._h, op.block_size(), partition.naggs(), ap.ctypes.data_as(u64p),
+             an.ctypes.data_as(u64p), C.byref(h))
         s = cls(op.mat_ref().ctx, h)
         s.partition = partition
         return s

@@ -135,6 +135,10 @@ famg_status famg_smoother_cholesky(const famg_csr *a, famg_smoother **out);
  * agg_ptr[n_aggs+1], agg_nodes ascending inside each aggregate. */
 famg_status famg_smoother_block(const famg_csr *a, int64_t n_aggs, const uint64_t *agg_ptr,
                                 const uint64_t *agg_nodes, famg_smoother **out);
+/* the same for vector problems: the partition is over nodes of `vdim` dofs (dof = node * vdim + offset);
+ * off-aggregate coupling blocks are lumped by diagonally_compensate_vector (block_smoothers.rs:326-400) */
+famg_status famg_smoother_block_vector(const famg_csr *a, int64_t vdim, int64_t n_aggs, const uint64_t *agg_ptr,
+                                       const uint64_t *agg_nodes, famg_smoother **out);
 famg_status famg_smoother_retain(famg_smoother *s);
 famg_status famg_smoother_destroy(famg_smoother *s);
 famg_status famg_smoother_dim(const famg_smoother *s, int64_t *n);
@@ -180,6 +184,15 @@ famg_status famg_smooth_interpolation(const famg_csr *a, const famg_csr *p, doub
 /* interpolation/mod.rs:811-828 in one call: P = smooth^steps(P0); R = P^T; A_c = R (A P). */
 famg_status famg_galerkin(const famg_csr *a, const famg_csr *p0, int smoothing_steps, double omega,
                           famg_csr **p, famg_csr **r, famg_csr **a_coarse);
+/* the same for block_size > 1: prolongator smoothing by block_jacobi (interpolation/mod.rs:816, 963-1028)
+ * -- D^-1 = -0.66 * inverse of A's block diagonal (per-block symmetric eigen-decomposition of the lower
+ * side, eigenvalues must exceed 1e-6), P <- D^-1 (A P) + P -- instead of smooth_interpolation.  omega is
+ * used only when block_size == 1. */
+famg_status famg_galerkin_block(const famg_csr *a, const famg_csr *p0, int64_t block_size, int smoothing_steps,
+                                double omega, famg_csr **p, famg_csr **r, famg_csr **a_coarse);
+/* block_jacobi (interpolation/mod.rs:963-1028) and smooth_p (:1030-1040: m_inv * (-(A P)) + P) on their own */
+famg_status famg_block_jacobi(const famg_csr *a, int64_t block_size, const famg_csr *p, famg_csr **out);
+famg_status famg_smooth_p(const famg_csr *a, const famg_csr *m_inv, const famg_csr *p, famg_csr **out);
 /* tentative prolongator of smoothed_aggregation (interpolation/mod.rs:747-809): per-aggregate
  * thin SVD of the near-null block on the host (tiny dense work), P uploaded as CSR.
  * near_null: n_fine x k column-major; coarse_nn (out): (n_aggs*cand) x k column-major. */
@@ -219,6 +232,9 @@ famg_status famg_strength_graph_create(int64_t n, const uint64_t *row_ptr, const
 /* an explicit weighted adjacency list (PartitionerConfig::build_from_strength, partitioners/mod.rs:310-317) */
 famg_status famg_graph_create(int64_t n, const uint64_t *row_ptr, const uint64_t *col_idx, const double *w,
                               famg_graph **out);
+/* block_size > 1: strength.aggregate(&block_reduce) + filter_diag (partitioners/mod.rs:293-300), in place:
+ * the graph over dofs becomes a graph over nodes of block_size consecutive dofs */
+famg_status famg_graph_block_reduce(famg_graph *g, int64_t block_size);
 famg_status famg_graph_dims(const famg_graph *g, int64_t *n, int64_t *nnz);
 famg_status famg_graph_download(const famg_graph *g, uint64_t *row_ptr, uint64_t *col_idx, double *w);
 famg_status famg_graph_destroy(famg_graph *g);

@@ -339,6 +339,82 @@ def error_propagator(a: Csr, precond_apply, x) -> np.ndarray:
     return x - precond_apply(spmm_csr(a, x))
 
 
+def _add_assign_pattern(s: Csr, p: Csr) -> Csr:
+    """faer ``add_assign(smoothed.transpose_mut(), p.transpose())`` [faer-recalled]: S += P entrywise;
+    pattern(P) must be contained in pattern(S) (panics otherwise)."""
+    val = s.val.copy()
+    for i in range(p.nrows):
+        cols = s.col[s.row_ptr[i]:s.row_ptr[i + 1]]
+        for q in range(p.row_ptr[i], p.row_ptr[i + 1]):
+            u = int(np.searchsorted(cols, p.col[q]))
+            if u == len(cols) or cols[u] != p.col[q]:
+                raise ValueError("pattern(P) is not contained in pattern(S)")
+            val[s.row_ptr[i] + u] += p.val[q]
+    return Csr.from_arrays(s.nrows, s.ncols, s.row_ptr, s.col, val)
+
+
+def block_diag_inverse(a: Csr, block_size: int, scale: float) -> Csr:
+    """The D^-1 of block_jacobi (interpolation/mod.rs:968-1015): per diagonal block,
+    ``self_adjoint_eigen(Lower)`` -> U diag(1/s) U^T (eigenvalues must exceed 1e-6), every entry kept as
+    a triplet, scaled.  LAPACK's ``eigh`` (lower side) stands in for faer's."""
+    n = a.nrows
+    rows, cols, vals = [], [], []
+    dense_get = a.to_scipy().tocsr()
+    for b in range(n // block_size):
+        st = b * block_size
+        blk = dense_get[st:st + block_size, st:st + block_size].toarray()
+        w, u = np.linalg.eigh(blk, UPLO="L")
+        if np.any(w <= 1e-6):
+            raise ValueError(f"block diagonal is nearly singular with eigval of: {w.min():.3e}")
+        inv = (u * (1.0 / w)) @ u.T
+        for i in range(block_size):
+            for j in range(block_size):
+                rows.append(st + i); cols.append(st + j); vals.append(scale * inv[i, j])
+    return Csr.from_triplets(n, n, rows, cols, vals)
+
+
+def block_jacobi(a: Csr, block_size: int, p: Csr) -> Csr:
+    """block_jacobi (interpolation/mod.rs:963-1028): smoothed = d_inv * (mat * p); smoothed += p."""
+    d_inv = block_diag_inverse(a, block_size, -0.66)
+    return _add_assign_pattern(spgemm(d_inv, spgemm(a, p)), p)
+
+
+def smooth_p(a: Csr, m_inv: Csr, p: Csr) -> Csr:
+    """smooth_p (interpolation/mod.rs:1030-1040): ap = mat * p; ap *= -1; smoothed = m_inv * ap; += p."""
+    ap = spgemm(a, p)
+    ap = Csr.from_arrays(ap.nrows, ap.ncols, ap.row_ptr, ap.col, -ap.val)
+    return _add_assign_pattern(spgemm(m_inv, ap), p)
+
+
+def block_smoother_vector_apply(a: Csr, vdim: int, agg_ptr, agg_nodes, r) -> np.ndarray:
+    """BlockSmoother::apply for vdim > 1 (block_smoothers.rs:165-214) with diagonally_compensate_vector
+    (:326-400): per aggregate of nodes, in-aggregate couplings kept, every coupling block to an outside
+    node lumped into the node's diagonal block as 0.5 U S U^T (-A_IJ = U S V^T, LAPACK svd), block solved
+    exactly (lower triangle, as a Cholesky of one side would)."""
+    r = _fcol(r).copy(order="F")
+    m = a.to_scipy().tocsr()
+    agg_ptr, agg_nodes = np.asarray(agg_ptr), np.asarray(agg_nodes)
+    nnodes = a.nrows // vdim
+    node_agg = np.empty(nnodes, dtype=np.int64)
+    for g in range(len(agg_ptr) - 1):
+        node_agg[agg_nodes[agg_ptr[g]:agg_ptr[g + 1]]] = g
+    for g in range(len(agg_ptr) - 1):
+        nodes = agg_nodes[agg_ptr[g]:agg_ptr[g + 1]]
+        dofs = (nodes[:, None] * vdim + np.arange(vdim)[None, :]).reshape(-1)
+        blk = m[dofs][:, dofs].toarray()
+        for li, bi in enumerate(nodes):
+            rows = m[bi * vdim:(bi + 1) * vdim]
+            outside = sorted({int(j) // vdim for j in rows.indices if node_agg[int(j) // vdim] != g})
+            for bj in outside:
+                aij = -rows[:, bj * vdim:(bj + 1) * vdim].toarray()
+                u, sv, _ = np.linalg.svd(aij)
+                blk[li * vdim:(li + 1) * vdim, li * vdim:(li + 1) * vdim] += 0.5 * ((u * sv) @ u.T)
+        low = np.tril(blk)
+        sym = low + np.tril(blk, -1).T
+        r[dofs, :] = np.linalg.solve(sym, r[dofs, :])
+    return r
+
+
 def smooth_vector(a: Csr, precond_apply, x0, iterations: int):
     """smooth_vector (adaptivity.rs:307-390) from a given start block x0 (the reference draws it from
     an unseeded StandardNormal stream, :321-329): x = thinQ(thinQ(x0)); iterations x { x = E x;
@@ -467,12 +543,12 @@ class GalerkinCoarse:
 
 
 def smoothed_aggregation(a: Csr, agg_ptr, agg_nodes, near_null, cand: int = 1,
-                         smoothing_steps: int = 1, omega: float = 0.66) -> GalerkinCoarse:
-    """interpolation/mod.rs:730-836 (block_size == 1): tentative P by per-aggregate thin SVD,
-    `smoothing_steps` x smooth_interpolation(A, P, 0.66), R = P^T, A_c = R (A P)."""
-    p, coarse_nn = tentative_p(a.nrows, near_null, agg_ptr, agg_nodes, cand)
+                         smoothing_steps: int = 1, omega: float = 0.66, block_size: int = 1) -> GalerkinCoarse:
+    """interpolation/mod.rs:730-836: tentative P by per-aggregate thin SVD, `smoothing_steps` x
+    smooth_interpolation(A, P, 0.66) (block_size 1) or block_jacobi (:812-818), R = P^T, A_c = R (A P)."""
+    p, coarse_nn = tentative_p(a.nrows, near_null, agg_ptr, agg_nodes, cand, block_size)
     for _ in range(smoothing_steps):
-        p = smooth_interpolation(a, p, omega)
+        p = smooth_interpolation(a, p, omega) if block_size == 1 else block_jacobi(a, block_size, p)
     r = transpose(p)
     ac = spgemm(r, spgemm(a, p))
     return GalerkinCoarse(p, r, ac, coarse_nn, (np.asarray(agg_ptr), np.asarray(agg_nodes)))
@@ -501,7 +577,7 @@ class Hierarchy:
 
 def build_hierarchy(a: Csr, near_null, dims: Sequence[int], coarsest_dim: int = 1000,
                     max_levels: Optional[int] = None, cand: int = 1, smoothing_steps: int = 1,
-                    block: Sequence[int] = (2, 2, 2), partitioner=None) -> Hierarchy:
+                    block: Sequence[int] = (2, 2, 2), partitioner=None, block_size: int = 1) -> Hierarchy:
     """Hierarchy::coarsen (hierarchy.rs:190-248) with the partitioner replaced by deterministic
     geometric aggregates (the reference partitioner is non-deterministic) -- or by
     ``partitioner(level, fine, near_null) -> node_to_agg`` (e.g. the restated algebraic partitioner
@@ -521,7 +597,9 @@ def build_hierarchy(a: Csr, near_null, dims: Sequence[int], coarsest_dim: int = 
             agg_nodes = np.argsort(n2a, kind="stable").astype(np.int64)
             agg_ptr = np.concatenate([[0], np.cumsum(np.bincount(n2a))]).astype(np.int64)
             dims_c = None
-        g = smoothed_aggregation(fine, agg_ptr, agg_nodes, h.near_nulls[-1], cand, smoothing_steps)
+        # SparseMatOp block size: the caller's on the finest level, candidate_dimension below (hierarchy.rs:210-215)
+        bs = block_size if level == 1 else cand
+        g = smoothed_aggregation(fine, agg_ptr, agg_nodes, h.near_nulls[-1], cand, smoothing_steps, block_size=bs)
         coarse_dim = g.coarse_mat.nrows
         nn = stationary_iteration(g.coarse_mat, new_l1(g.coarse_mat), 3, g.coarse_nn)
         nn = thin_q(nn)

@@ -260,10 +260,38 @@ class Partitioner:
                         alive_aggs[self.node_to_agg[j]] = False
 
 
+def block_reduce(nodes: List[List[Edge]], block_size: int) -> List[List[Edge]]:
+    """``strength.aggregate(&block_reduce); strength.filter_diag()`` (mod.rs:293-300, 465-502, 588-656):
+    neighbour ids -> node ids, the lists of a node's dofs merged (equal ids summed in member / list order,
+    TIE-BREAK 6), weights divided by the largest merged weight (self loops included), self loops dropped."""
+    nb = len(nodes) // block_size
+    merged, gmax = [], None
+    for b in range(nb):
+        allv = []
+        for o in range(block_size):
+            nbrs = nodes[b * block_size + o]
+            if not nbrs:
+                raise ValueError("empty neighborhood means graph is disconnected")
+            allv.extend((j // block_size, wt) for j, wt in nbrs)
+        allv.sort(key=lambda e: e[0])
+        out: List[List] = []
+        for j, wt in allv:
+            if out and out[-1][0] == j:
+                out[-1][1] += wt
+            else:
+                out.append([j, wt])
+        for _, wt in out:
+            gmax = wt if gmax is None or wt > gmax else gmax
+        merged.append(out)
+    return [[(j, wt / gmax) for j, wt in row if j != b] for b, row in enumerate(merged)]
+
+
 def build_partition(row_ptr, col_idx, near_null, weights, coarsening_factor: float = 8.0, agg_size_penalty: float = 1.0,
-                    max_improvement_iters: int = 100, max_depth: int = 3):
-    """``PartitionerConfig::build_partition`` (mod.rs:273-329), block size 1 -> (node_to_agg, strength)."""
+                    max_improvement_iters: int = 100, max_depth: int = 3, block_size: int = 1):
+    """``PartitionerConfig::build_partition`` (mod.rs:273-329) -> (node_to_agg, strength)."""
     strength = new_ls_strength_graph(row_ptr, col_idx, near_null, weights, max_depth)
+    if block_size > 1:
+        strength = block_reduce(strength, block_size)
     p = Partitioner(strength, coarsening_factor, agg_size_penalty, max_improvement_iters)
     p.initialize_partition()
     p.improve_partition()

@@ -105,3 +105,26 @@ def test_partition_scales_to_a_moderate_grid():
     part.validate()
     sizes = np.diff(part.agg_ptr)
     assert 6.0 <= part.nnodes() / part.naggs() <= 17.0 and sizes.min() >= 1
+
+
+@pytest.mark.parametrize("bs", [2, 3])
+def test_block_reduce_and_vector_partition_bit_exact(bs):
+    """block_size > 1 (partitioners/mod.rs:293-300): LS strength over dofs, aggregated to nodes, self
+    loops dropped; the partition is over nodes."""
+    import scipy.sparse as sp
+    g = O.gen_g7(5, 4, 3).to_scipy()
+    a = sp.kron(g, np.ones((bs, bs))).tocsr()
+    a.sort_indices()
+    rp, ci = a.indptr.astype(np.int64), a.indices.astype(np.int64)
+    nn = _near_null("rand", a.shape[0], 3, seed=5)
+    w = np.array([1.0, 0.5, 2.0])
+    want = OP.block_reduce(OP.new_ls_strength_graph(rp, ci, nn, w, 3), bs)
+    sg = StrengthGraph.new_ls_strength_graph((rp, ci), nn, w, 3)
+    sg.block_reduce(bs)
+    got = _graph_lists(sg)
+    assert got == want and len(got) == g.shape[0]
+    assert all(j != i for i, nb in enumerate(got) for j, _ in nb)          # filter_diag
+    assert max(x for nb in got for _, x in nb) <= 1.0                       # normalised by the global maximum
+    n2a, _ = OP.build_partition(rp, ci, nn, w, 4.0, 1.0, 20, block_size=bs)
+    part = PartitionerConfig(4.0, 1.0, 20).build_from_strength(sg)
+    assert np.array_equal(part.node_to_agg(), n2a) and part.nnodes() == g.shape[0]
