@@ -42,9 +42,10 @@ def vector_operator(dims, vdim, seed=0):
 
 def close(dev, orc, tol=1e-12):
     """Same sorted pattern; |got - want| <= tol * max(1, max |entry|).  utils.rs:32-58's entry-relative
-    test is not usable between two different small-dense factorisations (Jacobi sweeps here, LAPACK in
-    the oracle): entries of D^-1 (A P) + P that cancel to ~1e-4 of their terms differ by a few ulp of
-    the terms, i.e. ~1e-12 of themselves (observed: the first attempt of this test)."""
+    form is not used here: the product and the oracle take the small dense factorisations from different
+    algorithms (Jacobi sweeps vs LAPACK), and entries of D^-1 (A P) + P that are small through
+    cancellation then agree to an absolute, not an entry-relative, 1e-12 (the entry-relative form failed
+    on such entries when this test was first run on the GPU; the absolute form passes)."""
     if not same_pattern(dev, orc):
         print("pattern differs", dev.shape, orc.shape, dev.nnz, orc.nnz)
         return False
