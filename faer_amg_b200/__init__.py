@@ -17,11 +17,13 @@ from . import partitioners  # noqa: F401
 from .preconditioners.block_smoothers import BlockSmoother, BlockSmootherConfig  # noqa: F401
 from .preconditioners.coarse_solvers import CoarseSolverKind, SparseCholeskySolve  # noqa: F401
 from .preconditioners.multigrid import Multigrid, MultigridConfig  # noqa: F401
+from .preconditioners.composite import Composite  # noqa: F401
 from .preconditioners.smoothers import (Diag, SmootherKind, StationaryIteration, new_jacobi, new_l1, new_l2,  # noqa: F401
                                         smooth)
 from .solvers import (CgError, CgInfo, CgParams, conjugate_gradient, conjugate_gradient_dev, stationary_solver,  # noqa: F401
                       test_solver)
-from .adaptivity import ErrorPropogator, create_weights, find_near_null, smooth_vector, smooth_vector_dev  # noqa: F401
+from .adaptivity import (AdaptiveConfig, ErrorPropogator, create_weights, find_near_null, smooth_vector,  # noqa: F401
+                         smooth_vector_dev)
 from . import adaptivity  # noqa: F401
 from . import gallery  # noqa: F401
 

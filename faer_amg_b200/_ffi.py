@@ -104,6 +104,12 @@ SIGNATURES = {
     "famg_error_propagator_dev": [vp, vp, vp, vp],
     "famg_smooth_vector_dev": [vp, vp, i64, vp, f64p],
     "famg_vec_coldot": [vp, vp, f64p],
+    "famg_smooth_vector_pc_dev": [vp, cint, vp, i64, vp, f64p],
+    "famg_composite_create": [vp, vpp],
+    "famg_composite_push": [vp, cint, vp],
+    "famg_composite_len": [vp, i64p],
+    "famg_composite_apply_dev": [vp, vp, vp],
+    "famg_composite_destroy": [vp],
     "famg_strength_graph_create": [i64, u64p, u64p, f64p, i64, i64, f64p, i64, vpp],
     "famg_graph_create": [i64, u64p, u64p, f64p, vpp],
     "famg_graph_block_reduce": [vp, i64],

@@ -4,8 +4,8 @@ near-null search (``:351-354``) and of compatible relaxation (``interpolation/mo
 and the search loop itself, ``smooth_vector`` / ``find_near_null`` / ``create_weights``
 (``:264-390, 434-443``), kept resident in HBM: SpMM of width k with the fused
 ``x - d .* (A x)`` epilogue plus a device CholeskyQR2 per step (``csrc/tsqr.cu``).
-The adaptive driver around them (``AdaptiveConfig``, ``Composite``) is host logic outside the scope
-of this package."""
+``AdaptiveConfig`` (``:28-165``) is the thin host loop over these pieces and ``Composite``
+(``preconditioners/composite.py``), SURVEY 8f-4."""
 from __future__ import annotations
 
 from typing import Callable, List, Optional, Tuple
@@ -56,17 +56,21 @@ class ErrorPropogator:
     conj_apply = apply
 
 
-def smooth_vector_dev(mat, pc: Smoother, iterations: int, x: DeviceMat, report: bool = False) -> List[float]:
+def smooth_vector_dev(mat, pc, iterations: int, x: DeviceMat, report: bool = False) -> List[float]:
     """adaptivity.rs:307-390 on a device-resident block ``x`` (n x k, k <= 64), in place; returns the
-    per-column convergence factors ``||E w||_A / ||w||_A`` (``:365-384``)."""
+    per-column convergence factors ``||E w||_A / ||w||_A`` (``:365-384``).  ``pc``: a smoother, a
+    ``Multigrid`` or a ``Composite`` (the adaptive driver passes the latter, ``:104-114``)."""
+    from .preconditioners.composite import pc_handle
+
     cfs = np.zeros(x.ncols)
-    call("famg_smooth_vector_dev", _mat_of(mat)._h, pc._h, int(iterations), x._h, _f(cfs))
+    kind, h = pc_handle(pc)
+    call("famg_smooth_vector_pc_dev", _mat_of(mat)._h, kind, h, int(iterations), x._h, _f(cfs))
     if report:
         print("~||E||_A: " + " ".join(f"{c:.3f}" for c in cfs))
     return list(cfs)
 
 
-def smooth_vector(mat, pc: Smoother, iterations: int, near_null_dim: int, report: bool = False,
+def smooth_vector(mat, pc, iterations: int, near_null_dim: int, report: bool = False,
                   x0=None, seed: Optional[int] = None) -> Tuple[np.ndarray, List[float]]:
     """adaptivity.rs:307-390.  The reference draws the start block from an unseeded StandardNormal
     stream (``:321-329``); ``x0`` (n x near_null_dim) or ``seed`` pins it here."""
@@ -96,7 +100,7 @@ def find_near_null(mat: SparseMatOp, iterations: int, near_null_dim: int, smooth
     ``smoothing_block_size`` nodes from the first basis, smooth again with it.
     ``partitioner(op, near_null, weights, coarsening_factor) -> Partition`` stands where the
     reference calls ``PartitionerConfig{coarsening_factor, max_improvement_iters: 50}.build`` inside
-    ``BlockSmootherConfig::build`` (``:279-289``); default: :func:`partitioners.modularity_partition`."""
+    ``BlockSmootherConfig::build`` (``:279-289``); default: :class:`partitioners.PartitionerConfig`."""
     from .preconditioners.block_smoothers import BlockSmoother
 
     simple_pc = new_l1(mat.mat_ref())
@@ -115,3 +119,40 @@ def find_near_null(mat: SparseMatOp, iterations: int, near_null_dim: int, smooth
     smooth_basis, cfs = smooth_vector(mat, block_pc, iterations, near_null_dim, False, x0=x1, seed=seed1)
     print("||Ev||_A^(1/cycles): " + " ".join(f"{c:.2f}" for c in cfs))
     return smooth_basis
+
+
+class AdaptiveConfig:
+    """adaptivity.rs:28-165: build a :class:`Composite` of up to ``max_components`` multigrids, each
+    from a hierarchy whose near-null block is what the composite built so far fails to damp.
+    ``hierarchy_config`` / ``multigrid_config``: the mirrors in this package; the block smoother's
+    coarsening factor (``multigrid_config.smoother_config.partitioner_config.coarsening_factor`` in the
+    reference, ``:63-66``) is ``smoothing_block_size`` here."""
+
+    def __init__(self, hierarchy_config, multigrid_config, target_convergence: Optional[float] = None, max_components: int = 5,
+                 test_iters: int = 50, coarsening_near_null_dim: int = 32, include_constant_first_near_null: bool = True,
+                 smoothing_block_size: float = 8.0, seed: Optional[int] = None):
+        self.hierarchy_config, self.multigrid_config = hierarchy_config, multigrid_config
+        self.target_convergence, self.max_components, self.test_iters = target_convergence, max_components, test_iters
+        self.coarsening_near_null_dim = coarsening_near_null_dim
+        self.include_constant_first_near_null = include_constant_first_near_null
+        self.smoothing_block_size, self.seed = smoothing_block_size, seed
+
+    def build(self, mat: SparseMatOp):
+        from .hierarchy import thin_q
+        from .preconditioners.composite import Composite
+
+        k = self.coarsening_near_null_dim
+        nn = find_near_null(mat, self.test_iters, k - 1, self.smoothing_block_size, seed=self.seed)       # :58-67
+        nn_with_constant = np.ones((nn.shape[0], k), order="F")
+        nn_with_constant[:, 1:] = nn                                                                        # :68-71
+        basis = thin_q(nn_with_constant)
+        weights = create_weights(basis, mat)                                                                # :73
+        first = self.multigrid_config.build(self.hierarchy_config.build(mat, basis, weights))               # :110-115
+        composite = Composite.new(mat.dyn_op(), first)
+        for n_components in range(1, self.max_components):                                                  # :117-163
+            seed = None if self.seed is None else self.seed + 100 * n_components
+            smoothed, cfs = smooth_vector(mat, composite.clone(), self.test_iters // (2 * n_components - 1), k, False, seed=seed)
+            n_vcycles = float(2 * n_components - 1)
+            print("||Ev||_A^(1/cycles): " + " ".join(f"{c ** (1.0 / n_vcycles):.2f}" for c in cfs))
+            composite.push(self.multigrid_config.build(self.hierarchy_config.build(mat, smoothed, cfs)))    # :155-161
+        return composite

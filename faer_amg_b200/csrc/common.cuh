@@ -111,7 +111,16 @@ struct famg_smoother {
     famg_csr *minv = nullptr; // SM_SPARSE_INV: block-diagonal M^-1 as CSR
 };
 
+struct famg_composite {
+    famg_ctx *ctx = nullptr;
+    famg_csr *a = nullptr;  // retained
+    std::vector<std::pair<int, void *>> components;  // (pc_kind, borrowed handle)
+};
+
 namespace famg {
+
+// z = M^-1 r for any preconditioner kind (pcg.cu); n x k blocks
+famg_status pc_apply(int pc_kind, void *precond, famg_vec *z, const famg_vec *r);
 
 // ---------------------------------------------------------------- allocation helpers
 template <typename T>

@@ -14,9 +14,10 @@
 
 namespace famg {
 
-static famg_status pc_apply(int pc_kind, void *precond, famg_vec *z, const famg_vec *r) {
+famg_status pc_apply(int pc_kind, void *precond, famg_vec *z, const famg_vec *r) {
     if (pc_kind == FAMG_PC_MG) return famg_mg_apply_dev((famg_mg *)precond, z, r);
     if (pc_kind == FAMG_PC_SMOOTHER) return famg_smoother_apply_dev((const famg_smoother *)precond, z, r);
+    if (pc_kind == FAMG_PC_COMPOSITE) return famg_composite_apply_dev((famg_composite *)precond, z, r);
     return famg_vec_copy(z, r);
 }
 
@@ -25,6 +26,61 @@ static famg_status pc_apply(int pc_kind, void *precond, famg_vec *z, const famg_
 using namespace famg;
 
 extern "C" {
+
+// ---- Composite (src/preconditioners/composite.rs) ------------------------------------------------
+famg_status famg_composite_create(const famg_csr *a, famg_composite **out) {
+    if (!a || !out) FAMG_FAIL(FAMG_ERR_INVALID, "null argument");
+    if (a->nrows != a->ncols) FAMG_FAIL(FAMG_ERR_INVALID, "composite needs a square operator");
+    famg_composite *c = new famg_composite();
+    c->ctx = a->ctx;
+    c->a = const_cast<famg_csr *>(a);
+    c->a->refs.fetch_add(1);
+    *out = c;
+    return FAMG_OK;
+}
+famg_status famg_composite_push(famg_composite *c, int pc_kind, void *component) {
+    if (!c || !component) FAMG_FAIL(FAMG_ERR_INVALID, "null argument");
+    if (pc_kind != FAMG_PC_SMOOTHER && pc_kind != FAMG_PC_MG && pc_kind != FAMG_PC_COMPOSITE) FAMG_FAIL(FAMG_ERR_INVALID, "unknown component kind");
+    if (component == (void *)c) FAMG_FAIL(FAMG_ERR_INVALID, "a composite cannot contain itself");
+    c->components.emplace_back(pc_kind, component);
+    return FAMG_OK;
+}
+famg_status famg_composite_len(const famg_composite *c, int64_t *n) {
+    if (!c || !n) FAMG_FAIL(FAMG_ERR_INVALID, "null argument");
+    *n = (int64_t)c->components.size();
+    return FAMG_OK;
+}
+famg_status famg_composite_destroy(famg_composite *c) {
+    if (!c) return FAMG_OK;
+    cudaSetDevice(c->ctx->device);
+    csr_release(c->a);
+    delete c;
+    return FAMG_OK;
+}
+// composite.rs:66-83
+famg_status famg_composite_apply_dev(famg_composite *c, famg_vec *out, const famg_vec *rhs) {
+    if (!c || !out || !rhs) FAMG_FAIL(FAMG_ERR_INVALID, "null argument");
+    const int64_t n = c->a->nrows;
+    if (out->nrows != n || rhs->nrows != n || out->ncols != rhs->ncols || out->p == rhs->p) FAMG_FAIL(FAMG_ERR_INVALID, "composite apply shape mismatch");
+    famg_ctx *ctx = c->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const int k = (int)rhs->ncols;
+    famg_vec *ws = nullptr, *tmp = nullptr;
+    FAMG_TRY(famg_vec_create(ctx, n, k, &ws));
+    famg_status st = famg_vec_create(ctx, n, k, &tmp);
+    if (st == FAMG_OK) st = famg_vec_fill(out, 0.0);
+    if (st == FAMG_OK) st = famg_vec_copy(ws, rhs);
+    auto step = [&](const std::pair<int, void *> &comp) -> famg_status {
+        FAMG_TRY(pc_apply(comp.first, comp.second, tmp, ws));                             // ws <- M^-1 ws
+        FAMG_TRY(vec_axpby(ctx, out->p, out->ld, tmp->p, tmp->ld, n, k, 1.0, 1.0));       // out += ws
+        return famg_residual_dev(c->a, ws, rhs, out);                                     // ws = rhs - A out
+    };
+    const size_t m = c->components.size();
+    for (size_t i = m; i-- > 0 && st == FAMG_OK;) st = step(c->components[i]);
+    for (size_t i = 1; i < m && st == FAMG_OK; ++i) st = step(c->components[i]);
+    famg_vec_destroy(ws); famg_vec_destroy(tmp);
+    return st;
+}
 
 famg_status famg_pcg_solve_dev(const famg_csr *a, int pc_kind, void *precond, famg_vec *x, const famg_vec *b, double rel_tol,
                                double abs_tol, int64_t max_iters, int zero_guess, famg_cg_info *info) {

@@ -259,20 +259,27 @@ static famg_status coldot(famg_ctx *ctx, const double *x, int64_t ldx, const dou
     return FAMG_OK;
 }
 
-// out = x - M^-1 (A x); tmp (n x k) is used only for non-diagonal smoothers
-static famg_status eprop(const famg_csr *a, const famg_smoother *s, const double *x, int64_t ldx, double *out, int64_t ldo, double *tmp,
+// out = x - M^-1 (A x); tmp (n x k) is used only when the preconditioner is not a Diag smoother
+static famg_status eprop(const famg_csr *a, int pc_kind, void *precond, const double *x, int64_t ldx, double *out, int64_t ldo, double *tmp,
                          int64_t ldt, int k) {
     famg_ctx *ctx = a->ctx;
     SpmvArgs g; g.a = a; g.x = x; g.ldx = ldx; g.y = out; g.ldy = ldo; g.k = k;
-    if (s->kind == SM_DIAG) {
-        g.epi = EPI_EPROP; g.d = s->d;
+    if (pc_kind == FAMG_PC_SMOOTHER && ((const famg_smoother *)precond)->kind == SM_DIAG) {
+        g.epi = EPI_EPROP; g.d = ((const famg_smoother *)precond)->d;
         return spmv_launch(g);
     }
     g.epi = EPI_SPMV;
     FAMG_TRY(spmv_launch(g));                                        // out = A x
-    FAMG_TRY(smoother_apply_dev(s, out, ldo, tmp, ldt, k));          // tmp = M^-1 out
+    famg_vec vo, vt;
+    vec_wrap(ctx, out, a->nrows, k, ldo, &vo);
+    vec_wrap(ctx, tmp, a->nrows, k, ldt, &vt);
+    FAMG_TRY(pc_apply(pc_kind, precond, &vt, &vo));                  // tmp = M^-1 out
     FAMG_TRY(vec_copy(ctx, out, ldo, x, ldx, a->nrows, k));          // out = x
     return vec_axpby(ctx, out, ldo, tmp, ldt, a->nrows, k, -1.0, 1.0);  // out -= tmp
+}
+
+static bool is_diag(int pc_kind, const void *precond) {
+    return pc_kind == FAMG_PC_SMOOTHER && ((const famg_smoother *)precond)->kind == SM_DIAG;
 }
 
 }  // namespace famg
@@ -316,14 +323,22 @@ famg_status famg_error_propagator_dev(const famg_csr *a, const famg_smoother *s,
     if (x->ncols == 0 || a->nrows == 0) return FAMG_OK;
     famg_vec *tmp = nullptr;
     if (s->kind != SM_DIAG) FAMG_TRY(famg_vec_create(ctx, x->nrows, x->ncols, &tmp));
-    famg_status st = eprop(a, s, x->p, x->ld, out->p, out->ld, tmp ? tmp->p : nullptr, tmp ? tmp->ld : 0, (int)x->ncols);
+    famg_status st = eprop(a, FAMG_PC_SMOOTHER, (void *)s, x->p, x->ld, out->p, out->ld, tmp ? tmp->p : nullptr, tmp ? tmp->ld : 0,
+                           (int)x->ncols);
     famg_vec_destroy(tmp);
     return st;
 }
 
 famg_status famg_smooth_vector_dev(const famg_csr *a, const famg_smoother *s, int64_t iterations, famg_vec *x, double *cfs) {
-    if (!a || !s || !x || iterations < 0) FAMG_FAIL(FAMG_ERR_INVALID, "bad argument");
-    if (a->nrows != a->ncols || s->n != a->nrows || x->nrows != a->nrows) FAMG_FAIL(FAMG_ERR_INVALID, "smooth_vector shape mismatch");
+    if (!s) FAMG_FAIL(FAMG_ERR_INVALID, "bad argument");
+    if (a && s->n != a->nrows) FAMG_FAIL(FAMG_ERR_INVALID, "smooth_vector shape mismatch");
+    return famg_smooth_vector_pc_dev(a, FAMG_PC_SMOOTHER, (void *)s, iterations, x, cfs);
+}
+
+famg_status famg_smooth_vector_pc_dev(const famg_csr *a, int pc_kind, void *precond, int64_t iterations, famg_vec *x, double *cfs) {
+    if (!a || !precond || !x || iterations < 0) FAMG_FAIL(FAMG_ERR_INVALID, "bad argument");
+    if (pc_kind != FAMG_PC_SMOOTHER && pc_kind != FAMG_PC_MG && pc_kind != FAMG_PC_COMPOSITE) FAMG_FAIL(FAMG_ERR_INVALID, "unknown preconditioner kind");
+    if (a->nrows != a->ncols || x->nrows != a->nrows) FAMG_FAIL(FAMG_ERR_INVALID, "smooth_vector shape mismatch");
     FAMG_TRY(check_block(x));
     const int64_t n = x->nrows;
     const int k = (int)x->ncols;
@@ -336,14 +351,14 @@ famg_status famg_smooth_vector_dev(const famg_csr *a, const famg_smoother *s, in
     famg_vec *y = nullptr, *t = nullptr;
     FAMG_TRY(pool_alloc(ctx, bytes, &work));
     famg_status st = famg_vec_create(ctx, n, k, &y);
-    if (st == FAMG_OK && (s->kind != SM_DIAG || cfs)) st = famg_vec_create(ctx, n, k, &t);
+    if (st == FAMG_OK && (!is_diag(pc_kind, precond) || cfs)) st = famg_vec_create(ctx, n, k, &t);
     double *cur = x->p; int64_t ldc = x->ld;
     double *oth = y ? y->p : nullptr; int64_t ldo = y ? y->ld : 0;
     // adaptivity.rs:331 and :346: the random block is orthonormalised twice before the loop
     if (st == FAMG_OK) st = thin_q_dev(ctx, cur, ldc, n, k, (double *)work, grid);
     if (st == FAMG_OK) st = thin_q_dev(ctx, cur, ldc, n, k, (double *)work, grid);
     for (int64_t it = 0; it < iterations && st == FAMG_OK; ++it) {  // :351-354
-        st = eprop(a, s, cur, ldc, oth, ldo, t ? t->p : nullptr, t ? t->ld : 0, k);
+        st = eprop(a, pc_kind, precond, cur, ldc, oth, ldo, t ? t->p : nullptr, t ? t->ld : 0, k);
         std::swap(cur, oth); std::swap(ldc, ldo);
         if (st == FAMG_OK) st = thin_q_dev(ctx, cur, ldc, n, k, (double *)work, grid);
     }
@@ -354,13 +369,17 @@ famg_status famg_smooth_vector_dev(const famg_csr *a, const famg_smoother *s, in
         SpmvArgs g; g.a = a; g.epi = EPI_SPMV; g.x = x->p; g.ldx = x->ld; g.y = oth; g.ldy = ldo; g.k = k;
         st = spmv_launch(g);                                                                        // oth = A w
         if (st == FAMG_OK) st = coldot(ctx, x->p, x->ld, oth, ldo, n, k, wa.data());
-        if (st == FAMG_OK) st = smoother_apply_dev(s, oth, ldo, t->p, t->ld, k);                    // t = M^-1 A w
+        if (st == FAMG_OK) {
+            famg_vec vo;
+            vec_wrap(ctx, oth, n, k, ldo, &vo);
+            st = pc_apply(pc_kind, precond, t, &vo);                                                // t = M^-1 A w
+        }
         if (st == FAMG_OK) st = vec_axpby(ctx, t->p, t->ld, x->p, x->ld, n, k, 1.0, -1.0);          // t = w - t
         if (st == FAMG_OK) { g.x = t->p; g.ldx = t->ld; st = spmv_launch(g); }                      // oth = A Ev
         if (st == FAMG_OK) st = coldot(ctx, t->p, t->ld, oth, ldo, n, k, ea.data());
         for (int c = 0; c < k && st == FAMG_OK; ++c) cfs[c] = sqrt(ea[(size_t)c]) / sqrt(wa[(size_t)c]);
     }
-    famg_vec_destroy(y);  // synchronises the stream
+    famg_vec_destroy(y);
     famg_vec_destroy(t);
     pool_free(ctx, work, bytes);
     return st;

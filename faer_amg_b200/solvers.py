@@ -48,13 +48,9 @@ def _mat(op) -> SparseRowMat:
 
 
 def _pc(precond):
-    if precond is None:
-        return PC_NONE, None
-    if isinstance(precond, Multigrid):
-        return PC_MG, precond._h
-    if isinstance(precond, Smoother):
-        return PC_SMOOTHER, precond._h
-    raise TypeError(f"unsupported preconditioner {type(precond)}")
+    from .preconditioners.composite import pc_handle
+
+    return pc_handle(precond)
 
 
 def _finish(fn_status, info, max_iters):

@@ -219,6 +219,23 @@ famg_status famg_smooth_vector_dev(const famg_csr *a, const famg_smoother *s, in
 /* out[c] = x[:,c] . y[:,c] (deterministic two-stage reduction) */
 famg_status famg_vec_coldot(const famg_vec *x, const famg_vec *y, double *out);
 
+/* ---- Composite preconditioner (src/preconditioners/composite.rs) -------------------------------- */
+/* Symmetric multiplicative combination of several preconditioners around one operator (composite.rs:66-83):
+ *   out = 0; ws = rhs; for c in components reversed, then components[1..]: ws <- c^-1 ws; out += ws; ws = rhs - A out
+ * Device-resident: the `rhs - A out` step is the fused residual kernel.  Components are (pc_kind, handle)
+ * pairs -- smoothers and multigrids -- borrowed: the caller keeps them alive (the Rust side holds Arcs).
+ * Usable wherever a (pc_kind, precond) pair is accepted: famg_pcg_solve*, famg_stationary_solve,
+ * famg_smooth_vector_pc_dev (the adaptive driver's test loop, adaptivity.rs:108-114). */
+typedef struct famg_composite famg_composite;
+famg_status famg_composite_create(const famg_csr *a, famg_composite **out);      /* Composite::new_with_components(mat, vec![]) */
+famg_status famg_composite_push(famg_composite *c, int pc_kind, void *component); /* composite.rs:85-87 */
+famg_status famg_composite_len(const famg_composite *c, int64_t *n);
+famg_status famg_composite_apply_dev(famg_composite *c, famg_vec *out, const famg_vec *rhs);
+famg_status famg_composite_destroy(famg_composite *c);
+/* smooth_vector (adaptivity.rs:307-390) with any preconditioner kind; famg_smooth_vector_dev is the FAMG_PC_SMOOTHER case */
+famg_status famg_smooth_vector_pc_dev(const famg_csr *a, int pc_kind, void *precond, int64_t iterations, famg_vec *x,
+                                      double *cfs);
+
 /* ---- host partitioner: PartitionerConfig::build_partition, partitioners/mod.rs:273-329 -
  * Host-only (no device work, no ctx): the north-star keeps aggregation on the host.  A Rust build keeps
  * using the crate's own partitioner; these entry points give the non-Rust harness algebraic aggregates.
@@ -249,7 +266,7 @@ typedef struct {
     double abs_residual;
     double rel_residual;
 } famg_cg_info;
-enum { FAMG_PC_NONE = 0, FAMG_PC_SMOOTHER = 1, FAMG_PC_MG = 2 };
+enum { FAMG_PC_NONE = 0, FAMG_PC_SMOOTHER = 1, FAMG_PC_MG = 2, FAMG_PC_COMPOSITE = 3 };
 /* x (in: initial guess unless zero_guess; out: solution) and b are host buffers of a.nrows
  * doubles.  precond: famg_smoother* or famg_mg* according to pc_kind.  Returns
  * FAMG_ERR_NO_CONVERGENCE with info filled when max_iters is hit. */

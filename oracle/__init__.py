@@ -415,6 +415,22 @@ def block_smoother_vector_apply(a: Csr, vdim: int, agg_ptr, agg_nodes, r) -> np.
     return r
 
 
+def composite_apply(a: Csr, components, rhs) -> np.ndarray:
+    """Composite::implementation (composite.rs:66-83): ``components`` are callables ws -> M^-1 ws."""
+    rhs = _fcol(rhs)
+    out = np.zeros_like(rhs, order="F")
+    ws = rhs.copy(order="F")
+    for comp in reversed(components):
+        ws = comp(ws)
+        out = out + ws
+        ws = rhs - spmm_csr(a, out)
+    for comp in components[1:]:
+        ws = comp(ws)
+        out = out + ws
+        ws = rhs - spmm_csr(a, out)
+    return out
+
+
 def smooth_vector(a: Csr, precond_apply, x0, iterations: int):
     """smooth_vector (adaptivity.rs:307-390) from a given start block x0 (the reference draws it from
     an unseeded StandardNormal stream, :321-329): x = thinQ(thinQ(x0)); iterations x { x = E x;
