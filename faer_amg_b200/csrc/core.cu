@@ -293,6 +293,7 @@ famg_status famg_ctx_create(int device, famg_ctx **out) {
     ctx->num_sms = prop.multiProcessorCount;
     if (const char *v = getenv("FAMG_SPMV_VARIANT")) ctx->spmv_variant = atoi(v) == 1 ? 1 : 2;
     if (const char *v = getenv("FAMG_TMA_MIN_ROWS")) ctx->tma_min_rows = std::max(atoi(v), 1);
+    if (const char *v = getenv("FAMG_SPMM_CB")) ctx->spmm_cb = atoi(v) >= 2 ? 2 : 1;
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     {   // halo exchanges must not queue behind bulk compute: highest priority for the comm stream
         int lo = 0, hi = 0;
@@ -353,6 +354,9 @@ famg_status famg_ctx_set_option(famg_ctx *ctx, const char *key, int64_t value) {
         ctx->spmv_variant = (int)value;
     } else if (!strcmp(key, "tma_min_rows")) {
         ctx->tma_min_rows = (int)std::max<int64_t>(value, 1);
+    } else if (!strcmp(key, "spmm_cb")) {
+        if (value != 1 && value != 2) FAMG_FAIL(FAMG_ERR_INVALID, "spmm_cb must be 1 or 2");
+        ctx->spmm_cb = (int)value;
     } else {
         FAMG_FAIL(FAMG_ERR_INVALID, "unknown option '%s'", key);
     }

@@ -101,8 +101,56 @@ __device__ __forceinline__ void epi_store(double *yc, int row, double s, const E
     if (DOT) dot_acc += o.x * s;
 }
 
-template <int TPR, int EPI, bool DOT>
-__global__ void __launch_bounds__(SPMV_THREADS, 4) spmv_kernel(const SpmvKernelParams p) {
+// ---- column-blocked row walk for k > 1 (K2, SpMM) -------------------------------------------------
+// One pass over a row's staged (col, val) pairs feeds CB right-hand sides: CB x SPMV_U gathers are in
+// flight per thread instead of SPMV_U, and the walk is repeated k / CB times instead of k times.  With one
+// Measured on G7(128^3), E apply at k = 64: CB = 1: 1.27 ms, CB = 2 (72 registers, 3 CTAs/SM): 1.13 ms,
+// CB = 4 (96 registers + spills, 2 CTAs/SM): 1.93 ms -- CB = 2 is what ships (profiles/r1_nearnull.md).
+// Per column the products are summed in the same order as in the single-column walk: same bits.
+template <int TPR, int EPI, int CB, bool STAGED>
+__device__ __forceinline__ void spmm_cols(const SpmvKernelParams &p, int col0, int ncb, const double *__restrict__ vals,
+                                          const int *__restrict__ cols, int qa, int qe, int row, bool store) {
+    constexpr int GPW = 32 / TPR;
+    const double *xc[CB];
+    EpiOps ops[CB];
+    double s[CB];
+#pragma unroll
+    for (int c = 0; c < CB; ++c) {
+        const int col = col0 + (c < ncb ? c : 0);
+        xc[c] = p.x + (long long)col * p.ldx;
+        ops[c] = epi_prefetch<EPI, false>(p, xc[c], p.y + (long long)col * p.ldy, col, row, store && c < ncb);
+        s[c] = 0.0;
+    }
+    for (int q = qa; q < qe; q += TPR * SPMV_U) {
+        double pr[CB][SPMV_U];
+#pragma unroll
+        for (int u = 0; u < SPMV_U; ++u) {
+            const int qq = q + u * TPR;
+            double v = 0.0;
+            int j = 0;
+            const bool on = qq < qe;
+            if (on) { v = STAGED ? vals[qq] : __ldg(vals + qq); j = STAGED ? cols[qq] : __ldg(cols + qq); }
+#pragma unroll
+            for (int c = 0; c < CB; ++c) pr[c][u] = on ? v * __ldg(xc[c] + j) : 0.0;
+        }
+#pragma unroll
+        for (int c = 0; c < CB; ++c)
+#pragma unroll
+            for (int u = 0; u < SPMV_U; ++u) s[c] += pr[c][u];
+    }
+    double unused = 0.0;
+#pragma unroll
+    for (int c = 0; c < CB; ++c) {
+        if (TPR > 1) {
+#pragma unroll
+            for (int o = 16; o >= GPW; o >>= 1) s[c] += __shfl_xor_sync(0xffffffffu, s[c], o);
+        }
+        if (store && c < ncb) epi_store<EPI, false>(p.y + (long long)(col0 + c) * p.ldy, row, s[c], ops[c], unused);
+    }
+}
+
+template <int TPR, int EPI, bool DOT, int CB>
+__global__ void __launch_bounds__(SPMV_THREADS, CB == 1 ? 4 : 3) spmv_kernel(const SpmvKernelParams p) {
     constexpr int ROWS = SPMV_THREADS / TPR;
     __shared__ __align__(16) double s_val[SPMV_CAP];
     __shared__ __align__(16) int s_col[SPMV_CAP];
@@ -154,6 +202,14 @@ __global__ void __launch_bounds__(SPMV_THREADS, 4) spmv_kernel(const SpmvKernelP
     __syncthreads();
 
     double dot_acc = 0.0;
+    if constexpr (CB > 1) {
+        for (int c0 = 0; c0 < p.k; c0 += CB) {
+            const int ncb = min(CB, p.k - c0);
+            if (staged) spmm_cols<TPR, EPI, CB, true>(p, c0, ncb, s_val, s_col, a - q0a + lane, e - q0a, row, active && lane == 0);
+            else spmm_cols<TPR, EPI, CB, false>(p, c0, ncb, p.val, p.col, a + lane, e, row, active && lane == 0);
+        }
+        return;
+    }
     for (int c = 0; c < p.k; ++c) {
         const double *__restrict__ xc = p.x + (long long)c * p.ldx;
         double *yc = p.y + (long long)c * p.ldy;
@@ -260,8 +316,8 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-template <int TPR, int EPI, bool DOT>
-__global__ void __launch_bounds__(TMA_THREADS, TMA_CTAS) spmv_tma_kernel(const SpmvKernelParams p, const int nchunks) {
+template <int TPR, int EPI, bool DOT, int CB>
+__global__ void __launch_bounds__(TMA_THREADS, CB == 1 ? TMA_CTAS : 3) spmv_tma_kernel(const SpmvKernelParams p, const int nchunks) {
     constexpr int ROWS = TMA_CONSUMERS / TPR;
     extern __shared__ __align__(128) unsigned char smem[];
     double *s_val = reinterpret_cast<double *>(smem);
@@ -336,6 +392,14 @@ __global__ void __launch_bounds__(TMA_THREADS, TMA_CTAS) spmv_tma_kernel(const S
         const bool staged = cnt > 0 && cnt <= TMA_CAP;
         const double *sv = s_val + stage * TMA_CAP;
         const int *sc = s_col + stage * TMA_CAP;
+        if constexpr (CB > 1) {
+            if (staged) { mbar_wait(&full[stage], (fphase >> stage) & 1u); fphase ^= 1u << stage; }
+            for (int c0 = 0; c0 < p.k; c0 += CB) {
+                const int ncb = min(CB, p.k - c0);
+                if (staged) spmm_cols<TPR, EPI, CB, true>(p, c0, ncb, sv, sc, a - q0a + lane, e - q0a, row, active && lane == 0);
+                else spmm_cols<TPR, EPI, CB, false>(p, c0, ncb, p.val, p.col, a + lane, e, row, active && lane == 0);
+            }
+        } else
         for (int col = 0; col < p.k; ++col) {
             const double *__restrict__ xc = p.x + (long long)col * p.ldx;
             double *yc = p.y + (long long)col * p.ldy;
@@ -395,39 +459,46 @@ __global__ void __launch_bounds__(TMA_THREADS, TMA_CTAS) spmv_tma_kernel(const S
     }
 }
 
-template <int TPR, int EPI, bool DOT>
+template <int TPR, int EPI, bool DOT, int CB>
 static famg_status launch_one(SpmvKernelParams kp, int variant, int nrows1, int nrows2, int num_sms, int reserve_ctas, cudaStream_t st,
                               int *grid_out) {
     constexpr int ROWS = 256 / TPR;  // both variants use 256 row-walking threads
     kp.nchunks1 = (int)ceil_div(nrows1, ROWS);
     const int nchunks = kp.nchunks1 + (int)ceil_div(nrows2, ROWS);
     if (variant == 2) {
-        const int grid = std::max(1, std::min(nchunks, TMA_CTAS * num_sms - reserve_ctas));
+        constexpr int CTAS = CB == 1 ? TMA_CTAS : 3;  // resident CTAs per SM (register budget of the column block)
+        const int grid = std::max(1, std::min(nchunks, CTAS * num_sms - reserve_ctas));
         static bool configured = false;  // per template instance
         if (!configured) {
-            CUDA_TRY(cudaFuncSetAttribute(spmv_tma_kernel<TPR, EPI, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM));
+            CUDA_TRY(cudaFuncSetAttribute(spmv_tma_kernel<TPR, EPI, DOT, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM));
             configured = true;
         }
-        spmv_tma_kernel<TPR, EPI, DOT><<<grid, TMA_THREADS, TMA_SMEM, st>>>(kp, nchunks);
+        spmv_tma_kernel<TPR, EPI, DOT, CB><<<grid, TMA_THREADS, TMA_SMEM, st>>>(kp, nchunks);
         *grid_out = grid;
     } else {
-        spmv_kernel<TPR, EPI, DOT><<<nchunks, SPMV_THREADS, 0, st>>>(kp);
+        spmv_kernel<TPR, EPI, DOT, CB><<<nchunks, SPMV_THREADS, 0, st>>>(kp);
         *grid_out = nchunks;
     }
     return FAMG_OK;
 }
 
+template <int TPR, int EPI>
+static famg_status launch_cb(const SpmvKernelParams &kp, int cb, int variant, int nrows, int nrows2, int sms, int reserve, cudaStream_t st, int *grid) {
+    if (cb >= 2) return launch_one<TPR, EPI, false, 2>(kp, variant, nrows, nrows2, sms, reserve, st, grid);
+    return launch_one<TPR, EPI, false, 1>(kp, variant, nrows, nrows2, sms, reserve, st, grid);
+}
+
 template <int TPR>
-static famg_status launch_tpr(const SpmvKernelParams &kp, int epi, bool dot, int variant, int nrows, int nrows2, int sms, int reserve, cudaStream_t st, int *grid) {
+static famg_status launch_tpr(const SpmvKernelParams &kp, int epi, bool dot, int cb, int variant, int nrows, int nrows2, int sms, int reserve, cudaStream_t st, int *grid) {
     switch (epi) {
         case EPI_SPMV:
-            return dot ? launch_one<TPR, EPI_SPMV, true>(kp, variant, nrows, nrows2, sms, reserve, st, grid)
-                       : launch_one<TPR, EPI_SPMV, false>(kp, variant, nrows, nrows2, sms, reserve, st, grid);
-        case EPI_RESID: return launch_one<TPR, EPI_RESID, false>(kp, variant, nrows, nrows2, sms, reserve, st, grid);
-        case EPI_SMOOTH: return launch_one<TPR, EPI_SMOOTH, false>(kp, variant, nrows, nrows2, sms, reserve, st, grid);
-        case EPI_ADD: return launch_one<TPR, EPI_ADD, false>(kp, variant, nrows, nrows2, sms, reserve, st, grid);
-        case EPI_EPROP: return launch_one<TPR, EPI_EPROP, false>(kp, variant, nrows, nrows2, sms, reserve, st, grid);
-        default: return launch_one<TPR, EPI_SI, false>(kp, variant, nrows, nrows2, sms, reserve, st, grid);
+            return dot ? launch_one<TPR, EPI_SPMV, true, 1>(kp, variant, nrows, nrows2, sms, reserve, st, grid)
+                       : launch_cb<TPR, EPI_SPMV>(kp, cb, variant, nrows, nrows2, sms, reserve, st, grid);
+        case EPI_RESID: return launch_cb<TPR, EPI_RESID>(kp, cb, variant, nrows, nrows2, sms, reserve, st, grid);
+        case EPI_SMOOTH: return launch_cb<TPR, EPI_SMOOTH>(kp, cb, variant, nrows, nrows2, sms, reserve, st, grid);
+        case EPI_ADD: return launch_cb<TPR, EPI_ADD>(kp, cb, variant, nrows, nrows2, sms, reserve, st, grid);
+        case EPI_EPROP: return launch_cb<TPR, EPI_EPROP>(kp, cb, variant, nrows, nrows2, sms, reserve, st, grid);
+        default: return launch_cb<TPR, EPI_SI>(kp, cb, variant, nrows, nrows2, sms, reserve, st, grid);
     }
 }
 
@@ -457,15 +528,17 @@ famg_status spmv_launch(const SpmvArgs &args, int *num_ctas) {
     const bool dot = args.dot_partials != nullptr;
     // small operators (coarse levels) do not fill a persistent grid: keep the one-chunk-per-CTA kernel
     const int variant = (ctx->spmv_variant == 2 && nrows + nrows2 >= ctx->tma_min_rows) ? 2 : 1;
+    // right-hand sides walked per pass over a row (K2): 1 for k == 1 (the cycle / PCG path is untouched)
+    const int cb = args.k >= 2 ? std::min(ctx->spmm_cb, 2) : 1;
     int grid = 0;
     famg_status stt;
     switch (tpr) {
-        case 1: stt = launch_tpr<1>(kp, args.epi, dot, variant, nrows, nrows2, ctx->num_sms, args.reserve_ctas, st, &grid); break;
-        case 2: stt = launch_tpr<2>(kp, args.epi, dot, variant, nrows, nrows2, ctx->num_sms, args.reserve_ctas, st, &grid); break;
-        case 4: stt = launch_tpr<4>(kp, args.epi, dot, variant, nrows, nrows2, ctx->num_sms, args.reserve_ctas, st, &grid); break;
-        case 8: stt = launch_tpr<8>(kp, args.epi, dot, variant, nrows, nrows2, ctx->num_sms, args.reserve_ctas, st, &grid); break;
-        case 16: stt = launch_tpr<16>(kp, args.epi, dot, variant, nrows, nrows2, ctx->num_sms, args.reserve_ctas, st, &grid); break;
-        default: stt = launch_tpr<32>(kp, args.epi, dot, variant, nrows, nrows2, ctx->num_sms, args.reserve_ctas, st, &grid); break;
+        case 1: stt = launch_tpr<1>(kp, args.epi, dot, cb, variant, nrows, nrows2, ctx->num_sms, args.reserve_ctas, st, &grid); break;
+        case 2: stt = launch_tpr<2>(kp, args.epi, dot, cb, variant, nrows, nrows2, ctx->num_sms, args.reserve_ctas, st, &grid); break;
+        case 4: stt = launch_tpr<4>(kp, args.epi, dot, cb, variant, nrows, nrows2, ctx->num_sms, args.reserve_ctas, st, &grid); break;
+        case 8: stt = launch_tpr<8>(kp, args.epi, dot, cb, variant, nrows, nrows2, ctx->num_sms, args.reserve_ctas, st, &grid); break;
+        case 16: stt = launch_tpr<16>(kp, args.epi, dot, cb, variant, nrows, nrows2, ctx->num_sms, args.reserve_ctas, st, &grid); break;
+        default: stt = launch_tpr<32>(kp, args.epi, dot, cb, variant, nrows, nrows2, ctx->num_sms, args.reserve_ctas, st, &grid); break;
     }
     FAMG_TRY(stt);
     count_launch(ctx);
