@@ -100,6 +100,7 @@ SIGNATURES = {
     "famg_smooth_p": [vp, vp, vp, vpp],
     "famg_tentative_p": [vp, i64, i64, i64, i64, f64p, i64, i64, u64p, u64p, vpp, f64p],
     "famg_thin_q": [i64, i64, f64p, i64],
+    "famg_geometric_partition": [i64, i64, i64, i64, i64, i64, u64p, u64p, i64p],
     "famg_thin_q_dev": [vp],
     "famg_error_propagator_dev": [vp, vp, vp, vp],
     "famg_smooth_vector_dev": [vp, vp, i64, vp, f64p],

@@ -109,6 +109,24 @@ famg_status exclusive_scan_i32(famg_ctx *ctx, const int *in, int *out, int64_t n
 }
 
 // ---------------------------------------------------------------- CSR helpers
+static famg_status stream_alloc(famg_ctx *ctx, void **p, size_t bytes) {
+    *p = nullptr;
+    cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 1, ctx->stream);
+    if (e == cudaErrorMemoryAllocation) {  // give cached blocks back and retry once
+        cudaGetLastError();
+        pool_trim(ctx);
+        cudaMemPool_t mp;
+        if (cudaDeviceGetDefaultMemPool(&mp, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(mp, 0);
+        e = cudaMallocAsync(p, bytes ? bytes : 1, ctx->stream);
+    }
+    if (e != cudaSuccess) {
+        *p = nullptr;
+        set_error("cudaMallocAsync(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        return e == cudaErrorMemoryAllocation ? FAMG_ERR_ALLOC : FAMG_ERR_CUDA;
+    }
+    return FAMG_OK;
+}
+
 famg_status csr_alloc(famg_ctx *ctx, int64_t nrows, int64_t ncols, int64_t nnz, famg_csr **out) {
     *out = nullptr;
     if (nrows < 0 || ncols < 0 || nnz < 0) FAMG_FAIL(FAMG_ERR_INVALID, "negative CSR dimension");
@@ -117,9 +135,13 @@ famg_status csr_alloc(famg_ctx *ctx, int64_t nrows, int64_t ncols, int64_t nnz, 
                   (long long)nrows, (long long)ncols, (long long)nnz);
     famg_csr *a = new famg_csr();
     a->ctx = ctx; a->nrows = nrows; a->ncols = ncols; a->nnz = nnz;
-    famg_status st = dev_alloc(&a->row_ptr, nrows + 1 + CSR_PAD);
-    if (st == FAMG_OK) st = dev_alloc(&a->col, nnz + CSR_PAD);
-    if (st == FAMG_OK) st = dev_alloc(&a->val, nnz + CSR_PAD);
+    // stream-ordered allocation from the device's caching pool (release threshold raised in
+    // famg_ctx_create): a hierarchy build allocates and frees dozens of operators, and plain
+    // cudaMalloc / cudaFree both synchronise the device and hand memory back to the driver, which
+    // made every other build of the same hierarchy take seconds instead of 0.6 s
+    famg_status st = stream_alloc(ctx, (void **)&a->row_ptr, sizeof(int) * (size_t)(nrows + 1 + CSR_PAD));
+    if (st == FAMG_OK) st = stream_alloc(ctx, (void **)&a->col, sizeof(int) * (size_t)(nnz + CSR_PAD));
+    if (st == FAMG_OK) st = stream_alloc(ctx, (void **)&a->val, sizeof(double) * (size_t)(nnz + CSR_PAD));
     if (st != FAMG_OK) { csr_release(a); return st; }
     // zero the pads so aligned over-reads see valid indices / finite values
     cudaMemsetAsync(a->col + nnz, 0, sizeof(int) * CSR_PAD, ctx->stream);
@@ -132,7 +154,11 @@ famg_status csr_alloc(famg_ctx *ctx, int64_t nrows, int64_t ncols, int64_t nnz, 
 void csr_release(famg_csr *a) {
     if (!a) return;
     if (a->refs.fetch_sub(1) == 1) {
-        cudaFree(a->row_ptr); cudaFree(a->col); cudaFree(a->val);
+        // ordered after everything already queued on the context's stream that may read the buffers
+        cudaStream_t st = a->ctx->stream;
+        if (a->row_ptr) cudaFreeAsync(a->row_ptr, st);
+        if (a->col) cudaFreeAsync(a->col, st);
+        if (a->val) cudaFreeAsync(a->val, st);
         delete a;
     }
 }
@@ -150,7 +176,7 @@ famg_status csr_finalize_plan(famg_csr *a) {
     famg_ctx *ctx = a->ctx;
     a->avg_row_nnz = a->nrows > 0 ? (double)a->nnz / (double)a->nrows : 0.0;
     int *d_max = nullptr;
-    FAMG_TRY(dev_alloc(&d_max, 1));
+    FAMG_TRY(pool_alloc(ctx, 256, (void **)&d_max));  // pooled: a cudaMalloc / cudaFree pair per operator adds up over a build
     cudaMemsetAsync(d_max, 0, sizeof(int), ctx->stream);
     if (a->nrows > 0) {
         int blocks = (int)std::min<int64_t>(ceil_div(a->nrows, 256), 4 * ctx->num_sms);
@@ -160,7 +186,7 @@ famg_status csr_finalize_plan(famg_csr *a) {
     int h_max = 0;
     cudaError_t e = cudaMemcpyAsync(&h_max, d_max, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_max);
+    pool_free(ctx, d_max, 256);
     if (e != cudaSuccess) FAMG_FAIL(FAMG_ERR_CUDA, "csr plan failed: %s", cudaGetErrorString(e));
     a->max_row_nnz = h_max;
     // threads-per-row: each thread should own <= ~9 staged entries so one chunk of 256/tpr rows
@@ -227,6 +253,8 @@ famg_status pool_alloc(famg_ctx *ctx, size_t bytes, void **p) {
     if (e == cudaErrorMemoryAllocation) {  // give cached blocks back and retry once
         cudaGetLastError();
         pool_trim(ctx);
+        cudaMemPool_t mp;
+        if (cudaDeviceGetDefaultMemPool(&mp, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(mp, 0);  // cached operator storage
         e = cudaMalloc(p, bytes);
     }
     if (e != cudaSuccess) {
@@ -295,6 +323,14 @@ famg_status famg_ctx_create(int device, famg_ctx **out) {
     if (const char *v = getenv("FAMG_TMA_MIN_ROWS")) ctx->tma_min_rows = std::max(atoi(v), 1);
     if (const char *v = getenv("FAMG_SPMM_CB")) ctx->spmm_cb = atoi(v) >= 2 ? 2 : 1;
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    {   // keep freed operator storage cached in the device pool instead of returning it to the driver
+        cudaMemPool_t mp;
+        if (cudaDeviceGetDefaultMemPool(&mp, device) == cudaSuccess) {
+            uint64_t threshold = UINT64_MAX;
+            cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &threshold);
+        }
+        cudaGetLastError();
+    }
     {   // halo exchanges must not queue behind bulk compute: highest priority for the comm stream
         int lo = 0, hi = 0;
         CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));

@@ -6,6 +6,8 @@
 // is compiled with -fmad=false) so they are bit-identical to the oracle's generators.
 #include <cmath>
 
+#include <memory>
+
 #include "common.cuh"
 
 namespace famg {
@@ -186,6 +188,35 @@ famg_status famg_gallery_g27(famg_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, 
     return gallery_build(ctx, nx, ny, nz, 27, eps_y, eps_z, out);
 }
 
+// Deterministic geometric aggregates of a lexicographic nx*ny*nz grid (i = x + nx*(y + ny*z)): bx x by x bz
+// boxes, a trailing partial box joins its predecessor; nodes ascending inside every aggregate (BTreeSet
+// order).  Host-only helper for the benchmark configurations -- stands where the caller's
+// partitioner runs; 16.8 M nodes take 23 ms on 16 cores against 85 ms in numpy.
+famg_status famg_geometric_partition(int64_t nx, int64_t ny, int64_t nz, int64_t bx, int64_t by, int64_t bz, uint64_t *agg_ptr,
+                                     uint64_t *agg_nodes, int64_t *coarse_dims) {
+    if (nx < 1 || ny < 1 || nz < 1 || bx < 1 || by < 1 || bz < 1 || !coarse_dims) FAMG_FAIL(FAMG_ERR_INVALID, "geometric_partition: bad argument");
+    const int64_t cx = std::max<int64_t>(nx / bx, 1), cy = std::max<int64_t>(ny / by, 1), cz = std::max<int64_t>(nz / bz, 1);
+    coarse_dims[0] = cx; coarse_dims[1] = cy; coarse_dims[2] = cz;
+    if (!agg_ptr || !agg_nodes) return FAMG_OK;  // size query
+    const int64_t na = cx * cy * cz;
+    auto lo = [](int64_t a, int64_t b) { return a * b; };
+    auto hi = [](int64_t a, int64_t b, int64_t c, int64_t n) { return a == c - 1 ? n : (a + 1) * b; };
+    agg_ptr[0] = 0;
+    for (int64_t a = 0; a < na; ++a) {
+        const int64_t ax = a % cx, ay = (a / cx) % cy, az = a / (cx * cy);
+        agg_ptr[a + 1] = agg_ptr[a] + (uint64_t)((hi(ax, bx, cx, nx) - lo(ax, bx)) * (hi(ay, by, cy, ny) - lo(ay, by)) * (hi(az, bz, cz, nz) - lo(az, bz)));
+    }
+#pragma omp parallel for schedule(static)
+    for (int64_t a = 0; a < na; ++a) {
+        const int64_t ax = a % cx, ay = (a / cx) % cy, az = a / (cx * cy);
+        uint64_t t = agg_ptr[a];
+        for (int64_t z = lo(az, bz); z < hi(az, bz, cz, nz); ++z)
+            for (int64_t y = lo(ay, by); y < hi(ay, by, cy, ny); ++y)
+                for (int64_t x = lo(ax, bx); x < hi(ax, bx, cx, nx); ++x) agg_nodes[t++] = (uint64_t)(x + nx * (y + ny * z));
+    }
+    return FAMG_OK;
+}
+
 famg_status famg_tentative_p(famg_ctx *ctx, int64_t n_fine, int64_t block_size, int64_t k, int64_t cand, const double *near_null,
                              int64_t ld_nn, int64_t n_aggs, const uint64_t *agg_ptr, const uint64_t *agg_nodes, famg_csr **p,
                              double *coarse_nn) {
@@ -197,15 +228,19 @@ famg_status famg_tentative_p(famg_ctx *ctx, int64_t n_fine, int64_t block_size, 
     CUDA_TRY(cudaSetDevice(ctx->device));
     const int64_t nc = n_aggs * cand;
     // row i of P has exactly `cand` entries (columns ci*cand .. ci*cand+cand-1) => direct CSR
-    std::vector<int> rp((size_t)n_fine + 1), ci((size_t)(n_fine * cand));
-    std::vector<double> cv((size_t)(n_fine * cand), 0.0);
-    std::vector<char> seen((size_t)(n_fine / block_size), 0);
-    for (int64_t i = 0; i <= n_fine; ++i) rp[(size_t)i] = (int)(i * cand);
-    std::vector<double> u, s, v;
     if (k == 1 && cand == 1 && block_size == 1) {
         // scalar problems with one near-null vector (every BASELINE config): the thin SVD of an
         // m x 1 block is u = local/||local||, s = ||local||, v = 1 -- same operations, same bits as
-        // the general path, without the per-aggregate temporaries
+        // the general path, without the per-aggregate temporaries.  At 16.8 M rows this is host
+        // memory traffic: buffers are left uninitialised (every slot is written exactly once for a
+        // valid partition, and an invalid one fails below before anything is uploaded) and all
+        // passes run on every core.  (A pinned, context-owned staging arena was tried for the upload:
+        // no reproducible gain on the shared boxes, not kept.)
+        std::unique_ptr<int[]> rp1(new int[(size_t)n_fine + 1]), ci1(new int[(size_t)std::max<int64_t>(n_fine, 1)]);
+        std::unique_ptr<double[]> cv1(new double[(size_t)std::max<int64_t>(n_fine, 1)]);
+        std::unique_ptr<unsigned char[]> seen1(new unsigned char[(size_t)std::max<int64_t>(n_fine, 1)]);
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i <= n_fine; ++i) { rp1[(size_t)i] = (int)i; if (i < n_fine) seen1[(size_t)i] = 0; }
         int bad = 0;
         // aggregates are independent; each node is written by exactly one aggregate of a valid partition
 #pragma omp parallel for schedule(static) reduction(| : bad)
@@ -225,17 +260,24 @@ famg_status famg_tentative_p(famg_ctx *ctx, int64_t n_fine, int64_t block_size, 
             coarse_nn[g] = sv * 1.0;
             for (uint64_t t = b0; t < b1; ++t) {
                 const uint64_t node = agg_nodes[t];
-                ci[(size_t)node] = (int)g;
-                cv[(size_t)node] = sv > 0 ? near_null[node] / sv : 0.0;
-                seen[(size_t)node] += 1;  // one writer per node unless the partition is invalid (checked below)
+                ci1[(size_t)node] = (int)g;
+                cv1[(size_t)node] = sv > 0 ? near_null[node] / sv : 0.0;
+                __atomic_fetch_add(&seen1[(size_t)node], (unsigned char)1, __ATOMIC_RELAXED);  // a node listed twice must not go unnoticed
             }
         }
         if (bad & 1) FAMG_FAIL(FAMG_ERR_INVALID, "Agg size of 0 cannot support near-null dimension of 1");
         if (bad & 2) FAMG_FAIL(FAMG_ERR_INVALID, "invalid partition");
-        for (int64_t i = 0; i < n_fine; ++i)
-            if (seen[(size_t)i] != 1) FAMG_FAIL(FAMG_ERR_INVALID, "invalid partition");
-        return csr_from_host_i32(ctx, n_fine, nc, rp.data(), ci.data(), cv.data(), p);
+        int invalid = 0;
+#pragma omp parallel for schedule(static) reduction(| : invalid)
+        for (int64_t i = 0; i < n_fine; ++i) invalid |= seen1[(size_t)i] != 1;
+        if (invalid) FAMG_FAIL(FAMG_ERR_INVALID, "invalid partition");
+        return csr_from_host_i32(ctx, n_fine, nc, rp1.get(), ci1.get(), cv1.get(), p);
     }
+    std::vector<int> rp((size_t)n_fine + 1), ci((size_t)(n_fine * cand));
+    std::vector<double> cv((size_t)(n_fine * cand), 0.0);
+    std::vector<char> seen((size_t)(n_fine / block_size), 0);
+    for (int64_t i = 0; i <= n_fine; ++i) rp[(size_t)i] = (int)(i * cand);
+    std::vector<double> u, s, v;
     for (int64_t g = 0; g < n_aggs; ++g) {
         const int64_t na = (int64_t)(agg_ptr[g + 1] - agg_ptr[g]);
         const int64_t m = na * block_size;

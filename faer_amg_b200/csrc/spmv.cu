@@ -208,8 +208,7 @@ __global__ void __launch_bounds__(SPMV_THREADS, CB == 1 ? 4 : 3) spmv_kernel(con
             if (staged) spmm_cols<TPR, EPI, CB, true>(p, c0, ncb, s_val, s_col, a - q0a + lane, e - q0a, row, active && lane == 0);
             else spmm_cols<TPR, EPI, CB, false>(p, c0, ncb, p.val, p.col, a + lane, e, row, active && lane == 0);
         }
-        return;
-    }
+    } else {
     for (int c = 0; c < p.k; ++c) {
         const double *__restrict__ xc = p.x + (long long)c * p.ldx;
         double *yc = p.y + (long long)c * p.ldy;
@@ -260,6 +259,7 @@ __global__ void __launch_bounds__(SPMV_THREADS, CB == 1 ? 4 : 3) spmv_kernel(con
             p.dot_partials[blockIdx.x] = t;
         }
     }
+    }  // CB == 1
 }
 
 // ===================================================================================================

@@ -45,7 +45,7 @@ __device__ __forceinline__ void qr_load_tile(double (*tile)[QR_LDT], const doubl
 // of a 16 x 16 grid owns the KB x KB entries {ti + 16a} x {tj + 16b}: per tile row 2 KB shared loads
 // (consecutive ti -> consecutive words; tj takes 2 values per warp -> broadcast) feed KB^2 FMAs.
 template <int KB>
-__global__ void __launch_bounds__(QR_THREADS) gram_partial_kernel(const double *__restrict__ x, long long ld, long long n, int k,
+__global__ void __launch_bounds__(QR_THREADS, 3) gram_partial_kernel(const double *__restrict__ x, long long ld, long long n, int k,
                                                                   double *__restrict__ partials) {
     __shared__ double tile[QR_TILE][QR_LDT];
     for (int t = threadIdx.x; t < QR_TILE * QR_LDT; t += QR_THREADS) (&tile[0][0])[t] = 0.0;  // columns >= k stay zero
@@ -92,7 +92,7 @@ __global__ void sum_partials_kernel(const double *__restrict__ partials, int npa
 // Thread (r = tid % 64, g = tid / 64) owns row r and the CPT = 4 KB columns [g CPT, (g + 1) CPT): per
 // inner index one tile load and CPT warp-uniform (broadcast) coefficient loads feed CPT FMAs.
 template <int KB>
-__global__ void __launch_bounds__(QR_THREADS) apply_rinv_kernel(double *__restrict__ x, long long ld, long long n, int k,
+__global__ void __launch_bounds__(QR_THREADS, 3) apply_rinv_kernel(double *__restrict__ x, long long ld, long long n, int k,
                                                                 const double *__restrict__ rinv_rm) {
     constexpr int CPT = 4 * KB;
     extern __shared__ __align__(16) double qr_smem[];  // tile, then Rinv (k x QR_MAXK)
@@ -171,7 +171,7 @@ __global__ void coldot_reduce_kernel(const double *__restrict__ partials, int nb
 }
 
 static inline int qr_grid(famg_ctx *ctx, int64_t n) {
-    return (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, QR_TILE), 2 * (int64_t)ctx->num_sms));
+    return (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, QR_TILE), 3 * (int64_t)ctx->num_sms));  // 3 CTAs/SM (80 registers)
 }
 
 // one CholeskyQR pass; d_work holds grid*k*k partials, k*k Gram, k*QR_MAXK Rinv

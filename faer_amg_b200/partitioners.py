@@ -61,23 +61,18 @@ class Partition:
 def geometric_partition(dims: Sequence[int], block: Sequence[int] = (2, 2, 2)) -> Tuple[Partition, Tuple[int, int, int]]:
     """bx x by x bz boxes of a lexicographic grid (i = x + nx*(y + ny*z)); a trailing partial box
     joins its predecessor.  Returns the partition and the coarse grid dimensions."""
-    nx, ny, nz = dims
-    bx, by, bz = block
-    cx, cy, cz = max(nx // bx, 1), max(ny // by, 1), max(nz // bz, 1)
-    if nx == cx * bx and ny == cy * by and nz == cz * bz:
-        # regular case, built directly (no sort): aggregate (X,Y,Z) lists its nodes in (dz,dy,dx)
-        # order, which is ascending node order
-        ix = (bx * np.arange(cx, dtype=np.int64)[:, None] + np.arange(bx, dtype=np.int64)[None, :])
-        iy = (by * np.arange(cy, dtype=np.int64)[:, None] + np.arange(by, dtype=np.int64)[None, :]) * nx
-        iz = (bz * np.arange(cz, dtype=np.int64)[:, None] + np.arange(bz, dtype=np.int64)[None, :]) * (nx * ny)
-        nodes = (iz[:, None, None, :, None, None] + iy[None, :, None, None, :, None] + ix[None, None, :, None, None, :])
-        ptr = np.arange(cx * cy * cz + 1, dtype=np.int64) * (bx * by * bz)
-        return Partition(ptr, nodes.reshape(-1), nx * ny * nz, validate=False), (cx, cy, cz)
-    x = np.minimum(np.arange(nx) // bx, cx - 1)
-    y = np.minimum(np.arange(ny) // by, cy - 1)
-    z = np.minimum(np.arange(nz) // bz, cz - 1)
-    agg = (x[None, None, :] + cx * (y[None, :, None] + cy * z[:, None, None])).reshape(-1)
-    return Partition.from_node_to_agg(agg), (cx, cy, cz)
+    from ._ffi import call, i64p, u64p
+
+    nx, ny, nz = (int(d) for d in dims)
+    bx, by, bz = (int(b) for b in block)
+    coarse = np.zeros(3, dtype=np.int64)
+    call("famg_geometric_partition", nx, ny, nz, bx, by, bz, None, None, coarse.ctypes.data_as(i64p))
+    ptr = np.empty(int(coarse.prod()) + 1, dtype=np.uint64)
+    nodes = np.empty(nx * ny * nz, dtype=np.uint64)
+    call("famg_geometric_partition", nx, ny, nz, bx, by, bz, ptr.ctypes.data_as(u64p), nodes.ctypes.data_as(u64p),
+         coarse.ctypes.data_as(i64p))
+    # same bits as int64 (all values < 2^63): reinterpret, no copy
+    return Partition(ptr.view(np.int64), nodes.view(np.int64), nx * ny * nz, validate=False), tuple(int(c) for c in coarse)
 
 
 class GeometricPartitioner:

@@ -193,6 +193,12 @@ famg_status famg_galerkin_block(const famg_csr *a, const famg_csr *p0, int64_t b
 /* block_jacobi (interpolation/mod.rs:963-1028) and smooth_p (:1030-1040: m_inv * (-(A P)) + P) on their own */
 famg_status famg_block_jacobi(const famg_csr *a, int64_t block_size, const famg_csr *p, famg_csr **out);
 famg_status famg_smooth_p(const famg_csr *a, const famg_csr *m_inv, const famg_csr *p, famg_csr **out);
+/* Deterministic geometric aggregates of a lexicographic grid (the benchmark configurations' stand-in for the
+ * caller's partitioner): bx x by x bz boxes, trailing partial boxes join their predecessor, nodes
+ * ascending per aggregate.  Host-only.  agg_ptr: prod(coarse_dims) + 1 entries, agg_nodes: nx*ny*nz; pass NULL
+ * for both to query coarse_dims[3] first. */
+famg_status famg_geometric_partition(int64_t nx, int64_t ny, int64_t nz, int64_t bx, int64_t by, int64_t bz,
+                                     uint64_t *agg_ptr, uint64_t *agg_nodes, int64_t *coarse_dims);
 /* tentative prolongator of smoothed_aggregation (interpolation/mod.rs:747-809): per-aggregate
  * thin SVD of the near-null block on the host (tiny dense work), P uploaded as CSR.
  * near_null: n_fine x k column-major; coarse_nn (out): (n_aggs*cand) x k column-major. */
