@@ -92,6 +92,16 @@ impl GpuSmoother {
         check(unsafe { ffi::famg_smoother_cholesky(op.raw(), &mut h) });
         Self { h, n: op.nrows }
     }
+    /// `BlockSmoother::new` (block_smoothers.rs:88-123): one diagonally compensated block per aggregate,
+    /// solved exactly; `vdim > 1` lumps off-aggregate coupling blocks by `diagonally_compensate_vector`.
+    /// `agg_ptr` / `agg_nodes`: the `Partition`'s aggregates in CSR form (BTreeSet order).
+    pub fn block(op: &GpuSpmmOp, vdim: usize, agg_ptr: &[usize], agg_nodes: &[usize]) -> Self {
+        let mut h = std::ptr::null_mut();
+        check(unsafe {
+            ffi::famg_smoother_block_vector(op.raw(), vdim as i64, agg_ptr.len() as i64 - 1, agg_ptr.as_ptr(), agg_nodes.as_ptr(), &mut h)
+        });
+        Self { h, n: op.nrows }
+    }
     pub(crate) fn raw(&self) -> *const ffi::famg_smoother { self.h }
 }
 impl Drop for GpuSmoother { fn drop(&mut self) { unsafe { ffi::famg_smoother_destroy(self.h); } } }
@@ -158,6 +168,37 @@ impl BiLinOp<f64> for GpuMultigrid {
 }
 impl Precond<f64> for GpuMultigrid {}
 impl BiPrecond<f64> for GpuMultigrid {}
+
+/// GPU `Composite` (src/preconditioners/composite.rs:11-100): symmetric multiplicative combination of
+/// multigrids around one operator.  Components are kept alive by the `Arc`s held here.
+#[derive(Debug)]
+pub struct GpuComposite { h: *mut ffi::famg_composite, n: usize, components: Vec<Arc<GpuMultigrid>> }
+unsafe impl Send for GpuComposite {}
+unsafe impl Sync for GpuComposite {}
+impl GpuComposite {
+    pub fn new(mat: &GpuSpmmOp, first_component: Arc<GpuMultigrid>) -> Self {           // composite.rs:48-56
+        let mut h = std::ptr::null_mut();
+        check(unsafe { ffi::famg_composite_create(mat.raw(), &mut h) });
+        let mut c = Self { h, n: mat.nrows, components: Vec::new() };
+        c.push(first_component);
+        c
+    }
+    pub fn push(&mut self, component: Arc<GpuMultigrid>) {                                // composite.rs:85-87
+        check(unsafe { ffi::famg_composite_push(self.h, ffi::FAMG_PC_MG, component.raw() as *mut _) });
+        self.components.push(component);
+    }
+    pub fn components(&self) -> &Vec<Arc<GpuMultigrid>> { &self.components }
+    pub(crate) fn raw(&self) -> *mut ffi::famg_composite { self.h }
+}
+impl Drop for GpuComposite { fn drop(&mut self) { unsafe { ffi::famg_composite_destroy(self.h); } } }
+
+/// Prolongator smoothing for `block_size > 1` (interpolation/mod.rs:963-1028): returns the device CSR of
+/// `P - 0.66 D_b^-1 A P`; download with `famg_csr_download` into `SparseRowMat::new(..)`.
+pub fn block_jacobi(mat: &GpuSpmmOp, block_size: usize, p: &GpuSpmmOp) -> *mut ffi::famg_csr {
+    let mut out = std::ptr::null_mut();
+    check(unsafe { ffi::famg_block_jacobi(mat.raw(), block_size as i64, p.raw(), &mut out) });
+    out
+}
 
 /// Device-resident PCG: the whole `conjugate_gradient(..)` call of utils.rs:600-609 in one FFI
 /// call, so vectors cross PCIe once per solve instead of twice per operator apply.
