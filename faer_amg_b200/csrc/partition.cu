@@ -304,18 +304,38 @@ struct Partitioner {
         return delta_degree + agg_pen * delta_size;
     }
 
-    // modularity.rs:437-510
+    // modularity.rs:437-510.  The reference recomputes every node's best move in every pass; the result of
+    // that computation for node i depends only on the aggregates of i and of its neighbours and on the sizes
+    // of those aggregates, so after a pass only the members of aggregates whose size changed, and the nodes
+    // that list such a member as a neighbour, are recomputed -- the same swaps, pass for pass (the candidate
+    // count falls from ~n/4 to a handful within ~50 passes on grid problems).
     void improve_partition() {
         struct Swap { int64_t node, agg; double gain; };
         const int64_t n = nnodes();
+        // reverse adjacency of the (directed) base graph: who lists node j as a neighbour
+        std::vector<int64_t> in_ptr((size_t)n + 1, 0), in_idx;
+        for (int64_t i = 0; i < n; ++i)
+            for (const Edge &e : (*base)[(size_t)i]) ++in_ptr[(size_t)e.first + 1];
+        for (int64_t i = 0; i < n; ++i) in_ptr[(size_t)i + 1] += in_ptr[(size_t)i];
+        in_idx.resize((size_t)in_ptr[(size_t)n]);
+        {
+            std::vector<int64_t> fill(in_ptr.begin(), in_ptr.end() - 1);
+            for (int64_t i = 0; i < n; ++i)
+                for (const Edge &e : (*base)[(size_t)i]) in_idx[(size_t)fill[(size_t)e.first]++] = i;
+        }
         std::vector<Swap> best((size_t)n);
         std::vector<Swap> swaps;
+        std::vector<int64_t> todo((size_t)n), changed_aggs;
+        for (int64_t i = 0; i < n; ++i) todo[(size_t)i] = i;
+        std::vector<char> dirty((size_t)n, 0);
         for (int64_t pass = 0; pass < max_iters; ++pass) {
+            const int64_t ntodo = (int64_t)todo.size();
 #pragma omp parallel
             {
                 std::vector<int64_t> cand;
-#pragma omp for schedule(dynamic, 1024)
-                for (int64_t i = 0; i < n; ++i) {
+#pragma omp for schedule(dynamic, 256)
+                for (int64_t t = 0; t < ntodo; ++t) {
+                    const int64_t i = todo[(size_t)t];
                     best[(size_t)i] = {i, -1, 0.0};
                     const int64_t agg_i = node_to_agg[(size_t)i];
                     if (agg_sizes[(size_t)agg_i] == 1) continue;  // sole member cannot leave
@@ -336,8 +356,11 @@ struct Partitioner {
             for (int64_t i = 0; i < n; ++i)
                 if (best[(size_t)i].agg >= 0) swaps.push_back(best[(size_t)i]);
             if (swaps.empty()) break;
+            static const bool trace = getenv("FAMG_PARTITION_TRACE") != nullptr;
+            if (trace) fprintf(stderr, "improve_partition pass %lld: %zu candidate swaps, %lld nodes re-evaluated\n", (long long)pass, swaps.size(), (long long)ntodo);
             std::stable_sort(swaps.begin(), swaps.end(), [](const Swap &a, const Swap &b) { return a.gain > b.gain; });  // TIE-BREAK 5
             std::vector<char> alive_nodes((size_t)n, 1), alive_aggs((size_t)naggs(), 1);
+            changed_aggs.clear();
             for (const Swap &s : swaps) {
                 const int64_t old_agg = node_to_agg[(size_t)s.node];
                 if (!(alive_nodes[(size_t)s.node] && alive_aggs[(size_t)s.agg] && alive_aggs[(size_t)old_agg])) continue;
@@ -348,6 +371,8 @@ struct Partitioner {
                 src.erase(std::lower_bound(src.begin(), src.end(), s.node));
                 auto &dst = agg_to_node[(size_t)s.agg];
                 dst.insert(std::lower_bound(dst.begin(), dst.end(), s.node), s.node);
+                changed_aggs.push_back(old_agg);
+                changed_aggs.push_back(s.agg);
                 alive_aggs[(size_t)s.agg] = alive_aggs[(size_t)old_agg] = 0;
                 alive_nodes[(size_t)s.node] = 0;
                 for (const Edge &e : (*base)[(size_t)s.node]) {
@@ -355,6 +380,17 @@ struct Partitioner {
                     alive_aggs[(size_t)node_to_agg[(size_t)e.first]] = 0;
                 }
             }
+            // nodes whose best move may have changed: members of the resized aggregates (the moved nodes are
+            // among them) and everyone who lists such a member as a neighbour
+            todo.clear();
+            auto mark = [&](int64_t i) { if (!dirty[(size_t)i]) { dirty[(size_t)i] = 1; todo.push_back(i); } };
+            for (int64_t a : changed_aggs)
+                for (int64_t m : agg_to_node[(size_t)a]) {
+                    mark(m);
+                    for (int64_t q = in_ptr[(size_t)m]; q < in_ptr[(size_t)m + 1]; ++q) mark(in_idx[(size_t)q]);
+                }
+            std::sort(todo.begin(), todo.end());
+            for (int64_t i : todo) dirty[(size_t)i] = 0;
         }
     }
 };
