@@ -74,3 +74,30 @@ def test_cpp_mirror_links_and_fails_loudly_without_gpu():
     else:
         assert out.returncode == 3 and "no CPU fallback" in out.stdout
     assert "partitioner ok" in out.stdout  # the host-only partitioner runs with or without a device
+
+
+def test_argument_validation_without_a_device():
+    """Entry points added for the 8f rows reject bad arguments before touching CUDA (status codes, no crash)."""
+    import ctypes as C
+    from faer_amg_b200 import _ffi
+    from faer_amg_b200.partitioners import StrengthGraph
+    L = _ffi.lib()
+    out = C.c_void_p()
+    assert L.famg_thin_q_dev(None) == _ffi.ERR_INVALID
+    assert L.famg_composite_create(None, C.byref(out)) == _ffi.ERR_INVALID
+    assert L.famg_composite_push(None, 2, None) == _ffi.ERR_INVALID
+    assert L.famg_block_jacobi(None, 2, None, C.byref(out)) == _ffi.ERR_INVALID
+    assert L.famg_smooth_p(None, None, None, C.byref(out)) == _ffi.ERR_INVALID
+    assert L.famg_smooth_vector_pc_dev(None, 1, None, 3, None, None) == _ffi.ERR_INVALID
+    assert L.famg_smoother_block_vector(None, 2, 0, None, None, C.byref(out)) == _ffi.ERR_INVALID
+    assert b"bad argument" in L.famg_last_error() or b"null" in L.famg_last_error()
+    coarse = (C.c_int64 * 3)()
+    assert L.famg_geometric_partition(0, 4, 4, 2, 2, 2, None, None, coarse) == _ffi.ERR_INVALID
+    assert L.famg_geometric_partition(5, 4, 3, 2, 2, 2, None, None, coarse) == _ffi.OK and list(coarse) == [2, 2, 1]
+    g = StrengthGraph.from_csr([0, 1, 2, 3], [1, 2, 0], [1.0, 1.0, 1.0])
+    assert L.famg_graph_block_reduce(g._h, 0) == _ffi.ERR_INVALID
+    assert L.famg_graph_block_reduce(g._h, 2) == _ffi.ERR_INVALID  # 3 nodes are not a multiple of 2
+    assert L.famg_graph_block_reduce(g._h, 1) == _ffi.OK and g.dims() == (3, 3)
+    empty = StrengthGraph.from_csr([0], [], [])
+    naggs = C.c_int64(-1)
+    assert L.famg_partition_modularity(empty._h, 8.0, 1.0, 10, (C.c_uint64 * 1)(), C.byref(naggs)) == _ffi.OK and naggs.value == 0
