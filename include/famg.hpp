@@ -216,6 +216,25 @@ struct PartitionerConfig {
     }
 };
 
+// interpolation/mod.rs block_jacobi (:963-1028) and smooth_p (:1030-1040) for block_size > 1
+inline std::shared_ptr<SparseRowMat> block_jacobi(const SparseRowMat &mat, int64_t block_size, const SparseRowMat &p) {
+    famg_csr *out = nullptr;
+    check(famg_block_jacobi(mat.raw(), block_size, p.raw(), &out));
+    return std::make_shared<SparseRowMat>(out);
+}
+inline std::shared_ptr<SparseRowMat> smooth_p(const SparseRowMat &mat, const SparseRowMat &m_inv, const SparseRowMat &p) {
+    famg_csr *out = nullptr;
+    check(famg_smooth_p(mat.raw(), m_inv.raw(), p.raw(), &out));
+    return std::make_shared<SparseRowMat>(out);
+}
+
+// block_smoothers.rs BlockSmoother::new (:88-123); vdim > 1 uses diagonally_compensate_vector (:326-400)
+inline std::shared_ptr<Smoother> BlockSmoother(const SparseRowMat &mat, int64_t vdim, const Partition &partition) {
+    famg_smoother *s = nullptr;
+    check(famg_smoother_block_vector(mat.raw(), vdim, partition.naggs(), partition.agg_ptr.data(), partition.agg_nodes.data(), &s));
+    return std::make_shared<Smoother>(s);
+}
+
 // adaptivity.rs ErrorPropogator (:168-198) and smooth_vector (:307-390), device-resident.
 struct ErrorPropogator {
     const SparseRowMat &op;
@@ -228,6 +247,28 @@ inline std::vector<double> smooth_vector(const SparseRowMat &mat, const Smoother
     check(famg_smooth_vector_dev(mat.raw(), pc.raw(), iterations, x.raw(), cfs.data()));
     return cfs;
 }
+
+// preconditioners/composite.rs Composite (:11-100): symmetric multiplicative combination of multigrids around
+// one operator; components are kept alive by the shared_ptrs held here.
+class Composite {
+public:
+    Composite(const SparseRowMat &mat, std::shared_ptr<Multigrid> first_component) {
+        check(famg_composite_create(mat.raw(), &h_));
+        push(std::move(first_component));
+    }
+    ~Composite() { famg_composite_destroy(h_); }
+    Composite(const Composite &) = delete;
+    void push(std::shared_ptr<Multigrid> component) {  // composite.rs:85-87
+        check(famg_composite_push(h_, FAMG_PC_MG, component->raw()));
+        components_.push_back(std::move(component));
+    }
+    const std::vector<std::shared_ptr<Multigrid>> &components() const { return components_; }
+    void apply(DeviceMat &out, const DeviceMat &rhs) const { check(famg_composite_apply_dev(h_, out.raw(), rhs.raw())); }
+    famg_composite *raw() const { return h_; }
+private:
+    famg_composite *h_ = nullptr;
+    std::vector<std::shared_ptr<Multigrid>> components_;
+};
 
 // interpolation/mod.rs GalerkinCoarse (:34-40)
 struct GalerkinCoarse {

@@ -68,6 +68,18 @@ int main() {
         std::vector<double> b3((size_t)rows, 1.0), x3((size_t)rows, 0.0);
         famg::CgParams p3; p3.rel_tolerance = 1e-8;
         famg_cg_info i3 = famg::conjugate_gradient(x3.data(), *mg3, *a3, b3.data(), p3);
+        {   // Composite of the same multigrid twice (composite.rs:66-83) as a PCG preconditioner: fewer iterations
+            std::shared_ptr<famg::Multigrid> shared_mg(std::move(mg3));
+            famg::Composite comp(*a3, shared_mg);
+            comp.push(shared_mg);
+            std::vector<double> xc((size_t)rows, 0.0);
+            famg_cg_info ic{};
+            famg::check(famg_pcg_solve(a3->raw(), FAMG_PC_COMPOSITE, comp.raw(), xc.data(), b3.data(), 1e-8, 0.0, 1000, 1, &ic));
+            double diff = 0.0, nrm = 0.0;
+            for (size_t i = 0; i < xc.size(); ++i) { diff += (xc[i] - x3[i]) * (xc[i] - x3[i]); nrm += x3[i] * x3[i]; }
+            if (!(ic.iter_count <= i3.iter_count) || !(std::sqrt(diff) <= 1e-4 * std::sqrt(nrm))) return 1;  // E^3 instead of E per iteration
+            std::printf("composite ok: %lld PCG iterations (single multigrid: %lld)\n", (long long)ic.iter_count, (long long)i3.iter_count);
+        }
         std::printf("mirror ok: 32^3 hierarchy %zu levels, op complexity %.3f, %lld PCG iterations, rel residual %.2e\n", h.levels(),
                     h.op_complexity(), (long long)i3.iter_count, i3.rel_residual);
         // the oracle's count for this case is 15 (tests/golden/oracle_golden.json g7_32_l1)
