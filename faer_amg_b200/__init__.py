@@ -26,5 +26,6 @@ from .adaptivity import (AdaptiveConfig, ErrorPropogator, create_weights, find_n
                          smooth_vector_dev)
 from . import adaptivity  # noqa: F401
 from . import gallery  # noqa: F401
+from .utils import approx_convergence_factor, mats_are_equal, symmetry_test  # noqa: F401
 
 __version__ = "0.1.0"

@@ -106,3 +106,30 @@ def test_bench_reference_arm_runs_on_cpu():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["value"] > 0
     assert line["config"]["grid"] == [16, 16, 16]
+
+
+def test_utils_convergence_factor_and_symmetry_test_logic():
+    """utils.rs:691-736 / multigrid.rs:520-580 restated over the LinOp::apply surface: checked here with
+    numpy operators (no device): ||E||_A of a Jacobi iteration equals the spectral radius of I - D^-1 A."""
+    from faer_amg_b200.utils import approx_convergence_factor, symmetry_test
+
+    a = O.gen_g1(33).to_scipy().toarray()
+    n = a.shape[0]
+    d = 0.66 / np.diag(a)
+
+    class Op:
+        nrows = n
+
+        def __init__(self, m):
+            self.m = m
+
+        def apply(self, x):
+            return self.m @ x
+
+    cf = approx_convergence_factor(Op(a), Op(np.diag(d)), iterations=400, test_vecs=3, seed=1)
+    rho = np.max(np.abs(np.linalg.eigvals(np.eye(n) - np.diag(d) @ a)))
+    assert abs(cf - rho) < 1e-3 * rho
+    err, rel = symmetry_test(Op(np.linalg.inv(a)), test_dim=4, seed=2)
+    assert err < 1e-9
+    ns = a.copy(); ns[0, 5] += 1.0
+    assert symmetry_test(Op(ns), test_dim=4, seed=2)[0] > 1e-3
