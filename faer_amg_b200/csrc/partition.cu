@@ -31,6 +31,7 @@
 //                pops a BinaryHeap keyed by neighbour id only; equal ids are summed here in ascending
 //                (member of the aggregate, position in its list) order
 #include <cmath>
+#include <parallel/algorithm>  // __gnu_parallel::stable_sort: a stable sort has one result, so threads do not change it
 #include <queue>
 
 #include "common.cuh"
@@ -184,10 +185,21 @@ struct Partitioner {
 
     struct Triplet { int64_t i, j; double w; };
 
-    // modularity.rs:305-337
+    // modularity.rs:305-337 (same order: i ascending, list order; generated by all cores)
     void modularity_triplets(std::vector<Triplet> &out) const {
-        out.clear();
-        for (int64_t i = 0; i < (int64_t)strength.size(); ++i)
+        const int64_t nv = (int64_t)strength.size();
+        std::vector<int64_t> start((size_t)nv + 1, 0);
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < nv; ++i) {
+            int64_t c = 0;
+            for (const Edge &e : strength[(size_t)i]) c += i > e.first;
+            start[(size_t)i + 1] = c;
+        }
+        for (int64_t i = 0; i < nv; ++i) start[(size_t)i + 1] += start[(size_t)i];
+        out.resize((size_t)start[(size_t)nv]);
+#pragma omp parallel for schedule(dynamic, 1024)
+        for (int64_t i = 0; i < nv; ++i) {
+            int64_t t = start[(size_t)i];
             for (const Edge &e : strength[(size_t)i]) {
                 if (!(i > e.first)) continue;
                 const int64_t j = e.first;
@@ -197,8 +209,9 @@ struct Partitioner {
                 const double square_diff = std::pow(new_weight - cf, 2.0);
                 if (new_weight > cf) w -= agg_pen * square_diff;
                 else w += agg_pen * square_diff;
-                out.push_back({i, j, w});
+                out[(size_t)t++] = {i, j, w};
             }
+        }
     }
 
     // modularity.rs:339-383
@@ -211,7 +224,7 @@ struct Partitioner {
         std::vector<Triplet> wants;
         modularity_triplets(wants);
         if (wants.empty()) return;
-        std::stable_sort(wants.begin(), wants.end(), [](const Triplet &a, const Triplet &b) { return a.w < b.w; });  // TIE-BREAK 3
+        __gnu_parallel::stable_sort(wants.begin(), wants.end(), [](const Triplet &a, const Triplet &b) { return a.w < b.w; });  // TIE-BREAK 3
         std::vector<char> alive((size_t)vertex_count, 1);
         while (!wants.empty()) {
             const Triplet tr = wants.back();
@@ -358,7 +371,7 @@ struct Partitioner {
             if (swaps.empty()) break;
             static const bool trace = getenv("FAMG_PARTITION_TRACE") != nullptr;
             if (trace) fprintf(stderr, "improve_partition pass %lld: %zu candidate swaps, %lld nodes re-evaluated\n", (long long)pass, swaps.size(), (long long)ntodo);
-            std::stable_sort(swaps.begin(), swaps.end(), [](const Swap &a, const Swap &b) { return a.gain > b.gain; });  // TIE-BREAK 5
+            __gnu_parallel::stable_sort(swaps.begin(), swaps.end(), [](const Swap &a, const Swap &b) { return a.gain > b.gain; });  // TIE-BREAK 5
             std::vector<char> alive_nodes((size_t)n, 1), alive_aggs((size_t)naggs(), 1);
             changed_aggs.clear();
             for (const Swap &s : swaps) {
