@@ -1,22 +1,30 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the faer-amg hot path on B200.
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--grid 256]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--grid 256] [--stencil 7|27] [--weak]
 
 Workload (BASELINE.json north_star / configs[3]): PCG + AMG V(1,1)-cycle solve of the 3-D 7-point
 Poisson problem on an n^3 grid (default 256^3, 16.8 M unknowns) to rel. residual 1e-8, b = 1, zero
 initial guess; smoothed-aggregation hierarchy over 2x2x2 geometric aggregates built on the GPU
 (SpGEMM RAP), L1-Jacobi smoother, exact coarsest solve.  One *step* = one full solve.  The same
-problem is solved at every N ("strong" scaling); at N > 1 the fine levels are row-partitioned with
-NCCL halo exchange.
+problem is solved at every N ("strong" scaling); `--weak` keeps 256^3 rows per GPU instead (256^3,
+256^2x512, 256x512^2, 512^3 at N = 1, 2, 4, 8: BASELINE configs[4]); `--stencil 27 --grid 192` is
+configs[2].  At N > 1 every rank generates only its z-slab of the operator and builds only its rows
+of every level (csrc/dist_setup.cu); the fine levels exchange halos over peer memory (CUDA IPC over
+NVLink; NCCL bootstraps, carries the setup exchanges and is the fallback), small coarse levels are
+gathered and run replicated.
 
 metric  = PCG+AMG solve time (ms, lower is better), device-resident vectors          -> "value"
 e2e     = the same solve through the host-pointer C ABI call (pinned host b and x,
           H2D + D2H inside the timed region)                                         -> "e2e"
 roofline= the dominant kernel (fused diagonal smoother sweep on the fine level; SpMV and residual
-          reported next to it): algorithmic bytes / CUDA-event time vs the measured HBM copy peak
+          next to it), every level's kernels and the whole cycle: algorithmic bytes / CUDA-event time vs
+          the measured HBM copy peak; roofline_rap = the Galerkin products of every level
+dist_parity (N > 1) = distributed SpMV / V-cycle / hierarchy slabs compared bit for bit, and PCG
+          iteration counts, against the single-GPU path computed redundantly on every rank -- asserted
+          before the line is printed
 cpu_baseline / --impl reference = the CPU restatement of the reference (oracle/, "port"; the Rust
-          crate cannot be built here) on the box's host cores.
+          crate cannot be built here) on the box's host cores: full solves, nothing extrapolated.
 """
 import argparse
 import json
@@ -32,6 +40,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 REL_TOL = 1e-8
+WEAK_DIMS = {1: (256, 256, 256), 2: (256, 256, 512), 4: (256, 512, 512), 8: (512, 512, 512)}
 
 
 def peaks():
@@ -87,25 +96,42 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def golden_iters(n):
+def golden(args):
+    """Known answer of the CPU oracle for this workload (tests/golden/oracle_golden.json), if one is committed."""
     try:
         g = json.load(open(os.path.join(ROOT, "tests", "golden", "oracle_golden.json")))["amg"]
-        return int(g[f"g7_{n}_l1"]["iters"]["1e-08"]["iters"])
+        d = args.dims
+        name = f"g{args.stencil}_{d[0]}" if d[0] == d[1] == d[2] else f"g{args.stencil}_{d[0]}x{d[1]}x{d[2]}"
+        return g[f"{name}_l1"]
     except Exception:
         return None
 
 
+def workload_config(args):
+    name = "7-point Poisson" if args.stencil == 7 else "27-point anisotropic diffusion (eps_z=1e-2)"
+    d = args.dims
+    grid = f"{d[0]}^3" if d[0] == d[1] == d[2] else f"{d[0]}x{d[1]}x{d[2]}"
+    which = ("BASELINE configs[4], weak scaling: 256^3 rows per GPU" if args.weak else
+             "BASELINE configs[2]" if args.stencil == 27 else
+             "BASELINE configs[4], strong" if d == (512, 512, 512) else
+             "BASELINE configs[3]; configs[1] = 128^3 is a parity-test case")
+    return {"workload": f"3D {name} {grid} f64, PCG + smoothed-aggregation AMG V(1,1), L1-Jacobi smoother, "
+                        f"rel_tol {REL_TOL:g}, b=1, zero guess ({which})",
+            "grid": list(d), "rows": int(np.prod(d)), "rel_tol": REL_TOL, "l2": "inputs larger than L2 (no flush needed)",
+            "partition": f"{args.gpus} z-slab(s)"}
+
+
 # ------------------------------------------------------------------------------ CPU arm
-def cpu_sample(n, sample_iters, threads, hierarchy=None, verbose=False):
-    """Times `sample_iters` PCG+AMG iterations of the same workload with the oracle port:
-    ParSpmmOp-tiled operator applies on `threads` OpenMP threads, serial CSR R/P and vector ops,
-    unfused smooth/cycle with per-call allocation -- the reference's CPU path."""
+def cpu_solver(args, threads, hierarchy=None):
+    """The reference's CPU path restated (oracle/): ParSpmmOp-tiled operator applies on `threads` OpenMP threads,
+    serial CSR R/P and vector ops, unfused smooth/cycle with per-call allocation.  Returns a
+    callable running ONE full PCG+AMG solve of the workload and the setup seconds."""
     import oracle as O
     t0 = time.time()
     if hierarchy is None:
-        a = O.gen_g7(n)
+        a = (O.gen_g7 if args.stencil == 7 else O.gen_g27)(*args.dims)
         nn = np.full((a.nrows, 1), 1.0 / np.sqrt(a.nrows))
-        hierarchy = O.build_hierarchy(a, nn, (n, n, n))
+        hierarchy = O.build_hierarchy(a, nn, args.dims)
     a = hierarchy.operators[0]
     mg = O.multigrid_from_hierarchy(hierarchy, "l1", nthreads=threads)
     par = O.ParSpmmOp(a, threads) if threads > 1 else None
@@ -114,15 +140,9 @@ def cpu_sample(n, sample_iters, threads, hierarchy=None, verbose=False):
 
     def run():
         t = time.perf_counter()
-        _, info = O.pcg(a, b, mg, rel_tol=REL_TOL, abs_tol=0.0, max_iters=sample_iters, par=par)
+        _, info = O.pcg(a, b, mg, rel_tol=REL_TOL, abs_tol=0.0, max_iters=1000, par=par)
         return time.perf_counter() - t, info
-    return run, setup_s, hierarchy
-
-
-def scale_sample(seconds, sample_iters, full_iters):
-    """A capped run does 1 + s preconditioner applies and s operator applies; a full solve of I
-    iterations does I of each.  Per-iteration cost = t / (s + 1) (conservative for the CPU)."""
-    return seconds / (sample_iters + 1) * full_iters
+    return run, setup_s
 
 
 def run_reference(args):
@@ -135,39 +155,117 @@ def run_reference(args):
     os.environ["OMP_NUM_THREADS"] = str(cores)
     import oracle as O
     threads = O.num_threads()
-    full = golden_iters(args.n) or 16
-    s = args.sample_iters
-    run, setup_s, _ = cpu_sample(args.n, s, threads)
+    run, setup_s = cpu_solver(args, threads)
+    infos = []
     for _ in range(args.warmup):
         run()
-    times = [run()[0] for _ in range(args.steps)]
-    ms = scale_sample(float(np.mean(times)), s, full) * 1e3
-    sample = (f"{s} of {full} PCG iterations (1+{s} V-cycles, {s} operator applies) of the same {args.n}^3 solve per step, "
-              f"scaled x{full}/{s + 1}; hierarchy built by the oracle in {setup_s:.0f} s (untimed)")
+    times = []
+    for _ in range(args.steps):
+        t, info = run()
+        times.append(t); infos.append(info)
+    ms = float(np.mean(times)) * 1e3
+    sample = (f"full PCG+AMG solve ({infos[0].iters} iterations to rel {REL_TOL:g}) of the same workload per step, nothing scaled; "
+              f"hierarchy built by the oracle in {setup_s:.0f} s (untimed)")
     line = {"impl": "reference", "metric": "pcg_amg_solve_time", "value": ms, "unit": "ms", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args),
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False,
+            "scaling": "weak" if args.weak else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args), "pcg_iterations": int(infos[0].iters),
             "cpu_baseline": {"value": ms, "unit": "ms", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args):
-    name = "7-point Poisson" if args.stencil == 7 else "27-point anisotropic diffusion (eps_z=1e-2)"
-    return {"workload": f"3D {name} {args.n}^3 f64, PCG + smoothed-aggregation AMG V(1,1), L1-Jacobi smoother, "
-                        f"rel_tol {REL_TOL:g}, b=1, zero guess (BASELINE configs[3]; configs[1] = 128^3 is a parity-test case)",
-            "grid": [args.n] * 3, "rows": args.n ** 3, "rel_tol": REL_TOL, "l2": "inputs larger than L2 (no flush needed)",
-            "partition": f"{args.gpus} z-slab(s)"}
-
-
 # ------------------------------------------------------------------------------ GPU arm
+def ev_time(stream, fn, reps=1):
+    """milliseconds per call of fn, CUDA events on the launching stream."""
+    import torch
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        fn()
+    e1.record(stream)
+    e1.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def csr_bytes(m):
+    return 12.0 * m.nnz + 4.0 * (m.nrows + 1)
+
+
+def level_rooflines(F, ctx, stream, h, mg, peak):
+    """Every level's SpMV-family kernels (CUDA events, 20 launches each) and the whole V-cycle against the HBM peak."""
+    gbs = lambda b, ms: b / (ms * 1e-3) / 1e9  # noqa: E731
+    levels = []
+    for l in range(h.levels()):
+        a = h.get_mat_ref(l)
+        n, nnz = a.nrows, a.nnz
+        row = {"level": l, "rows": n, "nnz": nnz, "threads_per_row": a.plan()["threads_per_row"]}
+        if l + 1 < h.levels():
+            for name, which, extra in (("spmv", 0, 16.0 * n), ("residual", 1, 24.0 * n), ("smooth", 2, 32.0 * n)):
+                b = csr_bytes(a) + extra
+                ms = a.time_kernel(which, 20, 3)
+                row[name] = {"bytes": b, "ms": ms, "GB/s": gbs(b, ms), "frac": gbs(b, ms) / peak}
+            r, p = h.get_restriction(l), h.get_interpolation(l)
+            b = csr_bytes(r) + 8.0 * (r.nrows + r.ncols)
+            ms = r.time_kernel(0, 20, 3)
+            row["restrict"] = {"bytes": b, "ms": ms, "GB/s": gbs(b, ms), "frac": gbs(b, ms) / peak}
+            b = csr_bytes(p) + 8.0 * (p.nrows + p.ncols) + 8.0 * p.nrows
+            ms = p.time_kernel(3, 20, 3)
+            row["prolong_add"] = {"bytes": b, "ms": ms, "GB/s": gbs(b, ms), "frac": gbs(b, ms) / peak}
+        levels.append(row)
+    n0 = h.get_mat_ref(0).nrows
+    z, r = F.DeviceMat(ctx, n0, 1), F.DeviceMat(ctx, n0, 1)
+    r.fill(1.0)
+    for _ in range(3):
+        mg.apply_dev(z, r)
+    cyc_ms = ev_time(stream, lambda: mg.apply_dev(z, r), 20)
+    cb = mg.cycle_bytes(1)
+    return levels, {"cycle_ms": cyc_ms, "cycle_algorithmic_bytes": cb, "cycle_GB/s": gbs(cb, cyc_ms), "cycle_frac": gbs(cb, cyc_ms) / peak}
+
+
+def rap_rooflines(F, ctx, stream, h, peak):
+    """The sparse products of smoothed_aggregation (interpolation/mod.rs:814/938, 824-827, 828) level by level, timed
+    with CUDA events: S = (I - w D^-1 A) P0, R = P^T, AP = A P, A_c = R AP.  B_rap = compulsory bytes:
+    csr(A)+csr(P)+csr(AP) + csr(R)+csr(AP)+csr(A_c); the smoothing product and the transpose are listed next to it."""
+    from faer_amg_b200.interpolation import smooth_interpolation, tentative_prolongator
+    gbs = lambda b, ms: b / (ms * 1e-3) / 1e9  # noqa: E731
+    out = []
+    tot_b = tot_ms = 0.0
+    for l in range(h.levels() - 1):
+        a = h.get_mat_ref(l)
+        p0, _ = tentative_prolongator(ctx, a.nrows, h.get_partition(l), h.get_near_null(l), 1, 1)
+        ctx.sync()
+        box = {}
+
+        def timed(name, fn):
+            t = ev_time(stream, lambda: box.__setitem__(name, fn()))
+            return t
+        t_s = timed("p", lambda: smooth_interpolation(a, p0))
+        t_t = timed("r", lambda: box["p"].transpose())
+        t_ap = timed("ap", lambda: a @ box["p"])
+        t_ac = timed("ac", lambda: box["r"] @ box["ap"])
+        p, r, ap, ac = box["p"], box["r"], box["ap"], box["ac"]
+        b_rap = csr_bytes(a) + csr_bytes(p) + csr_bytes(ap) + csr_bytes(r) + csr_bytes(ap) + csr_bytes(ac)
+        b_s = csr_bytes(a) + csr_bytes(p0) + csr_bytes(p)
+        b_t = csr_bytes(p) + csr_bytes(r)
+        out.append({"level": l, "rows": a.nrows, "nnz_A": a.nnz, "nnz_P": p.nnz, "nnz_AP": ap.nnz, "nnz_Ac": ac.nnz,
+                    "rap": {"bytes": b_rap, "ms": t_ap + t_ac, "GB/s": gbs(b_rap, t_ap + t_ac), "frac": gbs(b_rap, t_ap + t_ac) / peak,
+                            "ms_AP": t_ap, "ms_R_AP": t_ac},
+                    "smooth_p": {"bytes": b_s, "ms": t_s, "GB/s": gbs(b_s, t_s)}, "transpose": {"bytes": b_t, "ms": t_t, "GB/s": gbs(b_t, t_t)}})
+        tot_b += b_rap + b_s + b_t
+        tot_ms += t_ap + t_ac + t_s + t_t
+        del box, p, r, ap, ac, p0
+    return {"levels": out, "total_bytes": tot_b, "total_ms": tot_ms, "GB/s": gbs(tot_b, tot_ms), "frac": gbs(tot_b, tot_ms) / peak,
+            "timing": "CUDA events around each product (first call after the two timed hierarchy builds: kernels loaded)"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
     import faer_amg_b200 as F
-    from faer_amg_b200.distributed import Comm, DistMultigrid, level_row_splits
+    from faer_amg_b200.distributed import (Comm, DistGeometricPartitioner, DistHierarchy, DistMat, DistMultigrid,
+                                           fine_plane_splits)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -177,37 +275,117 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    n = args.n
+    dims = args.dims
+    rows = int(np.prod(dims))
+    block = tuple(int(v) for v in args.block.split(","))
     ctx = F.Context.default(local_rank)
     stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
+    params = F.CgParams(0.0, REL_TOL, 1000)
+    comm = Comm.from_torch(ctx) if world > 1 else None
 
-    # ---- setup (untimed): operator + hierarchy on the device
-    t0 = time.perf_counter()
-    a = F.gallery.poisson7(ctx, n) if args.stencil == 7 else F.gallery.diffusion27(ctx, n)
-    ctx.sync()
-    t_gen = time.perf_counter() - t0
-    rows = a.nrows
-    nn = np.full((rows, 1), 1.0 / np.sqrt(rows))
-    def build_hierarchy():
+    def gen_global(d):
+        return F.gallery.poisson7(ctx, *d) if args.stencil == 7 else F.gallery.diffusion27(ctx, *d)
+
+    def build_global(a, d):
+        """single-GPU hierarchy + multigrid (Hierarchy::coarsen with the GPU SpGEMM RAP)"""
         t0 = time.perf_counter()
-        gp = F.GeometricPartitioner((n, n, n), tuple(int(v) for v in args.block.split(",")))
+        nn = np.full((a.nrows, 1), 1.0 / np.sqrt(a.nrows))
+        gp = F.GeometricPartitioner(d, block)
         h = F.HierarchyConfig(1000, F.AggregationConfig(1, 1, gp)).build(F.SparseMatOp(a), nn)
         mg = F.MultigridConfig(smoother="l1").build(h)
         ctx.sync()
-        return gp, h, mg, time.perf_counter() - t0
-    # first build pays CUDA's lazy module loading of every setup kernel; the second is steady state
-    gp, h, mg, t_setup_cold = build_hierarchy()
-    del h, mg
-    gp, h, mg, t_setup = build_hierarchy()
-    params = F.CgParams(0.0, REL_TOL, 1000)
+        return h, mg, time.perf_counter() - t0
 
-    if world > 1:
-        comm = Comm.from_torch(ctx)
-        splits = level_row_splits(gp.dims[: h.levels()], world)
-        dmg = DistMultigrid(comm, mg, splits, replicate_below=args.replicate_below)
-        nloc = dmg.nloc
-    else:
+    def build_dist(d):
+        """every rank: its z-slab of the operator, its rows of every level, the replicated tail"""
+        t0 = time.perf_counter()
+        n = int(np.prod(d))
+        rs = fine_plane_splits(d, world, block[2])
+        plane = d[0] * d[1]
+        gen = F.gallery.poisson7_slab if args.stencil == 7 else F.gallery.diffusion27_slab
+        slab = gen(ctx, d[0], d[1], d[2], int(rs[rank]) // plane, int(rs[rank + 1]) // plane)
+        ctx.sync()
+        t_gen = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        a0 = DistMat.from_slabs(comm, [slab], n)
+        nn = [np.full(int(rs[rank + 1] - rs[rank]), 1.0 / np.sqrt(n))]
+        dh = DistHierarchy(comm, a0, nn, DistGeometricPartitioner(d, block), coarsest_dim=1000, replicate_below=args.replicate_below)
+        dmg = DistMultigrid.from_hierarchy(comm, dh, smoother="l1")
+        ctx.sync()
+        return dh, dmg, t_gen, time.perf_counter() - t0
+
+    # ---- setup (untimed): operator + hierarchy on the device; the first build pays CUDA's lazy module
+    # loading of every setup kernel, the second is steady state
+    if world == 1:
+        t0 = time.perf_counter()
+        a = gen_global(dims)
+        ctx.sync()
+        t_gen = time.perf_counter() - t0
+        h, mg, t_setup_cold = build_global(a, dims)
+        del h, mg
+        h, mg, t_setup = build_global(a, dims)
         dmg, nloc = None, rows
+    else:
+        dh, dmg, t_gen, t_setup_cold = build_dist(dims)
+        del dh, dmg
+        dist.barrier()
+        dh, dmg, t_gen, t_setup = build_dist(dims)
+        nloc = dmg.nloc
+        ts = torch.tensor([t_gen, t_setup, t_setup_cold], device="cuda", dtype=torch.float64)
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        t_gen, t_setup, t_setup_cold = (float(v) for v in ts.tolist())
+
+    # ---- distributed parity, asserted before anything is reported (N > 1)
+    parity = None
+    if world > 1:
+        pd = dims if rows <= 256 ** 3 else (256, 256, 256)
+        if pd == dims:
+            pdh, pdmg = dh, dmg
+        else:
+            pdh, pdmg, _, _ = build_dist(pd)
+        ag = gen_global(pd)
+        gh, gmg, _ = build_global(ag, pd)
+        n = ag.nrows
+        r0, r1 = pdmg.row_begin, pdmg.row_end
+        xg = np.sin(0.37 * np.arange(n)) + 1e-3 * np.cos(0.011 * np.arange(n))
+        y = F.DeviceMat(ctx, r1 - r0, 1)
+        pdmg.spmv_dev(y, F.DeviceMat.from_host(ctx, xg[r0:r1]))
+        xd = F.DeviceMat.from_host(ctx, xg)
+        yg = F.DeviceMat(ctx, n, 1)
+        ag.apply_dev(yg, xd)
+        e_spmv = bool(np.array_equal(y.to_host().ravel(), yg.to_host().ravel()[r0:r1]))
+        pdmg.apply_dev(y, F.DeviceMat.from_host(ctx, xg[r0:r1]))
+        gmg.apply_dev(yg, xd)
+        e_cyc = bool(np.array_equal(y.to_host().ravel(), yg.to_host().ravel()[r0:r1]))
+
+        def rows_of(m, a0_, a1_):
+            rp, ci, v = m.to_host()
+            rp = rp.astype(np.int64)
+            return rp[a0_:a1_ + 1] - rp[a0_], ci[rp[a0_]:rp[a1_]], v[rp[a0_]:rp[a1_]]
+        e_h = pdh.levels() == gh.levels()
+        for l in range(1, pdh.n_dist):  # every distributed coarse operator: this rank's rows vs the undistributed build
+            rsl = pdh.A[l].row_split()
+            got = pdh.A[l].local(0, True).to_host()
+            want = rows_of(gh.get_mat_ref(l), int(rsl[rank]), int(rsl[rank + 1]))
+            e_h = e_h and all(np.array_equal(np.asarray(g_), np.asarray(w_)) for g_, w_ in zip((got[0].astype(np.int64), got[1], got[2]), want))
+        xs, bs = F.DeviceMat(ctx, n, 1), F.DeviceMat.from_host(ctx, np.ones(n))
+        i_single = F.conjugate_gradient_dev(xs, gmg, ag, bs, params)
+        xl, bl = F.DeviceMat(ctx, r1 - r0, 1), F.DeviceMat.from_host(ctx, np.ones(r1 - r0))
+        i_dist = pdmg.solve_dev(xl, bl, params)
+        e_x = float(np.max(np.abs(xl.to_host().ravel() - xs.to_host().ravel()[r0:r1])) / np.max(np.abs(xs.to_host())))
+        good = e_spmv and e_cyc and bool(e_h) and i_single.iter_count == i_dist.iter_count and e_x <= 1e-9
+        t = torch.tensor([1.0 if good else 0.0], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        parity = {"grid": list(pd), "spmv": "bit-exact" if e_spmv else "MISMATCH", "vcycle": "bit-exact" if e_cyc else "MISMATCH",
+                  "hierarchy_slabs": "bit-exact" if e_h else "MISMATCH", "pcg_iterations": {"single_gpu": i_single.iter_count, "distributed": i_dist.iter_count},
+                  "solution_rel_diff": e_x, "all_ranks": bool(t.item() == 1.0),
+                  "against": "the single-GPU hierarchy, cycle and PCG computed redundantly on every rank for this check (rank 0's view; all_ranks = min over ranks)"}
+        if t.item() != 1.0:
+            raise SystemExit(f"[rank {rank}] distributed parity FAILED: {json.dumps(parity)}")
+        del ag, gh, gmg, xs, bs, xl, bl, y, yg, xd
+        if pd != dims:
+            del pdh, pdmg
+
     B = F.DeviceMat.from_host(ctx, np.ones(nloc))
     X = F.DeviceMat(ctx, nloc, 1)
 
@@ -254,57 +432,91 @@ def run_ours(args):
         solve_host()
     ms_e2e, infos_h, _ = timed(solve_host, args.steps)
     iters = infos[0].iter_count
+    xsol = X.to_host().ravel()
+    xstat = np.asarray([float(np.dot(xsol, xsol)), float(xsol.sum())])
+    if world > 1:
+        t = torch.tensor(xstat, device="cuda", dtype=torch.float64)
+        dist.all_reduce(t)
+        xstat = t.cpu().numpy()
 
     line = None
     if rank == 0:
         peak, peak_src = peaks()
-        # ---- kernel roofline on the fine level (N = 1 view of the dominant kernel)
-        nnz = a.nnz
-        bytes_spmv = 12.0 * nnz + 4.0 * (rows + 1) + 16.0 * rows
-        bytes_resid = 12.0 * nnz + 4.0 * (rows + 1) + 24.0 * rows
-        bytes_smooth = 12.0 * nnz + 4.0 * (rows + 1) + 32.0 * rows
-        t_spmv = a.time_kernel(0, 50, 5)
-        t_resid = a.time_kernel(1, 50, 5)
-        t_smooth = a.time_kernel(2, 50, 5)
         gbs = lambda b, ms: b / (ms * 1e-3) / 1e9  # noqa: E731
-        traffic = None
+        # ---- kernel roofline on the fine level: the operator one GPU works on (its z-slab's worth of planes at N > 1)
+        if world == 1:
+            ar = a
+        else:
+            ar = (F.gallery.poisson7 if args.stencil == 7 else F.gallery.diffusion27)(ctx, dims[0], dims[1], max(dims[2] // world, 1))
+        rr, nnz = ar.nrows, ar.nnz
+        bytes_spmv = 12.0 * nnz + 4.0 * (rr + 1) + 16.0 * rr
+        bytes_resid = 12.0 * nnz + 4.0 * (rr + 1) + 24.0 * rr
+        bytes_smooth = 12.0 * nnz + 4.0 * (rr + 1) + 32.0 * rr
+        t_spmv = ar.time_kernel(0, 50, 5)
+        t_resid = ar.time_kernel(1, 50, 5)
+        t_smooth = ar.time_kernel(2, 50, 5)
+        traffic, traffic_src = None, None
         try:  # DRAM bytes per launch from the committed ncu --set full capture of this exact operator
-            if n == 256 and args.stencil == 7:
+            if dims == (256, 256, 256) and args.stencil == 7 and world == 1:
                 traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["smooth"]["traffic_bytes_per_launch"]
+                traffic_src = "profiles/r1_traffic.json (ncu --set full capture of this kernel on this operator; not measured in this run)"
         except Exception:
             pass
-        roofline = {"bound": "hbm", "kernel": "spmv_tma_kernel<TPR=1, EPI_SMOOTH> (fused x' = x + d.*(b - A x), fine level)",
+        tpr = ar.plan()["threads_per_row"]
+        roofline = {"bound": "hbm", "kernel": f"spmv_tma_kernel<TPR={tpr}, EPI_SMOOTH> (fused x' = x + d.*(b - A x), fine level"
+                                              + (f", one rank's {rr}-row share)" if world > 1 else ")"),
                     "achieved": gbs(bytes_smooth, t_smooth), "peak": peak, "unit": "GB/s",
                     "frac": gbs(bytes_smooth, t_smooth) / peak, "frac_of_nominal_8TBs": gbs(bytes_smooth, t_smooth) / 8000.0,
-                    "traffic": traffic, "peak_source": peak_src, "ms_per_launch": t_smooth, "algorithmic_bytes": bytes_smooth,
+                    "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "ms_per_launch": t_smooth,
+                    "algorithmic_bytes": bytes_smooth,
                     "spmv": {"GB/s": gbs(bytes_spmv, t_spmv), "ms": t_spmv, "frac": gbs(bytes_spmv, t_spmv) / peak},
-                    "residual": {"GB/s": gbs(bytes_resid, t_resid), "ms": t_resid, "frac": gbs(bytes_resid, t_resid) / peak},
-                    "cycle_algorithmic_bytes": mg.cycle_bytes(1)}
+                    "residual": {"GB/s": gbs(bytes_resid, t_resid), "ms": t_resid, "frac": gbs(bytes_resid, t_resid) / peak}}
+        roofline_rap = None
+        if world == 1:
+            levels, cyc = level_rooflines(F, ctx, stream, h, mg, peak)
+            roofline.update(cyc)
+            roofline["levels"] = levels
+            roofline["solve_share_of_cycle"] = cyc["cycle_ms"] * iters / ms_dev
+            roofline_rap = rap_rooflines(F, ctx, stream, h, peak)
+        g = golden(args)
+        hier = h if world == 1 else dh
         line = {"metric": "pcg_amg_solve_time", "value": ms_dev, "unit": "ms", "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": False, "scaling": "strong",
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": False, "scaling": "weak" if args.weak else "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args),
-                "pcg_iterations": iters, "rel_residual": infos[0].rel_residual, "levels": h.levels(),
-                "op_complexity": h.op_complexity(), "setup_ms": {"generate": t_gen * 1e3, "hierarchy_rap": t_setup * 1e3, "hierarchy_rap_first_call": t_setup_cold * 1e3},
+                "pcg_iterations": iters, "rel_residual": infos[0].rel_residual, "levels": hier.levels(),
+                "oracle_golden": None if g is None else {"pcg_iterations": g["iters"]["1e-08"]["iters"], "x_norm": g["iters"]["1e-08"]["x_norm"],
+                                                          "x_sum": g["iters"]["1e-08"]["x_sum"], "levels": g["levels"]},
+                "x_norm": float(np.sqrt(xstat[0])), "x_sum": float(xstat[1]),
+                "setup_ms": {"generate": t_gen * 1e3, "hierarchy_rap": t_setup * 1e3, "hierarchy_rap_first_call": t_setup_cold * 1e3,
+                             "what": "host wall clock, max over ranks; hierarchy_rap = second build (kernels loaded); at N > 1 every rank "
+                                     "builds only its row slabs (nothing global above the replicated tail)"},
                 "mdof_per_s": rows / (ms_dev * 1e-3) / 1e6,
-                "e2e": {"value": ms_e2e, "unit": "ms", "h2d_bytes_per_step": 8 * nloc, "d2h_bytes_per_step": 8 * nloc,
+                "e2e": {"value": ms_e2e, "unit": "ms", "h2d_bytes_per_step": 8 * nloc * world, "d2h_bytes_per_step": 8 * nloc * world,
                         "api": "famg_pcg_solve (host pointers, pinned)" if not dmg else "famg_dist_pcg_solve (host pointers, pinned)",
                         "pcg_iterations": infos_h[0].iter_count},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
-        # ---- CPU baseline on the host cores (bounded sample), rank 0, N = 1 only
+        if world == 1:
+            line["op_complexity"] = h.op_complexity()
+        else:
+            line["distributed_levels"] = dh.n_dist
+            line["halo"] = "peer-memory (CUDA IPC over NVLink) stores + flags; NCCL bootstrap / setup exchanges / fallback"
+        if roofline_rap is not None:
+            line["roofline_rap"] = roofline_rap
+        if parity is not None:
+            line["dist_parity"] = parity
+        if g is not None and iters != g["iters"]["1e-08"]["iters"]:
+            line["oracle_golden"]["MISMATCH"] = True
+        # ---- CPU baseline on the host cores: one full solve, rank 0, N = 1 only
         if world == 1 and not args.no_cpu:
             try:
                 import oracle as O
                 threads = O.num_threads()
-                full = iters
-                s = args.sample_iters
                 oh = download_hierarchy(h)
-                run, setup_s, _ = cpu_sample(n, s, threads, hierarchy=oh)
-                run()
-                t_cpu = float(np.mean([run()[0] for _ in range(2)]))
-                ms_cpu = scale_sample(t_cpu, s, full) * 1e3
-                line["cpu_baseline"] = {"value": ms_cpu, "unit": "ms", "cores": threads, "kind": "port",
-                                        "sample": f"{s} of {full} PCG iterations of the same solve (hierarchy downloaded from the GPU "
-                                                  f"build, bit-identical to the oracle's per tests), scaled x{full}/{s + 1}"}
+                run, setup_s = cpu_solver(args, threads, hierarchy=oh)
+                t_cpu, cinfo = run()
+                line["cpu_baseline"] = {"value": t_cpu * 1e3, "unit": "ms", "cores": threads, "kind": "port", "pcg_iterations": int(cinfo.iters),
+                                        "sample": "one full PCG+AMG solve of the same workload (hierarchy downloaded from the GPU build, "
+                                                  "bit-identical to the oracle's per tests); nothing scaled"}
             except Exception as exc:  # the baseline is a report, never a reason to lose the GPU line
                 line["cpu_baseline"] = {"error": repr(exc)}
         print(json.dumps(line), flush=True)
@@ -334,14 +546,24 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--grid", "--n", dest="n", type=int, default=256,
-                    help="grid points per dimension (use --grid under torchrun: its parser treats --n as an abbreviation)")
-    ap.add_argument("--sample-iters", type=int, default=2, help="PCG iterations per CPU sample")
+    ap.add_argument("--grid", "--n", dest="grid", default="256",
+                    help="grid points: N (cube) or NX,NY,NZ (use --grid under torchrun: its parser treats --n as an abbreviation)")
+    ap.add_argument("--weak", action="store_true", help="weak scaling: 256^3 rows per GPU (256^3, 256^2x512, 256x512^2, 512^3 at 1/2/4/8 GPUs)")
+    ap.add_argument("--sample-iters", type=int, default=0, help="ignored (the CPU legs run full solves)")
     ap.add_argument("--replicate-below", type=int, default=4096, help="rows per rank under which a level is replicated")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--stencil", type=int, default=7, choices=[7, 27], help="7-point Poisson (headline) or 27-point anisotropic diffusion")
     ap.add_argument("--block", default="2,2,2", help="geometric aggregate box")
     args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    if args.weak:
+        if world not in WEAK_DIMS:
+            raise SystemExit("--weak is defined for 1, 2, 4 and 8 GPUs")
+        args.dims = WEAK_DIMS[world]
+    else:
+        g = [int(v) for v in str(args.grid).split(",")]
+        args.dims = tuple(g * 3) if len(g) == 1 else tuple(g)
+    args.n = args.dims[0]
     if args.impl == "reference":
         run_reference(args)
     else:

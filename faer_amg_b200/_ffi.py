@@ -132,6 +132,21 @@ SIGNATURES = {
     "famg_dist_spmv_dev": [vp, vp, vp],
     "famg_dist_mg_apply_dev": [vp, vp, vp],
     "famg_time_kernel": [vp, cint, cint, cint, C.POINTER(C.c_float)],
+    "famg_gallery_g7_slab": [vp, i64, i64, i64, i64, i64, vpp],
+    "famg_gallery_g27_slab": [vp, i64, i64, i64, f64, f64, i64, i64, vpp],
+    "famg_comm_create_sim": [vp, cint, vpp],
+    "famg_comm_dims": [vp, C.POINTER(cint), C.POINTER(cint), C.POINTER(cint)],
+    "famg_comm_allgatherv_f64": [vp, C.POINTER(f64p), i64p, C.POINTER(f64p)],
+    "famg_dmat_create": [vp, vpp, i64, i64p, vpp],
+    "famg_dmat_finalize": [vp, cint],
+    "famg_dmat_retain": [vp],
+    "famg_dmat_destroy": [vp],
+    "famg_dmat_info": [vp, i64p, i64p, i64p, i64p],
+    "famg_dmat_local": [vp, cint, cint, vpp],
+    "famg_dmat_gather": [vp, vpp],
+    "famg_dist_coarsen": [vp, i64p, C.POINTER(u64p), C.POINTER(u64p), C.POINTER(f64p), cint, f64, vpp, vpp, vpp, C.POINTER(f64p)],
+    "famg_dist_smooth_near_null": [vp, cint, C.POINTER(f64p)],
+    "famg_dist_mg_create_levels": [vp, cint, vpp, vpp, vpp, cint, f64, vp, vpp],
 }
 
 _lib = None

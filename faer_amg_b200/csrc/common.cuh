@@ -56,6 +56,9 @@ struct famg_ctx {
     int num_sms = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t comm_stream = nullptr;  // halo exchange overlaps interior rows on this stream
+    cudaEvent_t ev_release = nullptr;    // orders operator frees after work queued on comm_stream
+    std::atomic<bool> comm_used{false};  // set once anything has been queued on comm_stream
+    std::atomic<int64_t> option_epoch{0};  // bumped by famg_ctx_set_option: captured graphs are keyed on it
     std::atomic<int64_t> launches{0};
     // small persistent scratch: scalars for dots / norms, pinned host mirror
     double *d_scalars = nullptr;  // 64 doubles
@@ -199,6 +202,15 @@ famg_status dense_gemv(famg_ctx *ctx, const double *inv, int64_t n, const double
 // ---------------------------------------------------------------- smoother apply (smoothers.cu)
 famg_status smoother_apply_dev(const famg_smoother *s, const double *in, int64_t ldi, double *out, int64_t ldo,
                                int k, cudaStream_t st = nullptr);
+
+// Diag smoother entries of the rows of `a` (rectangular row slabs allowed: the diagonal of local row i is
+// the entry with column id i; rows need not be sorted).  kind: FAMG_DIAG_L1 | FAMG_DIAG_JACOBI.
+famg_status diag_from_rows(const famg_csr *a, int kind, double omega, double *d_out);
+
+// sparse products (spgemm.cu)
+famg_status spgemm_impl(const famg_csr *a, const famg_csr *b, const famg_csr *p_for_smoothing, double omega, famg_csr **out,
+                        int epi_kind = 1);
+famg_status transpose_impl(const famg_csr *a, famg_csr **out);
 
 // one-sided Jacobi thin SVD of an m x k column-major block held in u (in: A, out: U); gallery.cu
 void host_thin_svd(int64_t m, int64_t k, std::vector<double> &u, std::vector<double> &s, std::vector<double> &v);

@@ -154,8 +154,13 @@ famg_status csr_alloc(famg_ctx *ctx, int64_t nrows, int64_t ncols, int64_t nnz, 
 void csr_release(famg_csr *a) {
     if (!a) return;
     if (a->refs.fetch_sub(1) == 1) {
-        // ordered after everything already queued on the context's stream that may read the buffers
+        // ordered after everything already queued on the context's stream that may read the buffers,
+        // and after the communication stream (NCCL halo path: boundary applies read operators there)
         cudaStream_t st = a->ctx->stream;
+        if (a->ctx->ev_release && a->ctx->comm_used.load(std::memory_order_relaxed)) {
+            cudaEventRecord(a->ctx->ev_release, a->ctx->comm_stream);
+            cudaStreamWaitEvent(st, a->ctx->ev_release, 0);
+        }
         if (a->row_ptr) cudaFreeAsync(a->row_ptr, st);
         if (a->col) cudaFreeAsync(a->col, st);
         if (a->val) cudaFreeAsync(a->val, st);
@@ -336,6 +341,7 @@ famg_status famg_ctx_create(int device, famg_ctx **out) {
         CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         CUDA_TRY(cudaStreamCreateWithPriority(&ctx->comm_stream, cudaStreamNonBlocking, hi));
     }
+    CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_release, cudaEventDisableTiming));
     CUDA_TRY(cudaMalloc((void **)&ctx->d_scalars, 64 * sizeof(double)));
     CUDA_TRY(cudaMemset(ctx->d_scalars, 0, 64 * sizeof(double)));
     CUDA_TRY(cudaMallocHost((void **)&ctx->h_scalars, 64 * sizeof(double)));
@@ -350,6 +356,7 @@ famg_status famg_ctx_destroy(famg_ctx *ctx) {
     cudaStreamSynchronize(ctx->comm_stream);
     pool_trim(ctx);
     cudaFree(ctx->d_scalars); cudaFreeHost(ctx->h_scalars); cudaFree(ctx->d_partials); cudaFree(ctx->pcg_ws);
+    if (ctx->ev_release) cudaEventDestroy(ctx->ev_release);
     cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->comm_stream);
     delete ctx;
     return FAMG_OK;
@@ -396,6 +403,7 @@ famg_status famg_ctx_set_option(famg_ctx *ctx, const char *key, int64_t value) {
     } else {
         FAMG_FAIL(FAMG_ERR_INVALID, "unknown option '%s'", key);
     }
+    ctx->option_epoch.fetch_add(1);  // kernel selection changed: graphs captured before must not be replayed
     return FAMG_OK;
 }
 

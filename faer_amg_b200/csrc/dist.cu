@@ -16,32 +16,17 @@
 // NCCL is resolved with dlopen at first use so that single-GPU users never need it and the copy
 // already loaded by the host process (e.g. torch's) is shared.
 #include <dlfcn.h>
-#include <nccl.h>
 
 #include <cmath>
 
-#include "mg_internal.cuh"
+#include "dist_internal.cuh"
 
 namespace famg {
 
-struct NcclApi {
-    void *handle = nullptr;
-    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
-    decltype(&ncclCommInitRank) CommInitRank = nullptr;
-    decltype(&ncclCommDestroy) CommDestroy = nullptr;
-    decltype(&ncclGetErrorString) GetErrorString = nullptr;
-    decltype(&ncclGroupStart) GroupStart = nullptr;
-    decltype(&ncclGroupEnd) GroupEnd = nullptr;
-    decltype(&ncclSend) Send = nullptr;
-    decltype(&ncclRecv) Recv = nullptr;
-    decltype(&ncclAllReduce) AllReduce = nullptr;
-    decltype(&ncclBroadcast) Broadcast = nullptr;
-    decltype(&ncclAllGather) AllGather = nullptr;
-};
-static NcclApi g_nccl;
+NcclApi g_nccl;
 static std::mutex g_nccl_mu;
 
-static famg_status nccl_load() {
+famg_status nccl_load() {
     std::lock_guard<std::mutex> lk(g_nccl_mu);
     if (g_nccl.handle) return FAMG_OK;
     void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
@@ -57,269 +42,9 @@ static famg_status nccl_load() {
     return FAMG_OK;
 }
 
-#define NCCL_TRY(expr)                                                                              \
-    do {                                                                                            \
-        ncclResult_t r__ = (expr);                                                                  \
-        if (r__ != ncclSuccess) FAMG_FAIL(FAMG_ERR_COMM, "%s failed: %s", #expr, g_nccl.GetErrorString(r__)); \
-    } while (0)
-
-}  // namespace famg
-
-struct famg_comm {
-    famg_ctx *ctx = nullptr;
-    int nranks = 1, rank = 0;
-    ncclComm_t comm = nullptr;
-    cudaEvent_t ev_packed = nullptr, ev_halo = nullptr;
-};
-
-namespace famg {
-
-// ---------------------------------------------------------------- halo plans
-// Peer-memory halo exchange (NVLink loads/stores instead of NCCL send/recv): every rank owns an
-// "arena" exported with CUDA IPC; per plan it holds one flag per peer, an epoch counter and two
-// receive buffers (parity = epoch & 1).  A pack kernel stores this rank's boundary entries straight
-// into its neighbours' receive buffers, fences, and publishes the epoch in their flag slots; the
-// consumer spins on its own flag slots (acquire, with a 20 s timeout) and moves the ghosts into the
-// vector's tail.  Epochs live in device memory, so the sequence replays inside CUDA graphs.
-constexpr int P2P_MAX_NB = 8;
-struct P2PPlanDev {
-    int nnb;                                  // neighbours (peers we exchange flags with, both ways)
-    int nghost;
-    double *rdst[2][P2P_MAX_NB];              // where my entries go on neighbour nb (per parity)
-    unsigned long long *rflag[P2P_MAX_NB];    // my slot in neighbour nb's flag array
-    const unsigned long long *lflag[P2P_MAX_NB];  // neighbour nb's slot in my flag array
-    int soff[P2P_MAX_NB], scnt[P2P_MAX_NB];   // my pack-list range for neighbour nb
-    unsigned long long *epoch;                // this plan's exchange counter (device)
-    unsigned int *done;                       // blocks of the pack kernel that have finished their stores
-    int total_send;
-    const double *lrecv[2];                   // my receive buffers
-    int *err;                                 // set on spin timeout
-};
-
-// Small collectives over the same arenas: sum-all-reduce of <= 4 doubles (PCG dot products) and the
-// all-gather of the restricted residual at the replicated-level transition.  Every rank stores its
-// contribution into every peer's slot, publishes the epoch, waits for all peers, then reduces in
-// rank order -- every rank forms bit-identical sums.
-constexpr int P2P_AR_WIDTH = 4;
-struct P2PCollDev {
-    int nranks, rank;
-    // all-reduce
-    double *ar_rslots[2][P2P_MAX_NB + 1];            // peer p's slot array (parity), indexed [rank*W + w]
-    unsigned long long *ar_rflag[P2P_MAX_NB + 1];    // my flag slot on peer p
-    const unsigned long long *ar_lflag;              // my flag array (one per peer)
-    const double *ar_lslots[2];
-    unsigned long long *ar_epoch;
-    // all-gather
-    double *ag_rbuf[2][P2P_MAX_NB + 1];              // peer p's gather buffer (parity)
-    unsigned long long *ag_rflag[P2P_MAX_NB + 1];
-    const unsigned long long *ag_lflag;
-    const double *ag_lbuf[2];
-    unsigned long long *ag_epoch;
-    unsigned int *ag_done;
-    int *err;
-};
-
-struct HaloPlan {
-    bool p2p = false;
-    P2PPlanDev dev{};
-    size_t arena_flags = 0, arena_recv[2] = {0, 0};  // byte offsets inside this rank's arena
-    int nloc = 0, nghost = 0;
-    std::vector<int> recv_cnt, recv_off, send_cnt, send_off;
-    int total_send = 0;
-    int *d_send_idx = nullptr;
-    double *d_sendbuf = nullptr;
-    bool any = false;
-};
-
-struct DistOp {
-    famg_csr *local = nullptr;  // slab, columns renumbered to [owned | ghost]
-    HaloPlan halo;
-    int ib = 0, ie = 0;         // rows [ib, ie) reference no ghost column
-};
-
-struct DistLevel {
-    int64_t r0 = 0, r1 = 0;  // owned rows of this level
-    DistOp A, R, P;          // R: rows of level l+1 (owned), cols level l.  P: rows level l, cols level l+1
-    bool has_R = false, has_P = false;
-    double *d = nullptr;     // owned slice of the Diag smoother
-    double *x = nullptr, *b = nullptr, *t = nullptr;  // work vectors with ghost tails
-    int64_t ld = 0;
-};
-
-}  // namespace famg
-
-struct famg_dist_mg {
-    famg_comm *comm = nullptr;
-    famg_mg *global = nullptr;
-    int lrep = 0;  // first replicated level
-    std::vector<famg::DistLevel> lv;
-    std::vector<std::vector<int64_t>> splits;  // per level, nranks+1
-    // transition buffers: gathered rhs / replicated solution of level lrep, and this rank's piece
-    // of the restricted residual before the gather
-    double *g_f = nullptr, *g_v = nullptr, *fc_loc = nullptr;
-    // PCG work vectors (with ghost tail for p)
-    double *pcg = nullptr; int64_t pcg_ld = 0;
-    // peer-memory exchange state
-    unsigned char *arena = nullptr; size_t arena_bytes = 0;
-    std::vector<void *> peer_arena;  // IPC-mapped arenas of the other ranks
-    int *d_p2p_err = nullptr;
-    bool p2p = false;
-    famg::P2PCollDev coll{};
-    bool p2p_coll = false;
-    // the distributed cycle (kernels on two streams + NCCL point-to-point / broadcast calls) is
-    // captured into one CUDA graph per (out, rhs) pair and replayed; disabled on the first failure
-    std::map<std::pair<const void *, const void *>, GraphEntry> graphs;
-    bool use_graph = true;
-};
-
-namespace famg {
-
-__global__ void mark_ghost_kernel(const int *__restrict__ rp, const int *__restrict__ col, int row0, int row1, int c0, int c1,
-                                  int *__restrict__ flags, int invert) {
-    // invert == 0: flag columns outside [c0,c1) (global index).  invert == 1: flag columns inside
-    // [c0,c1), stored relative to c0 (what the slab [row0,row1) needs from the owner of [c0,c1)).
-    const int i = row0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= row1) return;
-    for (int q = rp[i]; q < rp[i + 1]; ++q) {
-        const int c = col[q];
-        const bool inside = c >= c0 && c < c1;
-        if (!invert) { if (!inside) flags[c] = 1; }
-        else if (inside) flags[c - c0] = 1;
-    }
-}
-__global__ void compact_kernel(const int *__restrict__ flags, const int *__restrict__ pos, int n, int *__restrict__ out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && flags[i]) out[pos[i]] = i;
-}
-__global__ void gather_int_kernel(const int *__restrict__ src, const int *__restrict__ idx, int n, int *__restrict__ out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = src[idx[i]];
-}
-__global__ void renumber_kernel(int *__restrict__ col, int nnz, int c0, int c1, const int *__restrict__ ghost_pos) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= nnz) return;
-    const int c = col[q];
-    col[q] = (c >= c0 && c < c1) ? c - c0 : (c1 - c0) + ghost_pos[c];
-}
-__global__ void interior_range_kernel(const int *__restrict__ rp, const int *__restrict__ col, int nrows, int nloc_cols,
-                                      int *__restrict__ lo_hi) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nrows) return;
-    bool ghost = false;
-    for (int q = rp[i]; q < rp[i + 1]; ++q) ghost |= col[q] >= nloc_cols;
-    if (!ghost) return;
-    const int mid = nrows / 2;
-    if (i < mid) atomicMax(&lo_hi[0], i + 1); else atomicMin(&lo_hi[1], i);
-}
 __global__ void pack_kernel(const double *__restrict__ x, const int *__restrict__ idx, int n, double *__restrict__ buf) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) buf[i] = x[idx[i]];
-}
-
-static void halo_free(HaloPlan &h) { cudaFree(h.d_send_idx); cudaFree(h.d_sendbuf); h.d_send_idx = nullptr; h.d_sendbuf = nullptr; }
-static void distop_free(DistOp &o) { if (o.local) csr_release(o.local); o.local = nullptr; halo_free(o.halo); }
-
-// Build the slab of `m` owned by `rank` (rows rs[rank]..rs[rank+1]) with columns split by cs.
-static famg_status distop_build(famg_comm *cm, const famg_csr *m, const std::vector<int64_t> &rs, const std::vector<int64_t> &cs,
-                                bool replicated_cols, DistOp *op) {
-    famg_ctx *ctx = cm->ctx;
-    const int nr = cm->nranks, me = cm->rank;
-    const int row0 = (int)rs[me], row1 = (int)rs[me + 1];
-    FAMG_TRY(famg_csr_row_slab(m, row0, row1, &op->local));
-    HaloPlan &h = op->halo;
-    h.recv_cnt.assign(nr, 0); h.recv_off.assign(nr, 0); h.send_cnt.assign(nr, 0); h.send_off.assign(nr, 0);
-    op->ib = 0; op->ie = row1 - row0;
-    if (replicated_cols) {  // the consumer vector is replicated: global column indices, no halo
-        h.nloc = (int)m->ncols; h.nghost = 0; h.any = false;
-        return FAMG_OK;
-    }
-    const int c0 = (int)cs[me], c1 = (int)cs[me + 1], ncols = (int)m->ncols;
-    h.nloc = c1 - c0;
-    int *flags = nullptr, *pos = nullptr, *small = nullptr;
-    famg_status st = dev_alloc(&flags, ncols + 1);
-    if (st == FAMG_OK) st = dev_alloc(&pos, ncols + 2);
-    if (st == FAMG_OK) st = dev_alloc(&small, 4 * nr + 8);
-    auto done = [&](famg_status s) { cudaStreamSynchronize(ctx->stream); cudaFree(flags); cudaFree(pos); cudaFree(small); return s; };
-    if (st != FAMG_OK) return done(st);
-    // 1. my ghost columns (ascending => grouped by owner rank)
-    cudaMemsetAsync(flags, 0, sizeof(int) * (ncols + 1), ctx->stream);
-    if (row1 > row0) {
-        mark_ghost_kernel<<<(unsigned)ceil_div(row1 - row0, 256), 256, 0, ctx->stream>>>(m->row_ptr, m->col, row0, row1, c0, c1, flags, 0);
-        count_launch(ctx);
-    }
-    st = exclusive_scan_i32(ctx, flags, pos, ncols);
-    if (st != FAMG_OK) return done(st);
-    {
-        std::vector<int> hs(nr + 1), hp(nr + 1);
-        for (int p = 0; p <= nr; ++p) hs[p] = (int)cs[p];
-        cudaMemcpy(small, hs.data(), sizeof(int) * (nr + 1), cudaMemcpyHostToDevice);
-        gather_int_kernel<<<1, 256, 0, ctx->stream>>>(pos, small, nr + 1, small + nr + 1);
-        count_launch(ctx);
-        cudaStreamSynchronize(ctx->stream);
-        cudaMemcpy(hp.data(), small + nr + 1, sizeof(int) * (nr + 1), cudaMemcpyDeviceToHost);
-        if (nr + 1 > 256) return done((set_error("too many ranks"), FAMG_ERR_UNSUPPORTED));
-        for (int p = 0; p < nr; ++p) { h.recv_cnt[p] = hp[p + 1] - hp[p]; h.recv_off[p] = hp[p]; }
-        h.nghost = hp[nr];
-        if (h.recv_cnt[me] != 0) return done((set_error("internal: own columns flagged as ghosts"), FAMG_ERR_INVALID));
-    }
-    // 2. renumber the slab's columns
-    if (op->local->nnz) {
-        renumber_kernel<<<(unsigned)ceil_div(op->local->nnz, 256), 256, 0, ctx->stream>>>(op->local->col, (int)op->local->nnz, c0, c1, pos);
-        count_launch(ctx);
-    }
-    op->local->ncols = h.nloc + h.nghost;
-    // 3. what every peer needs from me (ascending local index => same order as the peer's ghost list)
-    std::vector<std::vector<int>> send_lists(nr);
-    for (int p = 0; p < nr; ++p) {
-        if (p == me || h.nloc == 0 || rs[p + 1] == rs[p]) continue;
-        cudaMemsetAsync(flags, 0, sizeof(int) * (h.nloc + 1), ctx->stream);
-        mark_ghost_kernel<<<(unsigned)ceil_div(rs[p + 1] - rs[p], 256), 256, 0, ctx->stream>>>(m->row_ptr, m->col, (int)rs[p], (int)rs[p + 1],
-                                                                                                c0, c1, flags, 1);
-        count_launch(ctx);
-        st = exclusive_scan_i32(ctx, flags, pos, h.nloc);
-        if (st != FAMG_OK) return done(st);
-        int cnt = 0;
-        cudaMemcpy(&cnt, pos + h.nloc, sizeof(int), cudaMemcpyDeviceToHost);
-        h.send_cnt[p] = cnt;
-        if (cnt) {
-            int *tmp = nullptr;
-            st = dev_alloc(&tmp, cnt);
-            if (st != FAMG_OK) return done(st);
-            compact_kernel<<<(unsigned)ceil_div(h.nloc, 256), 256, 0, ctx->stream>>>(flags, pos, h.nloc, tmp);
-            count_launch(ctx);
-            send_lists[p].resize(cnt);
-            cudaStreamSynchronize(ctx->stream);
-            cudaMemcpy(send_lists[p].data(), tmp, sizeof(int) * cnt, cudaMemcpyDeviceToHost);
-            cudaFree(tmp);
-        }
-    }
-    h.total_send = 0;
-    for (int p = 0; p < nr; ++p) { h.send_off[p] = h.total_send; h.total_send += h.send_cnt[p]; }
-    if (h.total_send) {
-        std::vector<int> all; all.reserve(h.total_send);
-        for (int p = 0; p < nr; ++p) all.insert(all.end(), send_lists[p].begin(), send_lists[p].end());
-        st = dev_alloc(&h.d_send_idx, h.total_send);
-        if (st == FAMG_OK) st = dev_alloc(&h.d_sendbuf, h.total_send);
-        if (st != FAMG_OK) return done(st);
-        cudaMemcpy(h.d_send_idx, all.data(), sizeof(int) * h.total_send, cudaMemcpyHostToDevice);
-    }
-    h.any = h.total_send > 0 || h.nghost > 0;
-    // 4. interior row range
-    {
-        const int nrows = row1 - row0;
-        int init[2] = {0, nrows};
-        cudaMemcpy(small, init, sizeof(init), cudaMemcpyHostToDevice);
-        if (nrows > 0 && h.nghost > 0) {
-            interior_range_kernel<<<(unsigned)ceil_div(nrows, 256), 256, 0, ctx->stream>>>(op->local->row_ptr, op->local->col, nrows, h.nloc, small);
-            count_launch(ctx);
-        }
-        cudaStreamSynchronize(ctx->stream);
-        cudaMemcpy(init, small, sizeof(init), cudaMemcpyDeviceToHost);
-        op->ib = init[0]; op->ie = std::max(init[0], init[1]);
-    }
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return done((set_error("dist setup: %s", cudaGetErrorString(e)), FAMG_ERR_CUDA));
-    return done(FAMG_OK);
 }
 
 // ---------------------------------------------------------------- peer-memory exchange kernels
@@ -506,8 +231,7 @@ static famg_status halo_begin(famg_comm *cm, const HaloPlan &h, double *x_ext) {
     }
     CUDA_TRY(cudaEventRecord(cm->ev_packed, ctx->stream));
     CUDA_TRY(cudaStreamWaitEvent(ctx->comm_stream, cm->ev_packed, 0));
-    static const bool skip_comm = getenv("FAMG_DEBUG_SKIP_HALO") != nullptr;  // timing experiments only (wrong results)
-    if (skip_comm) { CUDA_TRY(cudaEventRecord(cm->ev_halo, ctx->comm_stream)); return FAMG_OK; }
+    ctx->comm_used.store(true, std::memory_order_relaxed);
     NCCL_TRY(g_nccl.GroupStart());
     for (int p = 0; p < cm->nranks; ++p) {
         if (h.send_cnt[p]) NCCL_TRY(g_nccl.Send(h.d_sendbuf + h.send_off[p], (size_t)h.send_cnt[p], ncclDouble, p, cm->comm, ctx->comm_stream));
@@ -636,12 +360,12 @@ static famg_status dist_cycle(famg_dist_mg *dm, int level, double *va, const dou
     famg_mg *gm = dm->global;
     if (level == dm->lrep) {
         // replicated tail: gather f, run the global cycle from this level, keep the owned slice
-        MgLevel &G = gm->lv[level];
+        MgLevel &G = gm->lv[(size_t)dm->tail_first];
         const int64_t n = G.a->nrows;
         const auto &sp = dm->splits[level];
         FAMG_TRY(allgather_rows(dm, level, f, dm->g_f));
         if (!zero_guess) FAMG_TRY(allgather_rows(dm, level, va, dm->g_v));
-        FAMG_TRY(mg_cycle(gm, (size_t)level, dm->g_v, (n + 1) & ~(int64_t)1, dm->g_f, (n + 1) & ~(int64_t)1, 1, zero_guess));
+        FAMG_TRY(mg_cycle(gm, (size_t)dm->tail_first, dm->g_v, (n + 1) & ~(int64_t)1, dm->g_f, (n + 1) & ~(int64_t)1, 1, zero_guess));
         CUDA_TRY(cudaMemcpyAsync(va, dm->g_v + sp[cm->rank], sizeof(double) * (sp[cm->rank + 1] - sp[cm->rank]), cudaMemcpyDeviceToDevice,
                                  ctx->stream));
         return FAMG_OK;
@@ -651,7 +375,7 @@ static famg_status dist_cycle(famg_dist_mg *dm, int level, double *va, const dou
     double *cur = va, *oth = L.t;
     const int nu = gm->nu, mu = gm->mu;
     auto sweep = [&]() -> famg_status {
-        FAMG_TRY(dist_apply(cm, L.A, EPI_SMOOTH, cur, oth, f, L.d, nullptr, nullptr));
+        FAMG_TRY(dist_apply(cm, *L.A, EPI_SMOOTH, cur, oth, f, L.d, nullptr, nullptr));
         std::swap(cur, oth);
         return FAMG_OK;
     };
@@ -662,22 +386,22 @@ static famg_status dist_cycle(famg_dist_mg *dm, int level, double *va, const dou
         pre -= 1;
     }
     for (int i = 0; i < pre; ++i) FAMG_TRY(sweep());
-    FAMG_TRY(dist_apply(cm, L.A, EPI_RESID, cur, oth, f, nullptr, nullptr, nullptr));
+    FAMG_TRY(dist_apply(cm, *L.A, EPI_RESID, cur, oth, f, nullptr, nullptr, nullptr));
     const bool coarse_rep = level + 1 == dm->lrep;
     // restriction into the owned rows of level+1
     double *fc, *vc;
     if (coarse_rep) { fc = dm->fc_loc; vc = dm->g_v; }
     else { fc = dm->lv[level + 1].b; vc = dm->lv[level + 1].x; }
-    FAMG_TRY(dist_apply(cm, L.R, EPI_SPMV, oth, fc, nullptr, nullptr, nullptr, nullptr));
+    FAMG_TRY(dist_apply(cm, *L.R, EPI_SPMV, oth, fc, nullptr, nullptr, nullptr, nullptr));
     if (coarse_rep) {
-        MgLevel &G = gm->lv[level + 1];
+        MgLevel &G = gm->lv[(size_t)dm->tail_first];
         const int64_t ldg = (G.a->nrows + 1) & ~(int64_t)1;
         FAMG_TRY(allgather_rows(dm, level + 1, fc, dm->g_f));
-        for (int m = 0; m < mu; ++m) FAMG_TRY(mg_cycle(gm, (size_t)level + 1, dm->g_v, ldg, dm->g_f, ldg, 1, m == 0));
+        for (int m = 0; m < mu; ++m) FAMG_TRY(mg_cycle(gm, (size_t)dm->tail_first, dm->g_v, ldg, dm->g_f, ldg, 1, m == 0));
     } else {
         for (int m = 0; m < mu; ++m) FAMG_TRY(dist_cycle(dm, level + 1, vc, fc, m == 0));
     }
-    FAMG_TRY(dist_apply(cm, L.P, EPI_ADD, vc, cur, nullptr, nullptr, nullptr, nullptr));
+    FAMG_TRY(dist_apply(cm, *L.P, EPI_ADD, vc, cur, nullptr, nullptr, nullptr, nullptr));
     for (int i = 0; i < nu; ++i) FAMG_TRY(sweep());
     if (cur != va) FAMG_FAIL(FAMG_ERR_INVALID, "internal: distributed ping-pong parity broken");
     return FAMG_OK;
@@ -691,7 +415,7 @@ static famg_status p2p_setup(famg_dist_mg *d) {
     const int nr = cm->nranks, me = cm->rank;
     if (nr == 1 || nr > P2P_MAX_NB + 1) return FAMG_OK;
     std::vector<HaloPlan *> plans;
-    for (auto &L : d->lv) { plans.push_back(&L.A.halo); plans.push_back(&L.R.halo); plans.push_back(&L.P.halo); }
+    for (auto &L : d->lv) { plans.push_back(&L.A->halo); plans.push_back(&L.R->halo); plans.push_back(&L.P->halo); }
     const int np = (int)plans.size();
     if (np == 0) return FAMG_OK;
     // arena layout: per plan [flags nr x u64 | epoch u64 | pad to 256] [recv0] [recv1] (256-byte aligned)
@@ -702,7 +426,7 @@ static famg_status p2p_setup(famg_dist_mg *d) {
         for (int b = 0; b < 2; ++b) { h->arena_recv[b] = off; off = align(off + sizeof(double) * (size_t)std::max(h->nghost, 1)); }
     }
     // collective regions: all-reduce [flags nr | epoch | pad][slots0][slots1], all-gather [flags nr | epoch | done][buf0][buf1]
-    const size_t n_rep = (size_t)d->global->lv[d->lrep].a->nrows;
+    const size_t n_rep = (size_t)d->global->lv[(size_t)d->tail_first].a->nrows;
     size_t coll_off[6];
     coll_off[0] = off; off = align(off + sizeof(unsigned long long) * (nr + 2));
     coll_off[1] = off; off = align(off + sizeof(double) * (size_t)nr * P2P_AR_WIDTH);
@@ -803,10 +527,9 @@ static void dist_free(famg_dist_mg *d) {
     for (size_t p = 0; p < d->peer_arena.size(); ++p)
         if (d->peer_arena[p] && (int)p != d->comm->rank) cudaIpcCloseMemHandle(d->peer_arena[p]);
     cudaFree(d->arena); cudaFree(d->d_p2p_err);
-    for (auto &l : d->lv) {
-        distop_free(l.A); distop_free(l.R); distop_free(l.P);
-        cudaFree(l.d); cudaFree(l.x); cudaFree(l.b); cudaFree(l.t);
-    }
+    for (auto &l : d->lv) { cudaFree(l.d); cudaFree(l.x); cudaFree(l.b); cudaFree(l.t); }
+    for (famg_dmat *m : d->keep) dmat_release(m);
+    if (d->owns_tail && d->global) famg_mg_destroy(d->global);
     for (auto &g : d->graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
     cudaFree(d->g_f); cudaFree(d->g_v); cudaFree(d->fc_loc); cudaFree(d->pcg);
     delete d;
@@ -861,6 +584,7 @@ famg_status famg_comm_destroy(famg_comm *c) {
 
 famg_status famg_comm_allreduce_sum(famg_comm *c, double *vals, int n) {
     if (!c || !vals || n < 0 || n > 32) FAMG_FAIL(FAMG_ERR_INVALID, "bad argument (n <= 32)");
+    if (c->nlocal > 1) FAMG_FAIL(FAMG_ERR_UNSUPPORTED, "virtual communicators have no collectives outside the hierarchy setup");
     famg_ctx *ctx = c->ctx;
     CUDA_TRY(cudaSetDevice(ctx->device));
     CUDA_TRY(cudaMemcpyAsync(ctx->d_scalars + 32, vals, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
@@ -870,53 +594,32 @@ famg_status famg_comm_allreduce_sum(famg_comm *c, double *vals, int n) {
     return FAMG_OK;
 }
 
-famg_status famg_dist_mg_create(famg_comm *c, famg_mg *gm, const int64_t *const *row_splits, int64_t replicate_below,
-                                famg_dist_mg **out) {
-    if (!c || !gm || !row_splits || !out) FAMG_FAIL(FAMG_ERR_INVALID, "null argument");
-    *out = nullptr;
+// Work vectors, transition buffers and the peer-memory state once d->lv[*].{A,R,P}, d->splits, d->global and
+// d->tail_first are in place (both constructors end here).
+static famg_status dist_mg_finish(famg_dist_mg *d, int diag_kind, double omega, const famg_mg *diag_source) {
+    famg_comm *c = d->comm;
     famg_ctx *ctx = c->ctx;
-    if (gm->ctx != ctx) FAMG_FAIL(FAMG_ERR_INVALID, "multigrid and communicator live on different contexts");
-    CUDA_TRY(cudaSetDevice(ctx->device));
-    const int nl = (int)gm->lv.size(), nr = c->nranks;
-    famg_dist_mg *d = new famg_dist_mg();
-    d->comm = c; d->global = gm;
-    d->splits.resize(nl);
-    for (int l = 0; l < nl; ++l) {
-        d->splits[l].assign(row_splits[l], row_splits[l] + nr + 1);
-        const auto &sp = d->splits[l];
-        bool ok = sp[0] == 0 && sp[nr] == gm->lv[l].a->nrows;
-        for (int p = 0; p < nr; ++p) ok = ok && sp[p] <= sp[p + 1];
-        if (!ok) { dist_free(d); FAMG_FAIL(FAMG_ERR_INVALID, "row_splits of level %d do not partition its rows", l); }
-    }
-    // first replicated level: too few rows per rank, a non-Diag smoother, or the coarsest level
+    const int lrep = d->lrep;
     if (const char *v = getenv("FAMG_DIST_GRAPH")) d->use_graph = atoi(v) != 0;
-    int lrep = nl - 1;
-    for (int l = 0; l < nl - 1; ++l)
-        if (gm->lv[l].a->nrows / nr < replicate_below || gm->lv[l].s->kind != SM_DIAG) { lrep = l; break; }
-    d->lrep = lrep;
-    FAMG_TRY(mg_ensure_workspace(gm, 1));
-    d->lv.resize(lrep);
+    FAMG_TRY(mg_ensure_workspace(d->global, 1));
     famg_status st = FAMG_OK;
     for (int l = 0; l < lrep && st == FAMG_OK; ++l) {
-        DistLevel &L = d->lv[l];
-        MgLevel &G = gm->lv[l];
-        L.r0 = d->splits[l][c->rank]; L.r1 = d->splits[l][c->rank + 1];
-        st = distop_build(c, G.a, d->splits[l], d->splits[l], false, &L.A);
-        MgLevel &C = gm->lv[l + 1];
-        const bool coarse_rep = l + 1 == lrep;
-        if (st == FAMG_OK) { st = distop_build(c, C.r, d->splits[l + 1], d->splits[l], false, &L.R); L.has_R = true; }
-        if (st == FAMG_OK) { st = distop_build(c, C.p, d->splits[l], d->splits[l + 1], coarse_rep, &L.P); L.has_P = true; }
-        if (st != FAMG_OK) break;
+        DistLevel &L = d->lv[(size_t)l];
+        L.r0 = d->splits[(size_t)l][(size_t)c->rank]; L.r1 = d->splits[(size_t)l][(size_t)c->rank + 1];
         const int64_t nloc = L.r1 - L.r0;
         st = dev_alloc(&L.d, nloc);
-        if (st == FAMG_OK && nloc)
-            cudaMemcpyAsync(L.d, G.s->d + L.r0, sizeof(double) * nloc, cudaMemcpyDeviceToDevice, ctx->stream);
+        if (st != FAMG_OK) break;
+        if (diag_source) {  // slice of the replicated level smoother
+            if (nloc) cudaMemcpyAsync(L.d, diag_source->lv[(size_t)l].s->d + L.r0, sizeof(double) * nloc, cudaMemcpyDeviceToDevice, ctx->stream);
+        } else {
+            st = diag_from_rows(L.A->local, diag_kind, omega, L.d);
+        }
     }
     // vector tails: a level-l vector is consumed by A_l and R_l (level l columns) and by P_{l-1}
     for (int l = 0; l < lrep && st == FAMG_OK; ++l) {
-        DistLevel &L = d->lv[l];
-        int64_t ghost = std::max(L.A.halo.nghost, L.R.halo.nghost);
-        if (l > 0) ghost = std::max<int64_t>(ghost, d->lv[l - 1].P.halo.nghost);
+        DistLevel &L = d->lv[(size_t)l];
+        int64_t ghost = std::max(L.A->halo.nghost, L.R->halo.nghost);
+        if (l > 0) ghost = std::max<int64_t>(ghost, d->lv[(size_t)l - 1].P->halo.nghost);
         L.ld = (L.r1 - L.r0) + ghost + 2;
         st = dev_alloc(&L.x, L.ld);
         if (st == FAMG_OK) st = dev_alloc(&L.b, L.ld);
@@ -928,21 +631,21 @@ famg_status famg_dist_mg_create(famg_comm *c, famg_mg *gm, const int64_t *const 
         }
     }
     if (st == FAMG_OK) {
-        const int64_t n = gm->lv[lrep].a->nrows;
+        const int64_t n = d->global->lv[(size_t)d->tail_first].a->nrows;
         st = dev_alloc(&d->g_f, n + 2);
         if (st == FAMG_OK) st = dev_alloc(&d->g_v, n + 2);
-        if (st == FAMG_OK) st = dev_alloc(&d->fc_loc, d->splits[lrep][c->rank + 1] - d->splits[lrep][c->rank] + 2);
+        if (st == FAMG_OK) st = dev_alloc(&d->fc_loc, d->splits[(size_t)lrep][(size_t)c->rank + 1] - d->splits[(size_t)lrep][(size_t)c->rank] + 2);
     }
     if (st == FAMG_OK) {
         // PCG vectors r, z, q, x-scratch, and p with the ghost tail of A_0
-        const int64_t nloc = d->splits[0][c->rank + 1] - d->splits[0][c->rank];
+        const int64_t nloc = d->splits[0][(size_t)c->rank + 1] - d->splits[0][(size_t)c->rank];
         const int64_t ghost = lrep > 0 ? d->lv[0].ld : nloc + 2;
         d->pcg_ld = (std::max(nloc + 2, ghost) + 1) & ~(int64_t)1;
         st = dev_alloc(&d->pcg, 6 * d->pcg_ld);
         if (st == FAMG_OK) cudaMemsetAsync(d->pcg, 0, sizeof(double) * 6 * d->pcg_ld, ctx->stream);
     }
     cudaStreamSynchronize(ctx->stream);
-    if (st != FAMG_OK) { dist_free(d); return st; }
+    FAMG_TRY(st);
     {   // peer-memory halo exchange unless FAMG_HALO=nccl; every rank must reach the same decision
         const char *mode = getenv("FAMG_HALO");
         if (!(mode && !strcmp(mode, "nccl"))) {
@@ -954,11 +657,108 @@ famg_status famg_dist_mg_create(famg_comm *c, famg_mg *gm, const int64_t *const 
                 all_ok = (as == FAMG_OK && v[0] == (double)c->nranks) ? 1.0 : 0.0;
             }
             if (all_ok != 1.0) {  // somebody could not map a peer: everyone stays on NCCL send/recv
-                for (auto &L : d->lv) { L.A.halo.p2p = false; L.R.halo.p2p = false; L.P.halo.p2p = false; }
+                for (auto &L : d->lv) { L.A->halo.p2p = false; L.R->halo.p2p = false; L.P->halo.p2p = false; }
                 d->p2p = false; d->p2p_coll = false;
             }
         }
     }
+    return FAMG_OK;
+}
+
+// row slab [rs[rank], rs[rank+1]) of a replicated matrix as a one-part distributed matrix
+static famg_status dmat_from_replicated(famg_comm *c, const famg_csr *m, const std::vector<int64_t> &rs, const std::vector<int64_t> &cs,
+                                        bool replicated_cols, famg_dmat **out) {
+    famg_csr *slab = nullptr;
+    FAMG_TRY(famg_csr_row_slab(m, rs[(size_t)c->rank], rs[(size_t)c->rank + 1], &slab));
+    famg_dmat *dm = new famg_dmat();
+    dm->comm = c; dm->nrows = m->nrows; dm->ncols = m->ncols; dm->rsplit = rs; dm->csplit = cs;
+    dm->part.resize(1);
+    dm->part[0].local = slab;
+    famg_status st = dmat_finalize(dm, replicated_cols);
+    if (st != FAMG_OK) { dmat_release(dm); return st; }
+    *out = dm;
+    return FAMG_OK;
+}
+
+famg_status famg_dist_mg_create(famg_comm *c, famg_mg *gm, const int64_t *const *row_splits, int64_t replicate_below,
+                                famg_dist_mg **out) {
+    if (!c || !gm || !row_splits || !out) FAMG_FAIL(FAMG_ERR_INVALID, "null argument");
+    *out = nullptr;
+    famg_ctx *ctx = c->ctx;
+    if (gm->ctx != ctx) FAMG_FAIL(FAMG_ERR_INVALID, "multigrid and communicator live on different contexts");
+    if (c->nlocal != 1) FAMG_FAIL(FAMG_ERR_UNSUPPORTED, "a single-process virtual communicator can build hierarchies but not run the distributed cycle");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const int nl = (int)gm->lv.size(), nr = c->nranks;
+    famg_dist_mg *d = new famg_dist_mg();
+    d->comm = c; d->global = gm;
+    d->splits.resize((size_t)nl);
+    for (int l = 0; l < nl; ++l) {
+        d->splits[(size_t)l].assign(row_splits[l], row_splits[l] + nr + 1);
+        const auto &sp = d->splits[(size_t)l];
+        bool ok = sp[0] == 0 && sp[(size_t)nr] == gm->lv[(size_t)l].a->nrows;
+        for (int p = 0; p < nr; ++p) ok = ok && sp[(size_t)p] <= sp[(size_t)p + 1];
+        if (!ok) { dist_free(d); FAMG_FAIL(FAMG_ERR_INVALID, "row_splits of level %d do not partition its rows", l); }
+    }
+    // first replicated level: too few rows per rank, a non-Diag smoother, or the coarsest level
+    int lrep = nl - 1;
+    for (int l = 0; l < nl - 1; ++l)
+        if (gm->lv[(size_t)l].a->nrows / nr < replicate_below || gm->lv[(size_t)l].s->kind != SM_DIAG) { lrep = l; break; }
+    d->lrep = lrep; d->tail_first = lrep;
+    d->lv.resize((size_t)lrep);
+    famg_status st = FAMG_OK;
+    for (int l = 0; l < lrep && st == FAMG_OK; ++l) {
+        DistLevel &L = d->lv[(size_t)l];
+        MgLevel &G = gm->lv[(size_t)l], &C = gm->lv[(size_t)l + 1];
+        const bool coarse_rep = l + 1 == lrep;
+        famg_dmat *A = nullptr, *R = nullptr, *P = nullptr;
+        st = dmat_from_replicated(c, G.a, d->splits[(size_t)l], d->splits[(size_t)l], false, &A);
+        if (st == FAMG_OK) { d->keep.push_back(A); L.A = &A->part[0]; st = dmat_from_replicated(c, C.r, d->splits[(size_t)l + 1], d->splits[(size_t)l], false, &R); }
+        if (st == FAMG_OK) { d->keep.push_back(R); L.R = &R->part[0]; st = dmat_from_replicated(c, C.p, d->splits[(size_t)l], d->splits[(size_t)l + 1], coarse_rep, &P); }
+        if (st == FAMG_OK) { d->keep.push_back(P); L.P = &P->part[0]; }
+    }
+    if (st == FAMG_OK) st = dist_mg_finish(d, FAMG_DIAG_L1, 0.0, gm);
+    if (st != FAMG_OK) { dist_free(d); return st; }
+    *out = d;
+    return FAMG_OK;
+}
+
+// Level-wise construction from distributed operators (famg_dist_coarsen): a[l] (finalized), r[l] (finalized over
+// a[l]'s split), p[l] (finalized over a[l+1]'s split, or with replicated columns for the last one), l < nlevels;
+// `tail` is the replicated Multigrid of the remaining levels (its level 0 = the gathered a[nlevels]); it is
+// borrowed and must outlive the result.  Smoother of the distributed levels: FAMG_DIAG_L1 | FAMG_DIAG_JACOBI.
+famg_status famg_dist_mg_create_levels(famg_comm *c, int nlevels, famg_dmat *const *a, famg_dmat *const *r, famg_dmat *const *p,
+                                       int diag_kind, double omega, famg_mg *tail, famg_dist_mg **out) {
+    if (!c || !tail || !out || nlevels < 0 || (nlevels > 0 && (!a || !r || !p))) FAMG_FAIL(FAMG_ERR_INVALID, "bad argument");
+    *out = nullptr;
+    famg_ctx *ctx = c->ctx;
+    if (tail->ctx != ctx) FAMG_FAIL(FAMG_ERR_INVALID, "multigrid and communicator live on different contexts");
+    if (c->nlocal != 1) FAMG_FAIL(FAMG_ERR_UNSUPPORTED, "a single-process virtual communicator can build hierarchies but not run the distributed cycle");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const int nr = c->nranks;
+    for (int l = 0; l < nlevels; ++l) {
+        if (!a[l] || !r[l] || !p[l] || a[l]->comm != c || r[l]->comm != c || p[l]->comm != c) FAMG_FAIL(FAMG_ERR_INVALID, "level %d: null operator or foreign communicator", l);
+        if (!a[l]->finalized || a[l]->replicated_cols || !r[l]->finalized || r[l]->replicated_cols || !p[l]->finalized)
+            FAMG_FAIL(FAMG_ERR_INVALID, "level %d: operators must be finalized (famg_dmat_finalize)", l);
+        const bool last = l + 1 == nlevels;
+        if (p[l]->replicated_cols != last) FAMG_FAIL(FAMG_ERR_INVALID, "level %d: only the last prolongator has replicated columns", l);
+        const int64_t nc = last ? tail->lv[0].a->nrows : a[l + 1]->nrows;
+        if (a[l]->nrows != a[l]->ncols || r[l]->ncols != a[l]->nrows || p[l]->nrows != a[l]->nrows || r[l]->nrows != nc || p[l]->ncols != nc ||
+            a[l]->rsplit != a[l]->csplit || r[l]->csplit != a[l]->rsplit || p[l]->rsplit != a[l]->rsplit || (!last && (r[l]->rsplit != a[l + 1]->rsplit || p[l]->csplit != a[l + 1]->rsplit)))
+            FAMG_FAIL(FAMG_ERR_INVALID, "level %d: shape / split mismatch between A, R and P (hierarchy.rs:258-264)", l);
+    }
+    famg_dist_mg *d = new famg_dist_mg();
+    d->comm = c; d->global = tail; d->tail_first = 0; d->lrep = nlevels;
+    d->splits.resize((size_t)nlevels + 1);
+    d->lv.resize((size_t)nlevels);
+    for (int l = 0; l < nlevels; ++l) {
+        d->splits[(size_t)l] = a[l]->rsplit;
+        for (famg_dmat *m : {a[l], r[l], p[l]}) { m->refs.fetch_add(1); d->keep.push_back(m); }
+        d->lv[(size_t)l].A = &a[l]->part[0]; d->lv[(size_t)l].R = &r[l]->part[0]; d->lv[(size_t)l].P = &p[l]->part[0];
+    }
+    if (nlevels > 0) d->splits[(size_t)nlevels] = r[nlevels - 1]->rsplit;
+    else { d->splits[0].assign((size_t)nr + 1, tail->lv[0].a->nrows); d->splits[0][0] = 0; }
+    famg_status st = dist_mg_finish(d, diag_kind, omega, nullptr);
+    if (st != FAMG_OK) { dist_free(d); return st; }
     *out = d;
     return FAMG_OK;
 }
@@ -1031,7 +831,7 @@ famg_status famg_dist_spmv_dev(famg_dist_mg *d, famg_vec *y_local, const famg_ve
     if (d->lrep == 0) FAMG_FAIL(FAMG_ERR_UNSUPPORTED, "level 0 is replicated on this configuration");
     double *xe = d->pcg + 5 * d->pcg_ld;
     FAMG_TRY(vec_copy(ctx, xe, d->pcg_ld, x_local->p, x_local->ld, x_local->nrows, 1));
-    return dist_apply(d->comm, d->lv[0].A, EPI_SPMV, xe, y_local->p, nullptr, nullptr, nullptr, nullptr);
+    return dist_apply(d->comm, *d->lv[0].A, EPI_SPMV, xe, y_local->p, nullptr, nullptr, nullptr, nullptr);
 }
 
 famg_status famg_dist_pcg_solve_dev(famg_dist_mg *d, famg_vec *x, const famg_vec *b, double rel_tol, double abs_tol,
@@ -1046,7 +846,7 @@ famg_status famg_dist_pcg_solve_dev(famg_dist_mg *d, famg_vec *x, const famg_vec
     const int64_t n = x->nrows, ld = d->pcg_ld;
     info->iter_count = 0; info->abs_residual = 0; info->rel_residual = 0;
     double *r = d->pcg, *p = d->pcg + ld, *z = d->pcg + 2 * ld, *q = d->pcg + 3 * ld, *xe = d->pcg + 5 * ld;
-    DistOp &A = d->lv[0].A;
+    DistOp &A = *d->lv[0].A;
     enum { S_BB = 0, S_RR = 1, S_PTQ = 2, S_RTZ_A = 3, S_RTZ_B = 4 };
     double h[8];
     FAMG_TRY(vec_dot(ctx, b->p, b->p, n, S_BB));

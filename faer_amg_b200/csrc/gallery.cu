@@ -12,19 +12,21 @@
 
 namespace famg {
 
-__global__ void g7_count_kernel(int nx, int ny, int nz, int *__restrict__ cnt) {
-    const long long n = (long long)nx * ny * nz;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+// All four kernels work on the rows [row0, row0 + n) of the global operator (a z-slab for the
+// distributed generators; the whole grid otherwise); cnt / rp are indexed by the local row.
+__global__ void g7_count_kernel(int nx, int ny, int nz, long long row0, long long n, int *__restrict__ cnt) {
+    const long long li = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= n) return;
+    const long long i = row0 + li;
     const int x = (int)(i % nx), y = (int)((i / nx) % ny), z = (int)(i / ((long long)nx * ny));
-    cnt[i] = 1 + (x > 0) + (x + 1 < nx) + (y > 0) + (y + 1 < ny) + (z > 0) + (z + 1 < nz);
+    cnt[li] = 1 + (x > 0) + (x + 1 < nx) + (y > 0) + (y + 1 < ny) + (z > 0) + (z + 1 < nz);
 }
-__global__ void g7_fill_kernel(int nx, int ny, int nz, const int *__restrict__ rp, int *__restrict__ col, double *__restrict__ val) {
-    const long long n = (long long)nx * ny * nz;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+__global__ void g7_fill_kernel(int nx, int ny, int nz, long long row0, long long n, const int *__restrict__ rp, int *__restrict__ col, double *__restrict__ val) {
+    const long long li = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= n) return;
+    const long long i = row0 + li;
     const int x = (int)(i % nx), y = (int)((i / nx) % ny), z = (int)(i / ((long long)nx * ny));
-    int q = rp[i];
+    int q = rp[li];
     const int ii = (int)i, sxy = nx * ny;
     if (z > 0) { col[q] = ii - sxy; val[q++] = -1.0; }
     if (y > 0) { col[q] = ii - nx; val[q++] = -1.0; }
@@ -35,23 +37,23 @@ __global__ void g7_fill_kernel(int nx, int ny, int nz, const int *__restrict__ r
     if (z + 1 < nz) { col[q] = ii + sxy; val[q++] = -1.0; }
 }
 
-__global__ void g27_count_kernel(int nx, int ny, int nz, int *__restrict__ cnt) {
-    const long long n = (long long)nx * ny * nz;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+__global__ void g27_count_kernel(int nx, int ny, int nz, long long row0, long long n, int *__restrict__ cnt) {
+    const long long li = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= n) return;
+    const long long i = row0 + li;
     const int x = (int)(i % nx), y = (int)((i / nx) % ny), z = (int)(i / ((long long)nx * ny));
     const int cx = 1 + (x > 0) + (x + 1 < nx), cy = 1 + (y > 0) + (y + 1 < ny), cz = 1 + (z > 0) + (z + 1 < nz);
-    cnt[i] = cx * cy * cz;
+    cnt[li] = cx * cy * cz;
 }
 __device__ __forceinline__ double g27_k(int d) { return d == 0 ? 2.0 : -1.0; }
 __device__ __forceinline__ double g27_m(int d) { return d == 0 ? 4.0 / 6.0 : 1.0 / 6.0; }
-__global__ void g27_fill_kernel(int nx, int ny, int nz, double ey, double ez, const int *__restrict__ rp, int *__restrict__ col,
-                                double *__restrict__ val) {
-    const long long n = (long long)nx * ny * nz;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+__global__ void g27_fill_kernel(int nx, int ny, int nz, long long row0, long long n, double ey, double ez, const int *__restrict__ rp,
+                                int *__restrict__ col, double *__restrict__ val) {
+    const long long li = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= n) return;
+    const long long i = row0 + li;
     const int x = (int)(i % nx), y = (int)((i / nx) % ny), z = (int)(i / ((long long)nx * ny));
-    int q = rp[i];
+    int q = rp[li];
     for (int dz = -1; dz <= 1; ++dz) {
         if (z + dz < 0 || z + dz >= nz) continue;
         for (int dy = -1; dy <= 1; ++dy) {
@@ -68,18 +70,23 @@ __global__ void g27_fill_kernel(int nx, int ny, int nz, double ey, double ez, co
     }
 }
 
-static famg_status gallery_build(famg_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, int stencil, double ey, double ez, famg_csr **out) {
+// rows of the planes [z0, z1) (global column ids): the whole operator for (0, nz)
+static famg_status gallery_build(famg_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, int stencil, double ey, double ez, famg_csr **out,
+                                 int64_t z0 = 0, int64_t z1 = -1) {
     *out = nullptr;
     if (nx <= 0 || ny <= 0 || nz <= 0) FAMG_FAIL(FAMG_ERR_INVALID, "grid dimensions must be positive");
-    const int64_t n = nx * ny * nz;
-    if (n >= INT32_MAX) FAMG_FAIL(FAMG_ERR_UNSUPPORTED, "grid too large for 32-bit indices");
+    if (z1 < 0) z1 = nz;
+    if (z0 < 0 || z0 > z1 || z1 > nz) FAMG_FAIL(FAMG_ERR_INVALID, "bad plane range [%lld, %lld) of %lld", (long long)z0, (long long)z1, (long long)nz);
+    const int64_t ncols = nx * ny * nz;
+    if (ncols >= INT32_MAX) FAMG_FAIL(FAMG_ERR_UNSUPPORTED, "grid too large for 32-bit indices");
+    const int64_t row0 = z0 * nx * ny, n = (z1 - z0) * nx * ny;
     int *cnt = nullptr, *rp = nullptr;
     FAMG_TRY(dev_alloc(&cnt, n + 1));
     famg_status st = dev_alloc(&rp, n + 1);
-    const unsigned grid = (unsigned)ceil_div(n, 256);
+    const unsigned grid = (unsigned)std::max<int64_t>(ceil_div(n, 256), 1);
     if (st == FAMG_OK) {
-        if (stencil == 7) g7_count_kernel<<<grid, 256, 0, ctx->stream>>>((int)nx, (int)ny, (int)nz, cnt);
-        else g27_count_kernel<<<grid, 256, 0, ctx->stream>>>((int)nx, (int)ny, (int)nz, cnt);
+        if (stencil == 7) g7_count_kernel<<<grid, 256, 0, ctx->stream>>>((int)nx, (int)ny, (int)nz, row0, n, cnt);
+        else g27_count_kernel<<<grid, 256, 0, ctx->stream>>>((int)nx, (int)ny, (int)nz, row0, n, cnt);
         count_launch(ctx);
         st = exclusive_scan_i32(ctx, cnt, rp, n);
     }
@@ -90,11 +97,11 @@ static famg_status gallery_build(famg_ctx *ctx, int64_t nx, int64_t ny, int64_t 
         else if (total < 0) { set_error("gallery: more than 2^31 non-zeros"); st = FAMG_ERR_UNSUPPORTED; }
     }
     famg_csr *a = nullptr;
-    if (st == FAMG_OK) st = csr_alloc(ctx, n, n, total, &a);
+    if (st == FAMG_OK) st = csr_alloc(ctx, n, ncols, total, &a);
     if (st == FAMG_OK) {
         cudaMemcpyAsync(a->row_ptr, rp, sizeof(int) * (n + 1), cudaMemcpyDeviceToDevice, ctx->stream);
-        if (stencil == 7) g7_fill_kernel<<<grid, 256, 0, ctx->stream>>>((int)nx, (int)ny, (int)nz, a->row_ptr, a->col, a->val);
-        else g27_fill_kernel<<<grid, 256, 0, ctx->stream>>>((int)nx, (int)ny, (int)nz, ey, ez, a->row_ptr, a->col, a->val);
+        if (stencil == 7) g7_fill_kernel<<<grid, 256, 0, ctx->stream>>>((int)nx, (int)ny, (int)nz, row0, n, a->row_ptr, a->col, a->val);
+        else g27_fill_kernel<<<grid, 256, 0, ctx->stream>>>((int)nx, (int)ny, (int)nz, row0, n, ey, ez, a->row_ptr, a->col, a->val);
         count_launch(ctx);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { set_error("gallery: %s", cudaGetErrorString(e)); st = FAMG_ERR_CUDA; }
@@ -186,6 +193,19 @@ famg_status famg_gallery_g27(famg_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, 
     if (!ctx || !out) FAMG_FAIL(FAMG_ERR_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(ctx->device));
     return gallery_build(ctx, nx, ny, nz, 27, eps_y, eps_z, out);
+}
+
+famg_status famg_gallery_g7_slab(famg_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, int64_t z0, int64_t z1, famg_csr **out) {
+    if (!ctx || !out) FAMG_FAIL(FAMG_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return gallery_build(ctx, nx, ny, nz, 7, 0.0, 0.0, out, z0, z1);
+}
+
+famg_status famg_gallery_g27_slab(famg_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, double eps_y, double eps_z, int64_t z0, int64_t z1,
+                                  famg_csr **out) {
+    if (!ctx || !out) FAMG_FAIL(FAMG_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return gallery_build(ctx, nx, ny, nz, 27, eps_y, eps_z, out, z0, z1);
 }
 
 // Deterministic geometric aggregates of a lexicographic nx*ny*nz grid (i = x + nx*(y + ny*z)): bx x by x bz

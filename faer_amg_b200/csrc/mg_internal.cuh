@@ -12,8 +12,9 @@ struct MgLevel {
 
 struct GraphKey {
     const void *out, *rhs; int64_t ldo, ldr; int k, mu, nu;
+    int64_t epoch;  // famg_ctx::option_epoch at capture: a changed kernel selection never replays an old graph
     bool operator<(const GraphKey &o) const {
-        return std::tie(out, rhs, ldo, ldr, k, mu, nu) < std::tie(o.out, o.rhs, o.ldo, o.ldr, o.k, o.mu, o.nu);
+        return std::tie(out, rhs, ldo, ldr, k, mu, nu, epoch) < std::tie(o.out, o.rhs, o.ldo, o.ldr, o.k, o.mu, o.nu, o.epoch);
     }
 };
 struct GraphEntry { cudaGraphExec_t exec = nullptr; int64_t launches = 0; };

@@ -107,7 +107,7 @@ famg_status mg_apply_dev_raw(famg_mg *mg, double *out, int64_t ldo, const double
     famg_ctx *ctx = mg->ctx;
     FAMG_TRY(mg_ensure_workspace(mg, k));
     if (!mg->use_graph) return mg_cycle(mg, 0, out, ldo, rhs, ldr, k, true);
-    GraphKey key{out, rhs, ldo, ldr, k, mg->mu, mg->nu};
+    GraphKey key{out, rhs, ldo, ldr, k, mg->mu, mg->nu, ctx->option_epoch.load()};
     auto it = mg->graphs.find(key);
     if (it == mg->graphs.end()) {
         if (mg->graphs.size() > 64) {  // bounded cache

@@ -42,6 +42,8 @@ famg_status famg_composite_push(famg_composite *c, int pc_kind, void *component)
     if (!c || !component) FAMG_FAIL(FAMG_ERR_INVALID, "null argument");
     if (pc_kind != FAMG_PC_SMOOTHER && pc_kind != FAMG_PC_MG && pc_kind != FAMG_PC_COMPOSITE) FAMG_FAIL(FAMG_ERR_INVALID, "unknown component kind");
     if (component == (void *)c) FAMG_FAIL(FAMG_ERR_INVALID, "a composite cannot contain itself");
+    // components are retained (Arc semantics, like famg_mg's levels): a caller may drop its handle first
+    if (pc_kind == FAMG_PC_SMOOTHER) ((famg_smoother *)component)->refs.fetch_add(1);
     c->components.emplace_back(pc_kind, component);
     return FAMG_OK;
 }
@@ -53,6 +55,8 @@ famg_status famg_composite_len(const famg_composite *c, int64_t *n) {
 famg_status famg_composite_destroy(famg_composite *c) {
     if (!c) return FAMG_OK;
     cudaSetDevice(c->ctx->device);
+    for (auto &comp : c->components)
+        if (comp.first == FAMG_PC_SMOOTHER) smoother_release((famg_smoother *)comp.second);
     csr_release(c->a);
     delete c;
     return FAMG_OK;

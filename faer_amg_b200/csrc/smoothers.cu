@@ -51,9 +51,47 @@ __global__ void diag_l2_kernel(const int *__restrict__ row_ptr, const int *__res
     d[i] = 1.0 / s;
 }
 
-__global__ void diag_jacobi_kernel(const double *__restrict__ diag, int n, double omega, double *__restrict__ d) {
+__global__ void diag_jacobi_kernel(const double *diag, int n, double omega, double *d) {  // diag may alias d
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) d[i] = omega / diag[i];
+}
+
+// a_ii by linear search (row slabs of a distributed operator are not sorted by local column id)
+__global__ void diag_extract_linear_kernel(const int *__restrict__ row_ptr, const int *__restrict__ col, const double *__restrict__ val,
+                                           int n, double *__restrict__ diag, int *__restrict__ missing) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double v = 0.0; bool found = false;
+    for (int q = row_ptr[i]; q < row_ptr[i + 1]; ++q) if (col[q] == i) { v = val[q]; found = true; break; }
+    diag[i] = v;
+    if (!found) atomicAdd(missing, 1);
+}
+
+famg_status diag_from_rows(const famg_csr *a, int kind, double omega, double *d_out) {
+    famg_ctx *ctx = a->ctx;
+    const int n = (int)a->nrows;
+    if (n == 0) return FAMG_OK;
+    const unsigned grid = (unsigned)ceil_div(n, 256);
+    if (kind == FAMG_DIAG_L1) {
+        diag_l1_kernel<<<grid, 256, 0, ctx->stream>>>(a->row_ptr, a->val, n, d_out);
+        count_launch(ctx);
+        KERNEL_CHECK();
+        return FAMG_OK;
+    }
+    if (kind != FAMG_DIAG_JACOBI) FAMG_FAIL(FAMG_ERR_UNSUPPORTED, "distributed levels support the L1 and Jacobi diagonal smoothers");
+    int *missing = nullptr;
+    FAMG_TRY(pool_alloc(ctx, 256, (void **)&missing));
+    cudaMemsetAsync(missing, 0, sizeof(int), ctx->stream);
+    diag_extract_linear_kernel<<<grid, 256, 0, ctx->stream>>>(a->row_ptr, a->col, a->val, n, d_out, missing);
+    diag_jacobi_kernel<<<grid, 256, 0, ctx->stream>>>(d_out, n, omega, d_out);
+    count_launch(ctx, 2);
+    int h_missing = 0;
+    cudaError_t e = cudaMemcpyAsync(&h_missing, missing, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    pool_free(ctx, missing, 256);
+    if (e != cudaSuccess) FAMG_FAIL(FAMG_ERR_CUDA, "diag setup failed: %s", cudaGetErrorString(e));
+    if (h_missing) FAMG_FAIL(FAMG_ERR_NUMERIC, "matrix has %d rows without a diagonal entry", h_missing);
+    return FAMG_OK;
 }
 
 void smoother_release(famg_smoother *s) {
@@ -448,7 +486,7 @@ famg_status famg_smooth_dev(const famg_csr *a, const famg_smoother *s, famg_vec 
         }
     }
     if (st == FAMG_OK && cur != x->p) st = vec_copy(ctx, x->p, x->ld, cur, ldc, x->nrows, k);
-    famg_vec_destroy(t);  // synchronises the stream
+    famg_vec_destroy(t);  // returns the block to the context pool (stream-ordered reuse)
     famg_vec_destroy(t2);
     return st;
 }

@@ -256,12 +256,16 @@ __device__ void sg_row_fill(int i, int lane, const SgMat &a, const SgMat &b, int
         for (int t = lane; t < n; t += GROUP) { c_col[base + t] = list[t]; c_val[base + t] = vals[t]; }
     } else {
         // smooth_interpolation: scalar = w * (1/a_ii); v *= -scalar; then += P_ij where present
-        double dv = 0.0; bool found = false;
-        {
-            int lo = a0, hi = a1;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (a.col[mid] < i) lo = mid + 1; else hi = mid; }
-            if (lo < a1 && a.col[lo] == i) { dv = a.val[lo]; found = true; }
-        }
+        // The diagonal is searched linearly by the whole group: the rows of a distributed slab are
+        // renumbered to [owned | ghost] in place and are no longer sorted by (local) column id.
+        if (lane == 0) *cnt = -1;
+        group_sync<GROUP>();
+        for (int q = a0 + lane; q < a1; q += GROUP) if (a.col[q] == i) *cnt = q;
+        group_sync<GROUP>();
+        const int qd = *cnt;
+        const bool found = qd >= 0;
+        const double dv = found ? a.val[qd] : 0.0;
+        group_sync<GROUP>();
         if (lane == 0 && ep.enabled == 1 && (!found || !(dv > 1e-6))) atomicMax(ep.error_flag, 1);
         const double scalar = ep.omega * (1.0 / dv);
         const int p0 = ep.p.rp[i], p1 = ep.p.rp[i + 1];
@@ -529,13 +533,14 @@ __global__ void __launch_bounds__(256) sg_dense_kernel(SgArgs s, int ncols_b) {
             if (touched[j]) { s.c_col[pos] = j; s.c_val[pos] = acc[j]; ++pos; }
         return;
     }
-    // smooth_interpolation epilogue (see sg_row_fill)
-    double dv = 0.0; bool found = false;
-    {
-        int lo = a0, hi = a1;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (s.a.col[mid] < i) lo = mid + 1; else hi = mid; }
-        if (lo < a1 && s.a.col[lo] == i) { dv = s.a.val[lo]; found = true; }
-    }
+    // smooth_interpolation epilogue (see sg_row_fill; linear diagonal search for the same reason)
+    __shared__ int s_diag;
+    if (tid == 0) s_diag = -1;
+    __syncthreads();
+    for (int q = a0 + tid; q < a1; q += 256) if (s.a.col[q] == i) s_diag = q;
+    __syncthreads();
+    const bool found = s_diag >= 0;
+    const double dv = found ? s.a.val[s_diag] : 0.0;
     if (tid == 0 && s.ep.enabled == 1 && (!found || !(dv > 1e-6))) atomicMax(s.ep.error_flag, 1);
     const double scalar = s.ep.omega * (1.0 / dv);
     const int p0 = s.ep.p.rp[i], p1 = s.ep.p.rp[i + 1];
@@ -704,11 +709,15 @@ static famg_status sg_run_pass(famg_ctx *ctx, SgArgs base, const int *d_size, in
     return FAMG_OK;
 }
 
-famg_status spgemm_impl(const famg_csr *a, const famg_csr *b, const famg_csr *p_for_smoothing, double omega, famg_csr **out, int epi_kind = 1) {
+famg_status spgemm_impl(const famg_csr *a, const famg_csr *b, const famg_csr *p_for_smoothing, double omega, famg_csr **out, int epi_kind) {
     *out = nullptr;
     if (a->ncols != b->nrows) FAMG_FAIL(FAMG_ERR_INVALID, "spgemm: inner dimensions differ (%lld vs %lld)", (long long)a->ncols, (long long)b->nrows);
     famg_ctx *ctx = a->ctx;
     const int m = (int)a->nrows;
+    if (m == 0) {  // empty product: nothing to count, nothing to read back
+        FAMG_TRY(csr_alloc(ctx, 0, b->ncols, 0, out));
+        return csr_finalize_plan(*out);
+    }
     SgMat A{a->row_ptr, a->col, a->val}, B{b->row_ptr, b->col, b->val};
     // one pooled scratch block: ub | size | cls | perm | row_nnz(+1) | rp(+1) | counters(16)
     const size_t words = (size_t)6 * (m + 2) + 32;

@@ -468,10 +468,13 @@ static famg_status launch_one(SpmvKernelParams kp, int variant, int nrows1, int 
     if (variant == 2) {
         constexpr int CTAS = CB == 1 ? TMA_CTAS : 3;  // resident CTAs per SM (register budget of the column block)
         const int grid = std::max(1, std::min(nchunks, CTAS * num_sms - reserve_ctas));
-        static bool configured = false;  // per template instance
-        if (!configured) {
+        // the > 48 KB opt-in is a per-device attribute: one bit per device and template instance
+        static std::atomic<uint64_t> configured{0};
+        int dev = 0;
+        CUDA_TRY(cudaGetDevice(&dev));
+        if (!(configured.load(std::memory_order_relaxed) >> (dev & 63) & 1ull)) {
             CUDA_TRY(cudaFuncSetAttribute(spmv_tma_kernel<TPR, EPI, DOT, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM));
-            configured = true;
+            configured.fetch_or(1ull << (dev & 63), std::memory_order_relaxed);
         }
         spmv_tma_kernel<TPR, EPI, DOT, CB><<<grid, TMA_THREADS, TMA_SMEM, st>>>(kp, nchunks);
         *grid_out = grid;
@@ -601,11 +604,12 @@ famg_status famg_spmm(const famg_csr *a, double *out, int64_t ld_out, const doub
 }
 
 famg_status famg_time_kernel(const famg_csr *a, int which, int reps, int warmup, float *ms_avg) {
-    if (!a || !ms_avg || reps <= 0 || a->nrows != a->ncols) FAMG_FAIL(FAMG_ERR_INVALID, "bad argument (square operator required)");
+    if (!a || !ms_avg || reps <= 0 || which < 0 || which > 3) FAMG_FAIL(FAMG_ERR_INVALID, "bad argument");
+    if (which == 2 && a->nrows != a->ncols) FAMG_FAIL(FAMG_ERR_INVALID, "the smoother sweep needs a square operator");
     famg_ctx *ctx = a->ctx;
     CUDA_TRY(cudaSetDevice(ctx->device));
     famg_vec *x = nullptr, *y = nullptr, *b = nullptr, *d = nullptr;
-    FAMG_TRY(famg_vec_create(ctx, a->nrows, 1, &x));
+    FAMG_TRY(famg_vec_create(ctx, a->ncols, 1, &x));
     famg_status st = famg_vec_create(ctx, a->nrows, 1, &y);
     if (st == FAMG_OK) st = famg_vec_create(ctx, a->nrows, 1, &b);
     if (st == FAMG_OK) st = famg_vec_create(ctx, a->nrows, 1, &d);
@@ -616,7 +620,7 @@ famg_status famg_time_kernel(const famg_csr *a, int which, int reps, int warmup,
     if (st == FAMG_OK) {
         cudaEventCreate(&e0); cudaEventCreate(&e1);
         SpmvArgs s; s.a = a; s.x = x->p; s.ldx = x->ld; s.y = y->p; s.ldy = y->ld; s.b = b->p; s.ldb = b->ld; s.d = d->p; s.k = 1;
-        s.epi = which == 0 ? EPI_SPMV : which == 1 ? EPI_RESID : EPI_SMOOTH;
+        s.epi = which == 0 ? EPI_SPMV : which == 1 ? EPI_RESID : which == 2 ? EPI_SMOOTH : EPI_ADD;
         for (int i = 0; i < warmup && st == FAMG_OK; ++i) st = spmv_launch(s);
         cudaEventRecord(e0, ctx->stream);
         for (int i = 0; i < reps && st == FAMG_OK; ++i) st = spmv_launch(s);

@@ -133,10 +133,12 @@ static famg_status launch_gram(cudaStream_t st, int grid, const double *x, int64
 template <int KB>
 static famg_status launch_rinv(cudaStream_t st, int grid, double *x, int64_t ld, int64_t n, int k, const double *d_rinv) {
     constexpr int SMEM_MAX = (int)(sizeof(double) * (QR_TILE * QR_LDT + QR_MAXK * QR_MAXK));
-    static bool configured = false;  // per template instance
-    if (!configured) {
+    static std::atomic<uint64_t> configured{0};  // per template instance, one bit per device (the opt-in is a per-device attribute)
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (!(configured.load(std::memory_order_relaxed) >> (dev & 63) & 1ull)) {
         CUDA_TRY(cudaFuncSetAttribute(apply_rinv_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
-        configured = true;
+        configured.fetch_or(1ull << (dev & 63), std::memory_order_relaxed);
     }
     const size_t smem = sizeof(double) * ((size_t)QR_TILE * QR_LDT + (size_t)k * QR_MAXK);
     apply_rinv_kernel<KB><<<grid, QR_THREADS, smem, st>>>(x, ld, n, k, d_rinv);

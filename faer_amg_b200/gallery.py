@@ -30,6 +30,20 @@ def diffusion27(ctx: Context, nx: int, ny: Optional[int] = None, nz: Optional[in
     return SparseRowMat(ctx, h)
 
 
+def poisson7_slab(ctx: Context, nx: int, ny: int, nz: int, z0: int, z1: int) -> SparseRowMat:
+    """Rows of the planes [z0, z1) of G7 with global column ids (one rank's slab of the partitioned operator)."""
+    h = vp()
+    call("famg_gallery_g7_slab", ctx._h, nx, ny, nz, z0, z1, C.byref(h))
+    return SparseRowMat(ctx, h)
+
+
+def diffusion27_slab(ctx: Context, nx: int, ny: int, nz: int, z0: int, z1: int, eps_y: float = 1.0, eps_z: float = 1e-2) -> SparseRowMat:
+    """Rows of the planes [z0, z1) of G27 with global column ids."""
+    h = vp()
+    call("famg_gallery_g27_slab", ctx._h, nx, ny, nz, float(eps_y), float(eps_z), z0, z1, C.byref(h))
+    return SparseRowMat(ctx, h)
+
+
 def poisson1d(ctx: Context, n_elements: int) -> SparseRowMat:
     """make_finite_difference (examples/simple_geometric.rs:96-113)."""
     h = 1.0 / n_elements

@@ -113,11 +113,13 @@ class MultigridConfig:
             return BlockSmoother.new(op, hierarchy.get_partition(level))
         raise ValueError(self.smoother)
 
-    def build(self, hierarchy) -> Multigrid:
+    def build(self, hierarchy, is_tail: bool = False) -> Multigrid:
+        """``is_tail``: the hierarchy is the replicated tail of a distributed one -- its last level is the
+        coarsest level of the whole hierarchy even when it is the tail's only level."""
         level_count = hierarchy.levels()
         smoothers = []
         for level in range(level_count):  # multigrid.rs:105-119
-            if level + 1 == level_count and self.coarse_solver is not None and level_count > 1:
+            if level + 1 == level_count and self.coarse_solver is not None and (level_count > 1 or is_tail):
                 smoothers.append(CoarseSolverKind.build_from_sparse(self.coarse_solver, hierarchy.get_mat_ref(level)))
             else:
                 smoothers.append(self._level_smoother(hierarchy, level))

@@ -70,7 +70,7 @@ def conjugate_gradient(dst: np.ndarray, precond, mat, rhs, params: CgParams) -> 
     return.  Raises :class:`CgError` like the reference returns ``Err``."""
     m = _mat(mat)
     b = np.ascontiguousarray(np.asarray(rhs, dtype=np.float64).reshape(-1))
-    assert dst.dtype == np.float64 and dst.flags.c_contiguous or dst.flags.f_contiguous
+    assert dst.dtype == np.float64 and (dst.flags.c_contiguous or dst.flags.f_contiguous)
     x = dst.reshape(-1)
     kind, h = _pc(precond)
     info = CgInfoStruct()

@@ -95,6 +95,12 @@ famg_status famg_gallery_g7(famg_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, f
 famg_status famg_gallery_g27(famg_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, double eps_y,
                              double eps_z, famg_csr **out);
 
+/* rows of the planes [z0, z1) of the same operators, with global column ids: one rank's slab of a
+ * row-partitioned operator generated in place (nothing global is ever materialised) */
+famg_status famg_gallery_g7_slab(famg_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, int64_t z0, int64_t z1, famg_csr **out);
+famg_status famg_gallery_g27_slab(famg_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, double eps_y, double eps_z, int64_t z0,
+                                  int64_t z1, famg_csr **out);
+
 /* ---- dense multivectors on the device ----------------------------------------------------- */
 famg_status famg_vec_create(famg_ctx *ctx, int64_t nrows, int64_t ncols, famg_vec **out);
 famg_status famg_vec_destroy(famg_vec *v);
@@ -229,7 +235,8 @@ famg_status famg_vec_coldot(const famg_vec *x, const famg_vec *y, double *out);
 /* Symmetric multiplicative combination of several preconditioners around one operator (composite.rs:66-83):
  *   out = 0; ws = rhs; for c in components reversed, then components[1..]: ws <- c^-1 ws; out += ws; ws = rhs - A out
  * Device-resident: the `rhs - A out` step is the fused residual kernel.  Components are (pc_kind, handle)
- * pairs -- smoothers and multigrids -- borrowed: the caller keeps them alive (the Rust side holds Arcs).
+ * pairs: smoothers are retained by the composite; multigrid / composite components are borrowed and must
+ * outlive it (the Rust side holds the Arcs).
  * Usable wherever a (pc_kind, precond) pair is accepted: famg_pcg_solve*, famg_stationary_solve,
  * famg_smooth_vector_pc_dev (the adaptive driver's test loop, adaptivity.rs:108-114). */
 typedef struct famg_composite famg_composite;
@@ -286,7 +293,9 @@ famg_status famg_pcg_solve_dev(const famg_csr *a, int pc_kind, void *precond, fa
 famg_status famg_stationary_solve(const famg_csr *a, int pc_kind, void *precond, double *x,
                                   const double *b, double rel_tol, int64_t max_iters, int64_t *iters);
 
-/* ---- multi-GPU: 1-D row partition, NCCL halo exchange ------------------------- */
+/* ---- multi-GPU: 1-D row partition.  Data path: peer-memory (CUDA IPC over NVLink) halo
+ * exchange and small collectives; NCCL bootstraps the job, carries the setup-time exchanges and is the
+ * fallback data path when a peer cannot be mapped. ------------------------------------------------- */
 #define FAMG_UNIQUE_ID_BYTES 128
 famg_status famg_comm_unique_id(void *id_bytes /* 128 */);
 famg_status famg_comm_create(famg_ctx *ctx, int nranks, int rank, const void *id_bytes, famg_comm **out);
@@ -310,15 +319,65 @@ famg_status famg_dist_pcg_solve_dev(famg_dist_mg *d, famg_vec *x_local, const fa
 famg_status famg_dist_spmv_dev(famg_dist_mg *d, famg_vec *y_local, const famg_vec *x_local);
 famg_status famg_dist_mg_apply_dev(famg_dist_mg *d, famg_vec *out_local, const famg_vec *rhs_local);
 
+/* ---- distributed hierarchy construction (SURVEY 8(e) "RAP"; Hierarchy::coarsen, hierarchy.rs:190-248, on row
+ * slabs).  Every rank builds only its rows of P = (I - w D^-1 A) P0, A P and A_c = R (A P), fetching the off-rank
+ * rows of P0 / P / AP it needs; nothing global is materialised.  A famg_dmat is a row-partitioned sparse matrix:
+ * one slab per virtual rank hosted by the calling process -- one with a process per GPU; all `nranks` of them for
+ * a communicator made by famg_comm_create_sim, which runs the same construction inside one process on one GPU
+ * (exchanges become device copies; setup only, it cannot run the distributed cycle).  Per-rank array arguments
+ * below have one entry per hosted virtual rank (famg_comm_dims: nlocal). */
+typedef struct famg_dmat famg_dmat;
+famg_status famg_comm_create_sim(famg_ctx *ctx, int nranks, famg_comm **out);
+famg_status famg_comm_dims(const famg_comm *c, int *nranks, int *rank, int *nlocal);
+/* host all-gather of per-rank pieces (rank order): out[li] receives sum(counts) doubles */
+famg_status famg_comm_allgatherv_f64(famg_comm *c, const double *const *local, const int64_t *counts, double *const *out);
+/* Row slabs with GLOBAL column ids -> distributed matrix (row offsets follow from the slab heights, rank order).
+ * col_split: nranks + 1 column ownership boundaries, NULL for a square operator (same as the row split).
+ * The slabs are taken over: famg_dmat_finalize renumbers their columns in place. */
+famg_status famg_dmat_create(famg_comm *c, famg_csr *const *slabs, int64_t ncols_global, const int64_t *col_split, famg_dmat **out);
+/* collective: builds the halo plan (ghost columns, per-peer send lists) and renumbers the columns of every slab to
+ * [owned | ghost] without reordering the entries of a row; replicated_cols != 0 declares the consumer vector
+ * replicated instead (global column ids kept, no halo) */
+famg_status famg_dmat_finalize(famg_dmat *m, int replicated_cols);
+famg_status famg_dmat_retain(famg_dmat *m);
+famg_status famg_dmat_destroy(famg_dmat *m);
+/* global shape and the nranks + 1 row / column ownership boundaries (any pointer may be NULL) */
+famg_status famg_dmat_info(const famg_dmat *m, int64_t *nrows, int64_t *ncols, int64_t *row_split, int64_t *col_split);
+/* slab of hosted rank `local_index`; global_cols != 0: a copy with global column ids (verification, download) */
+famg_status famg_dmat_local(const famg_dmat *m, int local_index, int global_cols, famg_csr **out);
+/* collective: the whole matrix replicated on every rank (out: one handle per hosted rank) -- the transition to
+ * the replicated coarse tail */
+famg_status famg_dmat_gather(const famg_dmat *m, famg_csr **out);
+/* One coarsening step (smoothed_aggregation, interpolation/mod.rs:730-836; block_size 1, one near-null vector):
+ * a: finalized square operator.  Per hosted rank: its own aggregates over LOCAL row ids (n_aggs, agg_ptr,
+ * agg_nodes -- aggregates never straddle ranks; coarse ids are assigned rank after rank), the local slice of the
+ * near-null vector, and coarse_nn (out, n_aggs doubles).  Returns P (rows of a, global coarse column ids, not
+ * finalized), R (finalized over a's split) and A_c (global column ids, not finalized). */
+famg_status famg_dist_coarsen(famg_dmat *a, const int64_t *n_aggs, const uint64_t *const *agg_ptr, const uint64_t *const *agg_nodes,
+                              const double *const *near_null, int smoothing_steps, double omega, famg_dmat **p, famg_dmat **r,
+                              famg_dmat **a_coarse, double *const *coarse_nn);
+/* hierarchy.rs:217-228 on a finalized distributed level: `iters`-step L1 stationary iteration on the near-null
+ * slices (in place, host), then the thin Q of the single column with the sum of squares chained through the ranks
+ * in order -- bit-identical to the undistributed build */
+famg_status famg_dist_smooth_near_null(famg_dmat *a, int iters, double *const *near_null);
+/* Distributed Multigrid + PCG from level-wise distributed operators: a[l], r[l], p[l] (l < nlevels; all finalized,
+ * p[nlevels-1] with replicated columns) and the replicated Multigrid `tail` of the remaining levels (borrowed).
+ * diag_kind: FAMG_DIAG_L1 | FAMG_DIAG_JACOBI smoother of the distributed levels. */
+famg_status famg_dist_mg_create_levels(famg_comm *c, int nlevels, famg_dmat *const *a, famg_dmat *const *r, famg_dmat *const *p,
+                                       int diag_kind, double omega, famg_mg *tail, famg_dist_mg **out);
+
 /* ---- instrumentation ---------------------------------------------------------------------- */
 /* tuning knobs for A/B measurements: "spmv_variant" (1 = one staged chunk per CTA, 2 = persistent
- * TMA-fed pipeline), "tma_min_rows" (smallest operator the persistent kernel is used for) */
+ * TMA-fed pipeline), "tma_min_rows" (smallest operator the persistent kernel is used for), "spmm_cb"
+ * (right-hand sides per row walk for k > 1: 1 | 2).  Changing an option invalidates captured cycle graphs.
+ * One solve at a time per context: PCG work vectors and reduction scratch are context-owned. */
 famg_status famg_ctx_set_option(famg_ctx *ctx, const char *key, int64_t value);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 famg_status famg_ctx_launch_count(const famg_ctx *ctx, int64_t *count);
 /* time `reps` back-to-back launches of one fused kernel class with CUDA events on the context
- * stream; returns average milliseconds per launch.  which: 0 SpMV y=Ax, 1 residual,
- * 2 fused diagonal smoother sweep.  Vectors are internal scratch (values irrelevant). */
+ * stream; returns average milliseconds per launch.  which: 0 SpMV y=Ax, 1 residual, 2 fused diagonal
+ * smoother sweep (square operators), 3 y += A x (prolongation-correct).  Rectangular operators are accepted
+ * for 0, 1 and 3.  Vectors are internal scratch (values irrelevant). */
 famg_status famg_time_kernel(const famg_csr *a, int which, int reps, int warmup, float *ms_avg);
 
 #ifdef __cplusplus

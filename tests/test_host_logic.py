@@ -133,3 +133,36 @@ def test_utils_convergence_factor_and_symmetry_test_logic():
     assert err < 1e-9
     ns = a.copy(); ns[0, 5] += 1.0
     assert symmetry_test(Op(ns), test_dim=4, seed=2)[0] > 1e-3
+
+
+def test_dist_geometric_partitioner_matches_the_global_partition():
+    """Every rank's local boxes, concatenated in rank order, are the global boxes (aggregates never
+    straddle ranks), level after level."""
+    from faer_amg_b200.distributed import DistGeometricPartitioner, fine_plane_splits
+    from faer_amg_b200.partitioners import geometric_partition
+    for dims, nranks in [((8, 6, 16), 4), ((5, 7, 24), 3), ((4, 4, 64), 8), ((6, 6, 9), 1)]:
+        dp = DistGeometricPartitioner(dims)
+        rs = fine_plane_splits(dims, nranks)
+        level = 0
+        while True:
+            d = dp.level_dims(level)
+            gpart, coarse = geometric_partition(d)
+            plane = d[0] * d[1]
+            ptr, nodes, nxt = [0], [], [0]
+            try:
+                for r in range(nranks):
+                    if rs[r + 1] == rs[r]:
+                        nxt.append(nxt[-1]); continue
+                    lp = dp.local(level, int(rs[r]), int(rs[r + 1]))
+                    nodes.append(lp.agg_nodes + int(rs[r]))
+                    ptr.extend((lp.agg_ptr[1:] + len(np.concatenate(nodes[:-1])) if len(nodes) > 1 else lp.agg_ptr[1:]).tolist())
+                    nxt.append(nxt[-1] + lp.naggs())
+            except ValueError:
+                break  # slabs no longer hold whole boxes: this level would be replicated
+            assert np.array_equal(np.asarray(ptr), gpart.agg_ptr), (dims, nranks, level)
+            assert np.array_equal(np.concatenate(nodes), gpart.agg_nodes), (dims, nranks, level)
+            rs = np.asarray(nxt, dtype=np.int64)
+            level += 1
+            if int(np.prod(coarse)) <= 8:
+                break
+        assert level >= 1, (dims, nranks)
