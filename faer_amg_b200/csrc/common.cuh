@@ -143,6 +143,17 @@ constexpr int CSR_PAD = 16;  // elements of slack after col/val so aligned 128-b
 
 famg_status csr_alloc(famg_ctx *ctx, int64_t nrows, int64_t ncols, int64_t nnz, famg_csr **out);
 famg_status csr_finalize_plan(famg_csr *a);  // row statistics -> threads-per-row
+#ifndef FAMG_TPR_FILL
+#define FAMG_TPR_FILL 8.9
+#endif
+// threads per row from the average row length (the rule csr_finalize_plan applies).  The slabs of a
+// distributed operator use the GLOBAL average, so that every rank walks its rows with the same lane
+// split -- and therefore the same summation order -- as the undistributed operator.
+inline int tpr_for_avg(double avg_row_nnz) {
+    int tpr = 1;
+    while (tpr < 32 && avg_row_nnz > FAMG_TPR_FILL * tpr) tpr <<= 1;
+    return tpr;
+}
 void csr_release(famg_csr *a);
 void smoother_release(famg_smoother *s);
 famg_status vec_wrap(famg_ctx *ctx, double *p, int64_t nrows, int64_t ncols, int64_t ld, famg_vec *out);
@@ -168,7 +179,8 @@ struct SpmvArgs {
     const double *b = nullptr; int64_t ldb = 0;  // rhs (RESID, SMOOTH)
     const double *d = nullptr;                   // diagonal (SMOOTH, SI, EPROP)
     int k = 1;
-    double *dot_partials = nullptr;              // k == 1: per-CTA partial of sum_i x[i]*(A x)[i]
+    double *dot_partials = nullptr;              // k == 1: per-CTA partial of sum_i x[i]*(A x)[i] (EPI_SPMV) or of
+                                                 // sum_i b[i]*x'[i] (EPI_SMOOTH: PCG's r.z from the cycle's last sweep)
     int row_begin = 0, row_end = -1;             // row range (distributed interior/boundary split)
     int row2_begin = 0, row2_end = 0;            // optional second range handled by the same launch
     int reserve_ctas = 0;                        // leave this many CTA slots free (room for NCCL kernels)
@@ -188,6 +200,9 @@ famg_status reduce_partials(famg_ctx *ctx, const double *partials, int64_t count
 // x += alpha p; r -= alpha q; partial ||r||^2 -> slot_rr   with alpha = s[num]/s[den]
 famg_status pcg_update_xr(famg_ctx *ctx, double *x, double *r, const double *p, const double *q, int64_t n,
                           int slot_num, int slot_den, int slot_rr);
+// the same, leaving the per-CTA partials of ||r||^2 in ctx->d_partials (*num_partials of them) for a fused reduction
+famg_status pcg_update_xr_partials(famg_ctx *ctx, double *x, double *r, const double *p, const double *q, int64_t n, int slot_num,
+                                   int slot_den, int *num_partials);
 // p = z + beta p with beta = s[num]/s[den]
 famg_status pcg_update_p(famg_ctx *ctx, double *p, const double *z, int64_t n, int slot_num, int slot_den);
 famg_status vec_add_inplace(famg_ctx *ctx, double *x, const double *y, int64_t n);  // x += y

@@ -197,12 +197,7 @@ famg_status csr_finalize_plan(famg_csr *a) {
     // threads-per-row: each thread should own <= ~9 staged entries so one chunk of 256/tpr rows
     // fits a pipeline stage of 2304 non-zeros (spmv.cu).  Row-length statistics pick scalar-, sub-warp- or
     // warp-per-row.
-    int tpr = 1;
-#ifndef FAMG_TPR_FILL
-#define FAMG_TPR_FILL 8.9
-#endif
-    while (tpr < 32 && a->avg_row_nnz > FAMG_TPR_FILL * tpr) tpr <<= 1;
-    a->tpr = tpr;
+    a->tpr = tpr_for_avg(a->avg_row_nnz);
     return FAMG_OK;
 }
 

@@ -197,13 +197,49 @@ __global__ void __launch_bounds__(256) p2p_exchange_kernel(const P2PPlanDev pl, 
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < pl.nghost; j += stride) tail[j] = __ldcg(src + j);
 }
 
-static famg_status p2p_exchange(famg_comm *cm, const HaloPlan &h, double *x_ext) {
+static famg_status p2p_exchange(famg_comm *cm, const HaloPlan &h, double *x_ext, cudaStream_t st = nullptr) {
     const int work = std::max(h.total_send, h.nghost);
     const int grid = std::max(1, std::min(64, (work + 1023) / 1024));
-    p2p_exchange_kernel<<<grid, 256, 0, cm->ctx->stream>>>(h.dev, x_ext, h.nloc, h.d_send_idx);
+    p2p_exchange_kernel<<<grid, 256, 0, st ? st : cm->ctx->stream>>>(h.dev, x_ext, h.nloc, h.d_send_idx);
     count_launch(cm->ctx);
     KERNEL_CHECK();
     return FAMG_OK;
+}
+
+// sum of `count` per-CTA partials (fixed order) and its sum over the ranks, in one launch: scalars[slot]
+__global__ void __launch_bounds__(1024) p2p_reduce_allreduce_kernel(const P2PCollDev c, const double *__restrict__ partials, int count,
+                                                                    double *__restrict__ scalars, int slot) {
+    __shared__ double s_red[32];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < count; i += 1024) acc += partials[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    double mine = 0.0;
+    for (int w = 0; w < 32; ++w) mine += s_red[w];  // every lane of warp 0 forms the same local sum
+    const unsigned long long e = *c.ar_epoch + 1ull;
+    const int par = (int)(e & 1ull);
+    __syncwarp();
+    if (lane < c.nranks) {
+        c.ar_rslots[par][lane][c.rank * P2P_AR_WIDTH] = mine;  // lane == rank: my own arena
+        __threadfence_system();
+        st_release_sys(c.ar_rflag[lane], e);
+        const unsigned long long t0 = global_timer_ns();
+        while (ld_acquire_sys(c.ar_lflag + lane) < e) {
+            if (global_timer_ns() - t0 > 20000000000ull) { atomicExch(c.err, 1); break; }
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        const double *src = c.ar_lslots[par];
+        double sum = 0.0;
+        for (int r = 0; r < c.nranks; ++r) sum += __ldcg(src + r * P2P_AR_WIDTH);  // rank order: same bits everywhere
+        scalars[slot] = sum;
+        *c.ar_epoch = e;
+    }
 }
 
 static famg_status p2p_begin(famg_comm *cm, const HaloPlan &h, const double *x_ext) {
@@ -327,6 +363,80 @@ static famg_status dist_allreduce(famg_dist_mg *dm, int first, int count) {
     return allreduce_slots(cm, first, count);
 }
 
+// scalars[slot] = sum over ranks of the sum of `count` partials in ctx->d_partials
+static famg_status dist_reduce_allreduce(famg_dist_mg *dm, int count, int slot) {
+    famg_comm *cm = dm->comm;
+    famg_ctx *ctx = cm->ctx;
+    if (cm->nranks > 1 && dm->p2p_coll) {
+        p2p_reduce_allreduce_kernel<<<1, 1024, 0, ctx->stream>>>(dm->coll, ctx->d_partials, count, ctx->d_scalars, slot);
+        count_launch(ctx);
+        KERNEL_CHECK();
+        return FAMG_OK;
+    }
+    FAMG_TRY(reduce_partials(ctx, ctx->d_partials, count, slot));
+    return dist_allreduce(dm, slot, 1);
+}
+
+// ---- producer-side exchange (peer-memory mode): the exchange of a vector starts on the communication stream as soon
+// as the entries its consumers' peers need are final, and runs while the rest of the vector is still being computed.
+static famg_status exch_async(famg_dist_mg *dm, const HaloPlan &h, double *x_ext) {
+    famg_comm *cm = dm->comm;
+    famg_ctx *ctx = cm->ctx;
+    if (!h.any || cm->nranks == 1) return FAMG_OK;
+    if (dm->pending) FAMG_FAIL(FAMG_ERR_INVALID, "internal: two halo exchanges in flight");
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    CUDA_TRY(cudaStreamIsCapturing(ctx->stream, &cs));
+    const bool cap = cs == cudaStreamCaptureStatusActive;
+    cudaEvent_t ev_b = cap ? cm->ev_packed : cm->ev_packed_e;
+    dm->pending_ev = cap ? cm->ev_halo : cm->ev_halo_e;
+    CUDA_TRY(cudaEventRecord(ev_b, ctx->stream));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->comm_stream, ev_b, 0));
+    ctx->comm_used.store(true, std::memory_order_relaxed);
+    FAMG_TRY(p2p_exchange(cm, h, x_ext, ctx->comm_stream));
+    CUDA_TRY(cudaEventRecord(dm->pending_ev, ctx->comm_stream));
+    dm->pending = true;
+    return FAMG_OK;
+}
+static famg_status exch_wait(famg_dist_mg *dm) {
+    if (!dm->pending) return FAMG_OK;
+    CUDA_TRY(cudaStreamWaitEvent(dm->comm->ctx->stream, dm->pending_ev, 0));
+    dm->pending = false;
+    return FAMG_OK;
+}
+
+// y = epi(A_local x_ext ...) where the ghost tail of x_ext was filled by the exchange started by its producer; `next` is
+// the halo plan through which y will be consumed (nullptr: nobody reads its ghosts).  The rows whose results the peers
+// need run first, then the exchange of y starts on the communication stream while the remaining rows are computed.
+static famg_status dist_apply_push(famg_dist_mg *dm, const DistOp &op, int epi, double *x_ext, double *y, const double *b, const double *d,
+                                   const HaloPlan *next, double *dot_partials, int *num_partials) {
+    SpmvArgs g; g.a = op.local; g.epi = epi; g.x = x_ext; g.ldx = 0; g.y = y; g.ldy = 0; g.b = b; g.ldb = 0; g.d = d; g.k = 1;
+    const int nrows = (int)op.local->nrows;
+    int total = 0, n = 0;
+    if (num_partials) *num_partials = 0;
+    FAMG_TRY(exch_wait(dm));
+    const bool push = next && next->any && dm->comm->nranks > 1;
+    const int lo = push ? next->push_lo : 0, hi = push ? next->push_hi : nrows;
+    // split only when the remaining rows are worth a launch of their own and clearly outweigh the rows computed first
+    const bool split = push && hi - lo >= dm->split_min_rows && (int64_t)(hi - lo) >= 2 * (int64_t)(nrows - (hi - lo));
+    if (!split) {
+        g.dot_partials = dot_partials;
+        FAMG_TRY(spmv_launch(g, &n));
+        if (num_partials) *num_partials = n;
+        if (push) FAMG_TRY(exch_async(dm, *next, y));
+        return FAMG_OK;
+    }
+    g.row_begin = 0; g.row_end = lo; g.row2_begin = hi; g.row2_end = nrows;
+    g.dot_partials = dot_partials;
+    FAMG_TRY(spmv_launch(g, &n)); total += n;
+    FAMG_TRY(exch_async(dm, *next, y));
+    g.row_begin = lo; g.row_end = hi; g.row2_begin = 0; g.row2_end = 0;
+    g.dot_partials = dot_partials ? dot_partials + total : nullptr;
+    g.reserve_ctas = 32;  // the persistent kernel leaves a few CTA slots free so the exchange kernel is scheduled next to it
+    FAMG_TRY(spmv_launch(g, &n)); total += n;
+    if (num_partials) *num_partials = total;
+    return FAMG_OK;
+}
+
 // gather the owned pieces of a level vector into a replicated one
 static famg_status allgather_rows(famg_dist_mg *dm, int level, const double *local, double *global) {
     famg_comm *cm = dm->comm;
@@ -350,6 +460,58 @@ static famg_status allgather_rows(famg_dist_mg *dm, int level, const double *loc
         NCCL_TRY(g_nccl.Broadcast(p == cm->rank ? local : global + sp[p], global + sp[p], cnt, ncclDouble, p, cm->comm, cm->ctx->stream));
     }
     NCCL_TRY(g_nccl.GroupEnd());
+    return FAMG_OK;
+}
+
+// One visit of a distributed level with producer-side exchanges (peer-memory mode); result in va.  `final_plan`: the
+// plan through which the caller consumes va (the parent's prolongator), nullptr on the finest level, where the last
+// sweep instead leaves the partial sums of f . va (PCG's r.z) in dot_partials.
+static famg_status dist_cycle_push(famg_dist_mg *dm, int level, double *va, const double *f, bool zero_guess, const HaloPlan *final_plan,
+                                   double *dot_partials, int *dot_count) {
+    famg_comm *cm = dm->comm;
+    famg_ctx *ctx = cm->ctx;
+    famg_mg *gm = dm->global;
+    DistLevel &L = dm->lv[(size_t)level];
+    const int64_t nloc = L.r1 - L.r0;
+    double *cur = va, *oth = L.t;
+    const int nu = gm->nu, mu = gm->mu;
+    const HaloPlan *pa = &L.A->halo;
+    int pre = nu;
+    if (zero_guess) {
+        if (((nu - 1) + nu) & 1) std::swap(cur, oth);
+        FAMG_TRY(vec_scale_rows(ctx, L.d, f, 0, cur, 0, nloc, 1));
+        FAMG_TRY(exch_async(dm, *pa, cur));
+        pre -= 1;
+    } else {
+        FAMG_TRY(exch_async(dm, *pa, cur));  // W-cycle revisit: the iterate was produced without a push for this plan
+    }
+    for (int i = 0; i < pre; ++i) {
+        FAMG_TRY(dist_apply_push(dm, *L.A, EPI_SMOOTH, cur, oth, f, L.d, pa, nullptr, nullptr));
+        std::swap(cur, oth);
+    }
+    FAMG_TRY(dist_apply_push(dm, *L.A, EPI_RESID, cur, oth, f, nullptr, &L.R->halo, nullptr, nullptr));
+    const bool coarse_rep = level + 1 == dm->lrep;
+    double *fc, *vc;
+    if (coarse_rep) { fc = dm->fc_loc; vc = dm->g_v; }
+    else { fc = dm->lv[(size_t)level + 1].b; vc = dm->lv[(size_t)level + 1].x; }
+    FAMG_TRY(dist_apply_push(dm, *L.R, EPI_SPMV, oth, fc, nullptr, nullptr, nullptr, nullptr, nullptr));
+    if (coarse_rep) {
+        MgLevel &G = gm->lv[(size_t)dm->tail_first];
+        const int64_t ldg = (G.a->nrows + 1) & ~(int64_t)1;
+        FAMG_TRY(allgather_rows(dm, level + 1, fc, dm->g_f));
+        for (int m = 0; m < mu; ++m) FAMG_TRY(mg_cycle(gm, (size_t)dm->tail_first, dm->g_v, ldg, dm->g_f, ldg, 1, m == 0));
+    } else {
+        for (int m = 0; m < mu; ++m)
+            FAMG_TRY(dist_cycle_push(dm, level + 1, vc, fc, m == 0, m + 1 == mu ? &L.P->halo : nullptr, nullptr, nullptr));
+    }
+    FAMG_TRY(dist_apply_push(dm, *L.P, EPI_ADD, vc, cur, nullptr, nullptr, pa, nullptr, nullptr));
+    for (int i = 0; i < nu; ++i) {
+        const bool last = i + 1 == nu;
+        FAMG_TRY(dist_apply_push(dm, *L.A, EPI_SMOOTH, cur, oth, f, L.d, last ? final_plan : pa, last ? dot_partials : nullptr,
+                                 last ? dot_count : nullptr));
+        std::swap(cur, oth);
+    }
+    if (cur != va) FAMG_FAIL(FAMG_ERR_INVALID, "internal: distributed ping-pong parity broken");
     return FAMG_OK;
 }
 
@@ -568,6 +730,8 @@ famg_status famg_comm_create(famg_ctx *ctx, int nranks, int rank, const void *id
     }
     cudaEventCreateWithFlags(&c->ev_packed, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_packed_e, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_halo_e, cudaEventDisableTiming);
     *out = c;
     return FAMG_OK;
 }
@@ -578,6 +742,8 @@ famg_status famg_comm_destroy(famg_comm *c) {
     cudaStreamSynchronize(c->ctx->stream); cudaStreamSynchronize(c->ctx->comm_stream);
     if (c->comm) g_nccl.CommDestroy(c->comm);
     cudaEventDestroy(c->ev_packed); cudaEventDestroy(c->ev_halo);
+    if (c->ev_packed_e) cudaEventDestroy(c->ev_packed_e);
+    if (c->ev_halo_e) cudaEventDestroy(c->ev_halo_e);
     delete c;
     return FAMG_OK;
 }
@@ -601,6 +767,8 @@ static famg_status dist_mg_finish(famg_dist_mg *d, int diag_kind, double omega, 
     famg_ctx *ctx = c->ctx;
     const int lrep = d->lrep;
     if (const char *v = getenv("FAMG_DIST_GRAPH")) d->use_graph = atoi(v) != 0;
+    if (const char *v = getenv("FAMG_OVERLAP")) d->overlap = atoi(v) != 0;
+    if (const char *v = getenv("FAMG_OVERLAP_MIN_ROWS")) d->split_min_rows = std::max(atoi(v), 1);
     FAMG_TRY(mg_ensure_workspace(d->global, 1));
     famg_status st = FAMG_OK;
     for (int l = 0; l < lrep && st == FAMG_OK; ++l) {
@@ -778,20 +946,30 @@ static famg_status dist_check_local(const famg_dist_mg *d, const famg_vec *v) {
 }
 
 // out_local = B rhs_local: one distributed mu-cycle from a zero guess. (buffers: pcg slot 4/5)
-static famg_status dist_precond(famg_dist_mg *d, double *out_ext, const double *rhs) {
+// With dot_partials (peer-memory overlap mode) the last sweep also leaves *dot_count partial sums of rhs . out there.
+static famg_status dist_precond(famg_dist_mg *d, double *out_ext, const double *rhs, double *dot_partials = nullptr, int *dot_count = nullptr) {
     famg_ctx *ctx = d->comm->ctx;
-    if (!d->use_graph) return dist_cycle(d, 0, out_ext, rhs, true);
-    auto key = std::make_pair((const void *)out_ext, (const void *)rhs);
+    if (dot_count) *dot_count = 0;
+    const bool push = d->overlap && d->p2p && d->lrep > 0;
+    if (!push) dot_partials = nullptr;
+    auto run = [&](int *nd) -> famg_status {
+        if (push) return dist_cycle_push(d, 0, out_ext, rhs, true, nullptr, dot_partials, dot_partials ? nd : nullptr);
+        return dist_cycle(d, 0, out_ext, rhs, true);
+    };
+    if (!d->use_graph) return run(dot_count);
+    auto key = std::make_tuple((const void *)out_ext, (const void *)rhs, (const void *)dot_partials);
     auto it = d->graphs.find(key);
     if (it == d->graphs.end()) {
         const int64_t before = ctx->launches.load();
         cudaError_t e = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
         famg_status st = FAMG_ERR_CUDA;
         cudaGraph_t graph = nullptr;
+        int nd = 0;
         if (e == cudaSuccess) {
-            st = dist_cycle(d, 0, out_ext, rhs, true);
+            st = run(&nd);
             e = cudaStreamEndCapture(ctx->stream, &graph);
         }
+        d->pending = false;
         GraphEntry ent;
         if (st == FAMG_OK && e == cudaSuccess && graph) e = cudaGraphInstantiate(&ent.exec, graph, 0);
         if (graph) cudaGraphDestroy(graph);
@@ -800,14 +978,16 @@ static famg_status dist_precond(famg_dist_mg *d, double *out_ext, const double *
             cudaGetLastError();
             d->use_graph = false;
             ctx->launches.store(before);
-            return dist_cycle(d, 0, out_ext, rhs, true);
+            return run(dot_count);
         }
         ent.launches = ctx->launches.load() - before;
+        ent.dot_count = nd;
         ctx->launches.store(before);
         it = d->graphs.emplace(key, ent).first;
     }
     CUDA_TRY(cudaGraphLaunch(it->second.exec, ctx->stream));
     count_launch(ctx, (int)it->second.launches);
+    if (dot_count) *dot_count = it->second.dot_count;
     return FAMG_OK;
 }
 
@@ -868,32 +1048,54 @@ famg_status famg_dist_pcg_solve_dev(famg_dist_mg *d, famg_vec *x, const famg_vec
     double rn = sqrt(h[0]);
     bool converged = rn < thr;
     int slot_rtz = S_RTZ_A, slot_rtz_new = S_RTZ_B;
+    const bool push = d->overlap && d->p2p;
+    // p = z (+ beta p), with the exchange of p started as soon as the entries the neighbours need are written
+    auto update_p = [&](bool first, int slot_new, int slot_old) -> famg_status {
+        const HaloPlan &h = A.halo;
+        const int lo = h.push_lo, hi = h.push_hi;
+        auto piece = [&](int64_t off, int64_t cnt) -> famg_status {
+            if (cnt <= 0) return FAMG_OK;
+            if (first) return vec_copy(ctx, p + off, ld, z + off, ld, cnt, 1);
+            return pcg_update_p(ctx, p + off, z + off, cnt, slot_new, slot_old);
+        };
+        if (!push) return piece(0, n);
+        if (hi - lo < d->split_min_rows) { FAMG_TRY(piece(0, n)); return exch_async(d, h, p); }
+        FAMG_TRY(piece(0, lo));
+        FAMG_TRY(piece(hi, n - hi));
+        FAMG_TRY(exch_async(d, h, p));
+        return piece(lo, hi - lo);
+    };
+    auto rtz = [&](int nd, int slot) -> famg_status {
+        if (nd > 0) return dist_reduce_allreduce(d, nd, slot);
+        FAMG_TRY(vec_dot(ctx, r, z, n, slot));
+        return dist_allreduce(d, slot, 1);
+    };
     if (!converged) {
-        FAMG_TRY(dist_precond(d, z, r));
-        FAMG_TRY(vec_copy(ctx, p, ld, z, ld, n, 1));
-        FAMG_TRY(vec_dot(ctx, r, z, n, slot_rtz));
-        FAMG_TRY(dist_allreduce(d, slot_rtz, 1));
+        FAMG_TRY(ensure_partials(ctx, n + 8));
+        int nd = 0;
+        FAMG_TRY(dist_precond(d, z, r, ctx->d_partials, &nd));
+        FAMG_TRY(rtz(nd, slot_rtz));
+        FAMG_TRY(update_p(true, 0, 0));
         for (int64_t it = 0; it < max_iters; ++it) {
-            FAMG_TRY(ensure_partials(ctx, n + 8));
             int np = 0;
-            FAMG_TRY(dist_apply(cm, A, EPI_SPMV, p, q, nullptr, nullptr, ctx->d_partials, &np));
-            FAMG_TRY(reduce_partials(ctx, ctx->d_partials, np, S_PTQ));
-            FAMG_TRY(dist_allreduce(d, S_PTQ, 1));
-            FAMG_TRY(pcg_update_xr(ctx, x->p, r, p, q, n, slot_rtz, S_PTQ, S_RR));
-            FAMG_TRY(dist_allreduce(d, S_RR, 1));
+            if (push) FAMG_TRY(dist_apply_push(d, A, EPI_SPMV, p, q, nullptr, nullptr, nullptr, ctx->d_partials, &np));
+            else FAMG_TRY(dist_apply(cm, A, EPI_SPMV, p, q, nullptr, nullptr, ctx->d_partials, &np));
+            FAMG_TRY(dist_reduce_allreduce(d, np, S_PTQ));
+            FAMG_TRY(pcg_update_xr_partials(ctx, x->p, r, p, q, n, slot_rtz, S_PTQ, &np));
+            FAMG_TRY(dist_reduce_allreduce(d, np, S_RR));
             FAMG_TRY(read_scalars(ctx, S_RR, 4, h));
-            const double ptq = h[S_PTQ - S_RR], rtz = h[slot_rtz - S_RR];
-            if (!(ptq > 0.0) || !(rtz > 0.0))
-                FAMG_FAIL(FAMG_ERR_NOT_SPD, "pcg: operator or preconditioner is not positive definite (p.Ap=%g, r.z=%g)", ptq, rtz);
+            const double ptq = h[S_PTQ - S_RR], rtzv = h[slot_rtz - S_RR];
+            if (!(ptq > 0.0) || !(rtzv > 0.0))
+                FAMG_FAIL(FAMG_ERR_NOT_SPD, "pcg: operator or preconditioner is not positive definite (p.Ap=%g, r.z=%g)", ptq, rtzv);
             rn = sqrt(h[0]);
             info->iter_count = it + 1;
             if (rn < thr) { converged = true; break; }
-            FAMG_TRY(dist_precond(d, z, r));
-            FAMG_TRY(vec_dot(ctx, r, z, n, slot_rtz_new));
-            FAMG_TRY(dist_allreduce(d, slot_rtz_new, 1));
-            FAMG_TRY(pcg_update_p(ctx, p, z, n, slot_rtz_new, slot_rtz));
+            FAMG_TRY(dist_precond(d, z, r, ctx->d_partials, &nd));
+            FAMG_TRY(rtz(nd, slot_rtz_new));
+            FAMG_TRY(update_p(false, slot_rtz_new, slot_rtz));
             std::swap(slot_rtz, slot_rtz_new);
         }
+        FAMG_TRY(exch_wait(d));
     }
     info->abs_residual = rn; info->rel_residual = rn / b_norm;
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));

@@ -42,7 +42,8 @@ struct famg_comm {
     int nranks = 1, rank = 0;
     int nlocal = 1;
     ncclComm_t comm = nullptr;
-    cudaEvent_t ev_packed = nullptr, ev_halo = nullptr;
+    cudaEvent_t ev_packed = nullptr, ev_halo = nullptr;      // fork / join of the communication stream (inside captures)
+    cudaEvent_t ev_packed_e = nullptr, ev_halo_e = nullptr;  // the same for eager (uncaptured) work
     int vrank(int li) const { return nlocal > 1 ? li : rank; }
 };
 
@@ -103,6 +104,9 @@ struct HaloPlan {
     int *d_send_idx = nullptr;
     double *d_sendbuf = nullptr;
     bool any = false;
+    // rows outside [push_lo, push_hi) hold every entry some peer needs (the send list): a producer computes them
+    // first, so that the exchange of its output can start while the remaining rows are still being computed
+    int push_lo = 0, push_hi = 0;
 };
 
 // One (virtual) rank's share of a row-partitioned operator.  Columns are global indices until the
@@ -166,8 +170,14 @@ struct famg_dist_mg {
     bool p2p_coll = false;
     // the distributed cycle (kernels + peer-memory exchanges) is captured into one CUDA graph per
     // (out, rhs) pair and replayed; disabled on the first failure
-    std::map<std::pair<const void *, const void *>, GraphEntry> graphs;
+    std::map<std::tuple<const void *, const void *, const void *>, GraphEntry> graphs;  // (out, rhs, dot partials)
     bool use_graph = true;
+    // producer-side halo exchange on the communication stream, overlapped with the rows nobody is waiting for
+    // (peer-memory mode; FAMG_OVERLAP=0 keeps the exchange in front of every apply)
+    bool overlap = true;
+    bool pending = false;       // an exchange is in flight on the communication stream
+    cudaEvent_t pending_ev = nullptr;
+    int split_min_rows = 16384; // smallest remainder worth a launch of its own (FAMG_OVERLAP_MIN_ROWS)
 };
 
 namespace famg {

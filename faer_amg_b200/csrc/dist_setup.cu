@@ -249,6 +249,16 @@ famg_status dmat_finalize(famg_dmat *m, bool replicated_cols) {
     famg_ctx *ctx = cm->ctx;
     const int nr = cm->nranks, nl = cm->nlocal;
     if (nr > XCHG_MAX_RANKS) FAMG_FAIL(FAMG_ERR_UNSUPPORTED, "at most %d ranks", XCHG_MAX_RANKS);
+    {   // kernel plan from the statistics of the whole operator: same threads-per-row on every rank as on one GPU
+        std::vector<std::vector<int64_t>> mine((size_t)nl);
+        std::vector<int64_t> all;
+        for (int li = 0; li < nl; ++li) mine[(size_t)li] = {m->part[(size_t)li].local->nnz};
+        FAMG_TRY(xchg_allgather_meta(cm, 1, mine, all));
+        int64_t total = 0;
+        for (int p = 0; p < nr; ++p) total += all[(size_t)p];
+        const double avg = m->nrows > 0 ? (double)total / (double)m->nrows : 0.0;
+        for (int li = 0; li < nl; ++li) { m->part[(size_t)li].local->tpr = tpr_for_avg(avg); m->part[(size_t)li].local->avg_row_nnz = avg; }
+    }
     for (int li = 0; li < nl; ++li) {
         DistOp &op = m->part[(size_t)li];
         HaloPlan &h = op.halo;
@@ -345,9 +355,11 @@ famg_status dmat_finalize(famg_dmat *m, bool replicated_cols) {
         HaloPlan &h = op.halo;
         const int r = cm->vrank(li);
         const int c0 = (int)m->csplit[(size_t)r], c1 = (int)m->csplit[(size_t)r + 1];
+        std::vector<int> sidx((size_t)h.total_send);
         if (h.total_send) {
             add_const_kernel<<<(unsigned)ceil_div(h.total_send, 256), 256, 0, ctx->stream>>>(h.d_send_idx, h.total_send, -c0);
             count_launch(ctx);
+            cudaMemcpyAsync(sidx.data(), h.d_send_idx, sizeof(int) * sidx.size(), cudaMemcpyDeviceToHost, ctx->stream);
         }
         const int nnz = (int)op.local->nnz, nrows = (int)op.local->nrows;
         if (nnz) {
@@ -367,6 +379,13 @@ famg_status dmat_finalize(famg_dmat *m, bool replicated_cols) {
         famg_status st = sync_check(ctx, "halo plan (renumber)");
         if (st != FAMG_OK) { pool_free(ctx, lo_hi, 256); return st; }
         op.ib = init[0]; op.ie = std::max(init[0], init[1]);
+        // the producer-side split: entries [0, push_lo) and [push_hi, nloc) of a vector with this column layout cover the send list
+        h.push_lo = 0; h.push_hi = h.nloc;
+        for (int v : sidx) {
+            if (v < 0 || v >= h.nloc) { pool_free(ctx, lo_hi, 256); FAMG_FAIL(FAMG_ERR_COMM, "internal: a peer requested an entry this rank does not own"); }
+            if (v < h.nloc / 2) h.push_lo = std::max(h.push_lo, v + 1); else h.push_hi = std::min(h.push_hi, v);
+        }
+        if (h.push_hi < h.push_lo) h.push_hi = h.push_lo;
     }
     pool_free(ctx, lo_hi, 256);
     m->finalized = true;
@@ -667,6 +686,8 @@ famg_status famg_comm_create_sim(famg_ctx *ctx, int nranks, famg_comm **out) {
     c->ctx = ctx; c->nranks = nranks; c->rank = 0; c->nlocal = nranks;
     cudaEventCreateWithFlags(&c->ev_packed, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_packed_e, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_halo_e, cudaEventDisableTiming);
     *out = c;
     return FAMG_OK;
 }

@@ -48,10 +48,11 @@ famg_status mg_ensure_workspace(famg_mg *mg, int k) {
 // One visit of `level`.  The result is written to (va, lda); `zero_guess` says the incoming
 // iterate is identically zero (first visit), otherwise (va, lda) holds it.
 famg_status mg_cycle(famg_mg *mg, size_t level, double *va, int64_t lda, const double *f, int64_t ldf, int k,
-                            bool zero_guess) {
+                            bool zero_guess, double *dot_partials, int *dot_count) {
     famg_ctx *ctx = mg->ctx;
     MgLevel &L = mg->lv[level];
     const int64_t n = L.a->nrows;
+    if (dot_count) *dot_count = 0;
     if (level + 1 == mg->lv.size()) {
         // smoother.apply(v, f): v = M^-1 f whatever v held (multigrid.rs:292)
         return smoother_apply_dev(L.s, f, ldf, va, lda, k);
@@ -59,11 +60,12 @@ famg_status mg_cycle(famg_mg *mg, size_t level, double *va, int64_t lda, const d
     const bool diag = L.s->kind == SM_DIAG;
     double *cur = va, *oth = L.t;
     int64_t ldc = lda, ldo = L.ld;
-    auto sweep = [&]() -> famg_status {
+    auto sweep = [&](bool with_dot = false) -> famg_status {
         if (diag) {
             SpmvArgs g; g.a = L.a; g.epi = EPI_SMOOTH; g.x = cur; g.ldx = ldc; g.y = oth; g.ldy = ldo; g.b = f; g.ldb = ldf;
             g.d = L.s->d; g.k = k;
-            FAMG_TRY(spmv_launch(g));
+            if (with_dot) g.dot_partials = dot_partials;
+            FAMG_TRY(spmv_launch(g, with_dot ? dot_count : nullptr));
             std::swap(cur, oth); std::swap(ldc, ldo);
             return FAMG_OK;
         }
@@ -98,16 +100,20 @@ famg_status mg_cycle(famg_mg *mg, size_t level, double *va, int64_t lda, const d
         SpmvArgs g; g.a = C.p; g.epi = EPI_ADD; g.x = C.x; g.ldx = C.ld; g.y = cur; g.ldy = ldc; g.k = k;
         FAMG_TRY(spmv_launch(g));                                                    // :349-350
     }
-    for (int i = 0; i < mg->nu; ++i) FAMG_TRY(sweep());                              // :361-369
+    for (int i = 0; i < mg->nu; ++i)                                                 // :361-369
+        FAMG_TRY(sweep(i + 1 == mg->nu && diag && k == 1 && dot_partials != nullptr && dot_count != nullptr));
     if (cur != va) FAMG_FAIL(FAMG_ERR_INVALID, "internal: multigrid ping-pong parity broken");
     return FAMG_OK;
 }
 
-famg_status mg_apply_dev_raw(famg_mg *mg, double *out, int64_t ldo, const double *rhs, int64_t ldr, int k) {
+famg_status mg_apply_dev_raw(famg_mg *mg, double *out, int64_t ldo, const double *rhs, int64_t ldr, int k,
+                             double *dot_partials, int *dot_count) {
     famg_ctx *ctx = mg->ctx;
     FAMG_TRY(mg_ensure_workspace(mg, k));
-    if (!mg->use_graph) return mg_cycle(mg, 0, out, ldo, rhs, ldr, k, true);
-    GraphKey key{out, rhs, ldo, ldr, k, mg->mu, mg->nu, ctx->option_epoch.load()};
+    if (dot_count) *dot_count = 0;
+    if (mg->lv.size() < 2 || k != 1) dot_partials = nullptr;  // a one-level "multigrid" is the bare smoother apply
+    if (!mg->use_graph) return mg_cycle(mg, 0, out, ldo, rhs, ldr, k, true, dot_partials, dot_count);
+    GraphKey key{out, rhs, ldo, ldr, k, mg->mu, mg->nu, ctx->option_epoch.load(), dot_partials};
     auto it = mg->graphs.find(key);
     if (it == mg->graphs.end()) {
         if (mg->graphs.size() > 64) {  // bounded cache
@@ -116,12 +122,14 @@ famg_status mg_apply_dev_raw(famg_mg *mg, double *out, int64_t ldo, const double
         }
         const int64_t before = ctx->launches.load();
         CUDA_TRY(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-        famg_status st = mg_cycle(mg, 0, out, ldo, rhs, ldr, k, true);
+        int ndot = 0;
+        famg_status st = mg_cycle(mg, 0, out, ldo, rhs, ldr, k, true, dot_partials, &ndot);
         cudaGraph_t graph = nullptr;
         cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
         if (st != FAMG_OK) { if (graph) cudaGraphDestroy(graph); return st; }
         if (e != cudaSuccess) FAMG_FAIL(FAMG_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
         GraphEntry ent;
+        ent.dot_count = ndot;
         ent.launches = ctx->launches.load() - before;
         ctx->launches.store(before);
         e = cudaGraphInstantiate(&ent.exec, graph, 0);
@@ -131,6 +139,7 @@ famg_status mg_apply_dev_raw(famg_mg *mg, double *out, int64_t ldo, const double
     }
     CUDA_TRY(cudaGraphLaunch(it->second.exec, ctx->stream));
     count_launch(ctx, (int)it->second.launches);
+    if (dot_count) *dot_count = it->second.dot_count;
     return FAMG_OK;
 }
 

@@ -10,9 +10,25 @@
 // the multigrid cycle (one CUDA-graph launch), r.z dot, p update, plus the one-CTA reductions.
 #include <cmath>
 
-#include "common.cuh"
+#include "mg_internal.cuh"
 
 namespace famg {
+
+// z = M^-1 r and r.z into scalar `slot`.  With a multigrid whose fine level has a Diag smoother the product comes
+// out of the cycle's last sweep (per-CTA partials, reduced here): no extra pass over r and z.
+static famg_status pc_apply_rtz(famg_ctx *ctx, int pc_kind, void *precond, famg_vec *z, const famg_vec *r, int64_t n, int slot) {
+    if (pc_kind == FAMG_PC_MG) {
+        famg_mg *mg = (famg_mg *)precond;
+        if (!z || !r || mg->lv[0].a->nrows != n || z->p == r->p) FAMG_FAIL(FAMG_ERR_INVALID, "multigrid apply shape mismatch");
+        FAMG_TRY(ensure_partials(ctx, n + 8));
+        int nd = 0;
+        FAMG_TRY(mg_apply_dev_raw(mg, z->p, z->ld, r->p, r->ld, 1, ctx->d_partials, &nd));
+        if (nd > 0) return reduce_partials(ctx, ctx->d_partials, nd, slot);
+        return vec_dot(ctx, r->p, z->p, n, slot);
+    }
+    FAMG_TRY(pc_apply(pc_kind, precond, z, r));
+    return vec_dot(ctx, r->p, z->p, n, slot);
+}
 
 famg_status pc_apply(int pc_kind, void *precond, famg_vec *z, const famg_vec *r) {
     if (pc_kind == FAMG_PC_MG) return famg_mg_apply_dev((famg_mg *)precond, z, r);
@@ -137,9 +153,8 @@ famg_status famg_pcg_solve_dev(const famg_csr *a, int pc_kind, void *precond, fa
         if (st != FAMG_OK) break;
         rn = sqrt(h[0]);
         if (rn < thr) { converged = true; break; }
-        st = pc_apply(pc_kind, precond, z, r);
+        st = pc_apply_rtz(ctx, pc_kind, precond, z, r, n, slot_rtz);
         if (st == FAMG_OK) st = famg_vec_copy(p, z);
-        if (st == FAMG_OK) st = vec_dot(ctx, r->p, z->p, n, slot_rtz);
         for (int64_t it = 0; it < max_iters && st == FAMG_OK; ++it) {
             // q = A p, fused partial sums of p.q
             SpmvArgs g; g.a = a; g.epi = EPI_SPMV; g.x = p->p; g.ldx = p->ld; g.y = q->p; g.ldy = q->ld; g.k = 1;
@@ -162,8 +177,7 @@ famg_status famg_pcg_solve_dev(const famg_csr *a, int pc_kind, void *precond, fa
             rn = sqrt(h[0]);
             info->iter_count = it + 1;
             if (rn < thr) { converged = true; break; }
-            st = pc_apply(pc_kind, precond, z, r);
-            if (st == FAMG_OK) st = vec_dot(ctx, r->p, z->p, n, slot_rtz_new);
+            st = pc_apply_rtz(ctx, pc_kind, precond, z, r, n, slot_rtz_new);
             if (st == FAMG_OK) st = pcg_update_p(ctx, p->p, z->p, n, slot_rtz_new, slot_rtz);
             std::swap(slot_rtz, slot_rtz_new);
         }

@@ -90,7 +90,9 @@ __device__ __forceinline__ void epi_store(double *yc, int row, double s, const E
         yc[row] = o.b - s;                       // multigrid.rs:341-342
     } else if (EPI == EPI_SMOOTH) {
         const double r = o.b - s;                // x' = x + d .* (b - A x)   (multigrid.rs:419-422)
-        yc[row] = o.x + o.d * r;
+        const double xn = o.x + o.d * r;
+        yc[row] = xn;
+        if (DOT) dot_acc += o.b * xn;            // b . x': PCG's r.z when this is the cycle's last sweep (b = r, x' = z)
     } else if (EPI == EPI_ADD) {
         yc[row] = o.y + s;                       // multigrid.rs:349-350
     } else if (EPI == EPI_EPROP) {
@@ -98,7 +100,7 @@ __device__ __forceinline__ void epi_store(double *yc, int row, double s, const E
     } else {
         yc[row] = o.x + o.d * (o.x - s);         // EPI_SI: x' = x + d .* (x - A x)   (smoothers.rs:153-156, literal)
     }
-    if (DOT) dot_acc += o.x * s;
+    if (DOT && EPI != EPI_SMOOTH) dot_acc += o.x * s;
 }
 
 // ---- column-blocked row walk for k > 1 (K2, SpMM) -------------------------------------------------
@@ -498,7 +500,9 @@ static famg_status launch_tpr(const SpmvKernelParams &kp, int epi, bool dot, int
             return dot ? launch_one<TPR, EPI_SPMV, true, 1>(kp, variant, nrows, nrows2, sms, reserve, st, grid)
                        : launch_cb<TPR, EPI_SPMV>(kp, cb, variant, nrows, nrows2, sms, reserve, st, grid);
         case EPI_RESID: return launch_cb<TPR, EPI_RESID>(kp, cb, variant, nrows, nrows2, sms, reserve, st, grid);
-        case EPI_SMOOTH: return launch_cb<TPR, EPI_SMOOTH>(kp, cb, variant, nrows, nrows2, sms, reserve, st, grid);
+        case EPI_SMOOTH:
+            return dot ? launch_one<TPR, EPI_SMOOTH, true, 1>(kp, variant, nrows, nrows2, sms, reserve, st, grid)
+                       : launch_cb<TPR, EPI_SMOOTH>(kp, cb, variant, nrows, nrows2, sms, reserve, st, grid);
         case EPI_ADD: return launch_cb<TPR, EPI_ADD>(kp, cb, variant, nrows, nrows2, sms, reserve, st, grid);
         case EPI_EPROP: return launch_cb<TPR, EPI_EPROP>(kp, cb, variant, nrows, nrows2, sms, reserve, st, grid);
         default: return launch_cb<TPR, EPI_SI>(kp, cb, variant, nrows, nrows2, sms, reserve, st, grid);
@@ -517,7 +521,8 @@ famg_status spmv_launch(const SpmvArgs &args, int *num_ctas) {
     if ((args.epi == EPI_RESID || args.epi == EPI_SMOOTH) && !args.b) FAMG_FAIL(FAMG_ERR_INVALID, "spmv: missing rhs");
     if ((args.epi == EPI_SMOOTH || args.epi == EPI_SI || args.epi == EPI_EPROP) && (!args.d || args.y == args.x))
         FAMG_FAIL(FAMG_ERR_INVALID, "spmv: smoother sweep needs a diagonal and distinct in/out vectors");
-    if (args.dot_partials && (args.k != 1 || args.epi != EPI_SPMV)) FAMG_FAIL(FAMG_ERR_INVALID, "spmv: dot needs k == 1");
+    if (args.dot_partials && (args.k != 1 || (args.epi != EPI_SPMV && args.epi != EPI_SMOOTH)))
+        FAMG_FAIL(FAMG_ERR_INVALID, "spmv: fused dot products exist for y = A x (x . A x) and the smoother sweep (b . x'), k == 1");
     SpmvKernelParams kp;
     kp.row_ptr = a->row_ptr; kp.col = a->col; kp.val = a->val;
     kp.row_begin = row_begin; kp.row_end = row_end;

@@ -112,13 +112,20 @@ __global__ void __launch_bounds__(VT) pcg_xr_kernel(double *__restrict__ x, doub
     double t = block_sum(acc, s_red);
     if (threadIdx.x == 0) partials[blockIdx.x] = t;
 }
-famg_status pcg_update_xr(famg_ctx *ctx, double *x, double *r, const double *p, const double *q, int64_t n, int slot_num,
-                          int slot_den, int slot_rr) {
+famg_status pcg_update_xr_partials(famg_ctx *ctx, double *x, double *r, const double *p, const double *q, int64_t n, int slot_num,
+                                   int slot_den, int *num_partials) {
     int grid = vec_grid(ctx, n, 4);
     FAMG_TRY(ensure_partials(ctx, grid));
     pcg_xr_kernel<<<grid, VT, 0, ctx->stream>>>(x, r, p, q, n, ctx->d_scalars, slot_num, slot_den, ctx->d_partials);
     count_launch(ctx);
     KERNEL_CHECK();
+    *num_partials = grid;
+    return FAMG_OK;
+}
+famg_status pcg_update_xr(famg_ctx *ctx, double *x, double *r, const double *p, const double *q, int64_t n, int slot_num,
+                          int slot_den, int slot_rr) {
+    int grid = 0;
+    FAMG_TRY(pcg_update_xr_partials(ctx, x, r, p, q, n, slot_num, slot_den, &grid));
     return reduce_partials(ctx, ctx->d_partials, grid, slot_rr, nullptr);
 }
 
