@@ -183,10 +183,17 @@ struct SpmvArgs {
                                                  // sum_i b[i]*x'[i] (EPI_SMOOTH: PCG's r.z from the cycle's last sweep)
     int row_begin = 0, row_end = -1;             // row range (distributed interior/boundary split)
     int row2_begin = 0, row2_end = 0;            // optional second range handled by the same launch
-    int reserve_ctas = 0;                        // leave this many CTA slots free (room for NCCL kernels)
+    int reserve_ctas = 0;                        // leave this many CTA slots free (room for the concurrently running exchange / NCCL kernels)
+    // producer-side halo exchange: all rows are computed, [sig_hi, nrows) and [0, sig_lo) first; every consumer warp adds
+    // 1 to *sig per finished chunk of those rows (8 per chunk of 256 / tpr rows): spmv_signal_target() in total
+    unsigned *sig = nullptr; int sig_lo = 0, sig_hi = 0;
     cudaStream_t stream = nullptr;               // default: ctx stream
 };
 famg_status spmv_launch(const SpmvArgs &args, int *num_ctas = nullptr);
+inline unsigned spmv_signal_target(const famg_csr *a, int sig_lo, int sig_hi) {
+    const int rows = 256 / a->tpr;
+    return 8u * (unsigned)(ceil_div((int64_t)a->nrows - sig_hi, rows) + ceil_div(sig_lo, rows));
+}
 
 // ---------------------------------------------------------------- vector ops (vecops.cu)
 famg_status vec_scale_rows(famg_ctx *ctx, const double *d, const double *in, int64_t ldi, double *out,

@@ -165,9 +165,26 @@ __global__ void __launch_bounds__(256) p2p_allgather_wait_kernel(const P2PCollDe
 // Unsplit applies: pack and wait+copy in ONE launch (<= 64 co-resident CTAs).  Every CTA stores
 // its slice into the neighbours' buffers; the last one to finish publishes the epoch; then every CTA
 // acquire-spins on this rank's own flags and moves its slice of the ghosts into the vector tail.
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// `sig` / `target` (producer-side exchange): the kernel is launched next to the kernel that is still computing x_ext and
+// starts packing once that kernel's consumer warps have counted `target` finished boundary chunks into *sig.
 __global__ void __launch_bounds__(256) p2p_exchange_kernel(const P2PPlanDev pl, double *__restrict__ x_ext, int nloc,
-                                                           const int *__restrict__ send_idx) {
+                                                           const int *__restrict__ send_idx, unsigned *sig, unsigned target) {
     __shared__ bool s_last;
+    if (sig) {
+        if (threadIdx.x == 0) {
+            const unsigned long long t0 = global_timer_ns();
+            while (ld_acquire_gpu_u32(sig) < target) {
+                if (global_timer_ns() - t0 > 20000000000ull) { atomicExch(pl.err, 2); break; }
+            }
+        }
+        __syncthreads();
+    }
     const unsigned long long e = *pl.epoch + 1ull;
     const int par = (int)(e & 1ull);
     const int stride = gridDim.x * blockDim.x;
@@ -183,7 +200,7 @@ __global__ void __launch_bounds__(256) p2p_exchange_kernel(const P2PPlanDev pl, 
     if (s_last) {
         __threadfence_system();
         if (threadIdx.x < pl.nnb) st_release_sys(pl.rflag[threadIdx.x], e);
-        if (threadIdx.x == 0) { *pl.done = 0u; *pl.epoch = e; }
+        if (threadIdx.x == 0) { *pl.done = 0u; *pl.epoch = e; if (sig) *sig = 0u; }  // every CTA is past its wait on *sig
     }
     if (threadIdx.x < pl.nnb) {
         const unsigned long long t0 = global_timer_ns();
@@ -197,10 +214,11 @@ __global__ void __launch_bounds__(256) p2p_exchange_kernel(const P2PPlanDev pl, 
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < pl.nghost; j += stride) tail[j] = __ldcg(src + j);
 }
 
-static famg_status p2p_exchange(famg_comm *cm, const HaloPlan &h, double *x_ext, cudaStream_t st = nullptr) {
+static famg_status p2p_exchange(famg_comm *cm, const HaloPlan &h, double *x_ext, cudaStream_t st = nullptr, unsigned *sig = nullptr,
+                                unsigned target = 0) {
     const int work = std::max(h.total_send, h.nghost);
-    const int grid = std::max(1, std::min(64, (work + 1023) / 1024));
-    p2p_exchange_kernel<<<grid, 256, 0, st ? st : cm->ctx->stream>>>(h.dev, x_ext, h.nloc, h.d_send_idx);
+    const int grid = std::max(1, std::min(sig ? 32 : 64, (work + 1023) / 1024));  // co-resident with the producer kernel when signalled
+    p2p_exchange_kernel<<<grid, 256, 0, st ? st : cm->ctx->stream>>>(h.dev, x_ext, h.nloc, h.d_send_idx, sig, target);
     count_launch(cm->ctx);
     KERNEL_CHECK();
     return FAMG_OK;
@@ -379,23 +397,35 @@ static famg_status dist_reduce_allreduce(famg_dist_mg *dm, int count, int slot) 
 
 // ---- producer-side exchange (peer-memory mode): the exchange of a vector starts on the communication stream as soon
 // as the entries its consumers' peers need are final, and runs while the rest of the vector is still being computed.
-static famg_status exch_async(famg_dist_mg *dm, const HaloPlan &h, double *x_ext) {
+// fork point: what the exchange kernel has to wait for on the compute stream
+static famg_status exch_fork(famg_dist_mg *dm, cudaEvent_t *ev_b) {
     famg_comm *cm = dm->comm;
     famg_ctx *ctx = cm->ctx;
-    if (!h.any || cm->nranks == 1) return FAMG_OK;
     if (dm->pending) FAMG_FAIL(FAMG_ERR_INVALID, "internal: two halo exchanges in flight");
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     CUDA_TRY(cudaStreamIsCapturing(ctx->stream, &cs));
     const bool cap = cs == cudaStreamCaptureStatusActive;
-    cudaEvent_t ev_b = cap ? cm->ev_packed : cm->ev_packed_e;
+    *ev_b = cap ? cm->ev_packed : cm->ev_packed_e;
     dm->pending_ev = cap ? cm->ev_halo : cm->ev_halo_e;
-    CUDA_TRY(cudaEventRecord(ev_b, ctx->stream));
+    CUDA_TRY(cudaEventRecord(*ev_b, ctx->stream));
+    return FAMG_OK;
+}
+static famg_status exch_launch(famg_dist_mg *dm, cudaEvent_t ev_b, const HaloPlan &h, double *x_ext, unsigned *sig, unsigned target) {
+    famg_comm *cm = dm->comm;
+    famg_ctx *ctx = cm->ctx;
     CUDA_TRY(cudaStreamWaitEvent(ctx->comm_stream, ev_b, 0));
     ctx->comm_used.store(true, std::memory_order_relaxed);
-    FAMG_TRY(p2p_exchange(cm, h, x_ext, ctx->comm_stream));
+    FAMG_TRY(p2p_exchange(cm, h, x_ext, ctx->comm_stream, sig, target));
     CUDA_TRY(cudaEventRecord(dm->pending_ev, ctx->comm_stream));
     dm->pending = true;
     return FAMG_OK;
+}
+// exchange of a finished vector on the communication stream
+static famg_status exch_async(famg_dist_mg *dm, const HaloPlan &h, double *x_ext) {
+    if (!h.any || dm->comm->nranks == 1) return FAMG_OK;
+    cudaEvent_t ev_b = nullptr;
+    FAMG_TRY(exch_fork(dm, &ev_b));
+    return exch_launch(dm, ev_b, h, x_ext, nullptr, 0);
 }
 static famg_status exch_wait(famg_dist_mg *dm) {
     if (!dm->pending) return FAMG_OK;
@@ -410,31 +440,33 @@ static famg_status exch_wait(famg_dist_mg *dm) {
 static famg_status dist_apply_push(famg_dist_mg *dm, const DistOp &op, int epi, double *x_ext, double *y, const double *b, const double *d,
                                    const HaloPlan *next, double *dot_partials, int *num_partials) {
     SpmvArgs g; g.a = op.local; g.epi = epi; g.x = x_ext; g.ldx = 0; g.y = y; g.ldy = 0; g.b = b; g.ldb = 0; g.d = d; g.k = 1;
-    const int nrows = (int)op.local->nrows;
-    int total = 0, n = 0;
+    int n = 0;
     if (num_partials) *num_partials = 0;
     FAMG_TRY(exch_wait(dm));
     const bool push = next && next->any && dm->comm->nranks > 1;
-    const int lo = push ? next->push_lo : 0, hi = push ? next->push_hi : nrows;
-    // split only when the remaining rows are worth a launch of their own and clearly outweigh the rows computed first
-    const bool split = push && hi - lo >= dm->split_min_rows && (int64_t)(hi - lo) >= 2 * (int64_t)(nrows - (hi - lo));
-    if (!split) {
-        g.dot_partials = dot_partials;
+    g.dot_partials = dot_partials;
+    if (!push) {
         FAMG_TRY(spmv_launch(g, &n));
         if (num_partials) *num_partials = n;
-        if (push) FAMG_TRY(exch_async(dm, *next, y));
         return FAMG_OK;
     }
-    g.row_begin = 0; g.row_end = lo; g.row2_begin = hi; g.row2_end = nrows;
-    g.dot_partials = dot_partials;
-    FAMG_TRY(spmv_launch(g, &n)); total += n;
-    FAMG_TRY(exch_async(dm, *next, y));
-    g.row_begin = lo; g.row_end = hi; g.row2_begin = 0; g.row2_end = 0;
-    g.dot_partials = dot_partials ? dot_partials + total : nullptr;
-    g.reserve_ctas = 32;  // the persistent kernel leaves a few CTA slots free so the exchange kernel is scheduled next to it
-    FAMG_TRY(spmv_launch(g, &n)); total += n;
-    if (num_partials) *num_partials = total;
-    return FAMG_OK;
+    if (dm->overlap_mode != 2) {  // exchange after the whole apply (no overlap)
+        FAMG_TRY(spmv_launch(g, &n));
+        if (num_partials) *num_partials = n;
+        return exch_async(dm, *next, y);
+    }
+    // One launch computes the rows the peers need first and counts them into *sig; the exchange kernel is launched
+    // BEFORE it on the communication stream, waits for the count, and then packs / pushes / waits for the neighbours
+    // while this kernel is still busy with the remaining rows.
+    // (The producer is launched first: if a tool serialises kernels in launch order the exchange simply runs after it.)
+    const int lo = next->push_lo, hi = next->push_hi;
+    cudaEvent_t ev_b = nullptr;
+    FAMG_TRY(exch_fork(dm, &ev_b));
+    g.sig = dm->d_sig; g.sig_lo = lo; g.sig_hi = hi;
+    g.reserve_ctas = dm->reserve_ctas;  // the persistent kernel leaves CTA slots free for the exchange kernel next to it
+    FAMG_TRY(spmv_launch(g, &n));
+    if (num_partials) *num_partials = n;
+    return exch_launch(dm, ev_b, *next, y, dm->d_sig, spmv_signal_target(op.local, lo, hi));
 }
 
 // gather the owned pieces of a level vector into a replicated one
@@ -601,6 +633,8 @@ static famg_status p2p_setup(famg_dist_mg *d) {
     CUDA_TRY(cudaMemset(d->arena, 0, off));
     FAMG_TRY(dev_alloc(&d->d_p2p_err, 1));
     CUDA_TRY(cudaMemset(d->d_p2p_err, 0, sizeof(int)));
+    FAMG_TRY(dev_alloc(&d->d_sig, 4));
+    CUDA_TRY(cudaMemset(d->d_sig, 0, 4 * sizeof(unsigned)));
     // exchange IPC handles and layouts through NCCL all-gathers of raw bytes
     const int rec = (int)sizeof(cudaIpcMemHandle_t);
     const int lay = (int)(sizeof(long long) * ((size_t)np * (3 + nr) + 8));  // plan rows + 8-word header (collective offsets)
@@ -688,7 +722,7 @@ static famg_status p2p_setup(famg_dist_mg *d) {
 static void dist_free(famg_dist_mg *d) {
     for (size_t p = 0; p < d->peer_arena.size(); ++p)
         if (d->peer_arena[p] && (int)p != d->comm->rank) cudaIpcCloseMemHandle(d->peer_arena[p]);
-    cudaFree(d->arena); cudaFree(d->d_p2p_err);
+    cudaFree(d->arena); cudaFree(d->d_p2p_err); cudaFree(d->d_sig);
     for (auto &l : d->lv) { cudaFree(l.d); cudaFree(l.x); cudaFree(l.b); cudaFree(l.t); }
     for (famg_dmat *m : d->keep) dmat_release(m);
     if (d->owns_tail && d->global) famg_mg_destroy(d->global);
@@ -767,8 +801,9 @@ static famg_status dist_mg_finish(famg_dist_mg *d, int diag_kind, double omega, 
     famg_ctx *ctx = c->ctx;
     const int lrep = d->lrep;
     if (const char *v = getenv("FAMG_DIST_GRAPH")) d->use_graph = atoi(v) != 0;
-    if (const char *v = getenv("FAMG_OVERLAP")) d->overlap = atoi(v) != 0;
+    if (const char *v = getenv("FAMG_OVERLAP")) { d->overlap_mode = std::min(std::max(atoi(v), 0), 2); d->overlap = d->overlap_mode != 0; }
     if (const char *v = getenv("FAMG_OVERLAP_MIN_ROWS")) d->split_min_rows = std::max(atoi(v), 1);
+    if (const char *v = getenv("FAMG_RESERVE_CTAS")) d->reserve_ctas = std::max(atoi(v), 0);
     FAMG_TRY(mg_ensure_workspace(d->global, 1));
     famg_status st = FAMG_OK;
     for (int l = 0; l < lrep && st == FAMG_OK; ++l) {

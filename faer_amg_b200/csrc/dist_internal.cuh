@@ -175,6 +175,10 @@ struct famg_dist_mg {
     // producer-side halo exchange on the communication stream, overlapped with the rows nobody is waiting for
     // (peer-memory mode; FAMG_OVERLAP=0 keeps the exchange in front of every apply)
     bool overlap = true;
+    int overlap_mode = 2;       // FAMG_OVERLAP: 0 exchange in front of every apply (round-1 order), 1 producer-side exchange after
+                                // the producing kernel, 2 producer-side exchange running next to the producing kernel
+    int reserve_ctas = 32;      // CTA slots the persistent producer leaves to the exchange kernel (FAMG_RESERVE_CTAS)
+    unsigned *d_sig = nullptr;  // finished-boundary-chunk counter of the producer kernel in flight
     bool pending = false;       // an exchange is in flight on the communication stream
     cudaEvent_t pending_ev = nullptr;
     int split_min_rows = 16384; // smallest remainder worth a launch of its own (FAMG_OVERLAP_MIN_ROWS)

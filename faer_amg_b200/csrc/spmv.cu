@@ -53,6 +53,11 @@ struct SpmvKernelParams {
     const double *d;
     int k;
     double *dot_partials;
+    // producer-side halo exchange (dist.cu): the first nsig chunks hold every row a peer needs; each consumer warp
+    // bumps *sig when its rows of such a chunk are stored, and the concurrently running exchange kernel starts
+    // packing when the count is complete
+    int nsig;
+    unsigned *sig;
 };
 
 
@@ -247,6 +252,11 @@ __global__ void __launch_bounds__(SPMV_THREADS, CB == 1 ? 4 : 3) spmv_kernel(con
         }
         if (active && lane == 0) epi_store<EPI, DOT>(yc, row, s, ops, dot_acc);
     }
+    if ((int)blockIdx.x < p.nsig) {  // warp-uniform
+        __syncwarp();
+        __threadfence();
+        if ((tid & 31) == 0) atomicAdd(p.sig, 1u);
+    }
     if (DOT) {
         // deterministic CTA reduction of x_i * (A x)_i -> one partial per CTA
         double v = dot_acc;
@@ -439,6 +449,11 @@ __global__ void __launch_bounds__(TMA_THREADS, CB == 1 ? TMA_CTAS : 3) spmv_tma_
             }
             if (active && lane == 0) epi_store<EPI, DOT>(yc, row, s, ops, dot_acc);
         }
+        if (c < p.nsig) {  // warp-uniform: this chunk's rows are awaited by the exchange kernel
+            __syncwarp();
+            __threadfence();
+            if ((tid & 31) == 0) atomicAdd(p.sig, 1u);
+        }
         if (staged) {
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(&empty[stage]);
@@ -466,6 +481,9 @@ static famg_status launch_one(SpmvKernelParams kp, int variant, int nrows1, int 
                               int *grid_out) {
     constexpr int ROWS = 256 / TPR;  // both variants use 256 row-walking threads
     kp.nchunks1 = (int)ceil_div(nrows1, ROWS);
+    // signalled launches run [push_hi, n) as the first range and [0, push_hi) as the second; kp.nsig arrives holding
+    // push_lo: the signalled chunks are the whole first range and the chunks covering [0, push_lo) of the second
+    if (kp.sig) kp.nsig = kp.nchunks1 + (int)ceil_div(kp.nsig, ROWS); else kp.nsig = 0;
     const int nchunks = kp.nchunks1 + (int)ceil_div(nrows2, ROWS);
     if (variant == 2) {
         constexpr int CTAS = CB == 1 ? TMA_CTAS : 3;  // resident CTAs per SM (register budget of the column block)
@@ -530,6 +548,14 @@ famg_status spmv_launch(const SpmvArgs &args, int *num_ctas) {
     kp.x = args.x; kp.ldx = args.ldx; kp.y = args.y; kp.ldy = args.ldy;
     kp.b = args.b; kp.ldb = args.ldb; kp.d = args.d; kp.k = args.k;
     kp.dot_partials = args.dot_partials;
+    kp.sig = args.sig; kp.nsig = args.sig ? args.sig_lo : 0;
+    if (args.sig) {  // boundary-first row order (see SpmvArgs::sig)
+        if (args.k != 1 || args.sig_lo < 0 || args.sig_hi < args.sig_lo || args.sig_hi > (int)a->nrows || args.row_begin != 0 || args.row_end >= 0 ||
+            args.row2_end > args.row2_begin)
+            FAMG_FAIL(FAMG_ERR_INVALID, "internal: signalled launches cover all rows of a single right-hand side");
+        kp.row_begin = row_begin = args.sig_hi; kp.row_end = row_end = (int)a->nrows;
+        kp.row2_begin = 0; kp.row2_end = args.sig_hi;
+    }
     const int tpr = a->tpr;
     const int nrows = row_end - row_begin;
     const int nrows2 = kp.row2_end - kp.row2_begin;

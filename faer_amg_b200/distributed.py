@@ -389,7 +389,8 @@ class DistHierarchy:
                 nn_q = thin_q(nn_dev.to_host())                            # :228
                 cfg = HierarchyConfig(self.coarsest_dim, AggregationConfig(self.smoothing_steps, 1, self.partitioner.tail(level + 1)))
                 self.tail = Hierarchy(SparseMatOp(g), nn_q, None, cfg)
-                self.tail.coarsen()
+                if nc > self.coarsest_dim:  # the level loop's own test (hierarchy.rs:199), already decided for this level
+                    self.tail.coarsen()
                 return
             Ac.finalize(False)
             P.finalize(False)

@@ -104,3 +104,12 @@ def test_virtual_communicator_cannot_run_the_cycle(ctx):
     comm, rs, dh = _dist_hierarchy(ctx, (16, 16, 16), 7, 2, 40, 200)
     with pytest.raises(F.FamgError):
         DistMultigrid.from_hierarchy(comm, dh)
+
+
+def test_tail_of_one_level(ctx):
+    """The first replicated level is already below coarsest_dim: the tail is that single level (no extra coarsening)."""
+    a, nn, h = _global_hierarchy(ctx, (24, 20, 16), 7, 200)
+    comm, rs, dh = _dist_hierarchy(ctx, (24, 20, 16), 7, 2, 200, 100)
+    assert dh.levels() == h.levels() == 3 and dh.tail.levels() == 1
+    w = h.get_mat_ref(2)
+    _same(dh.tail.get_mat_ref(0), w, 0, w.nrows, "tail")
