@@ -173,8 +173,11 @@ __device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned *p) {
 
 // `sig` / `target` (producer-side exchange): the kernel is launched next to the kernel that is still computing x_ext and
 // starts packing once that kernel's consumer warps have counted `target` finished boundary chunks into *sig.
+// `sd` / `sf`: the vector being exchanged is sd .* sf (the first sweep from a zero guess, v = d .* f), still being written
+// by a kernel running next to this one: the entries to send are formed here from the operands (same product, same bits).
 __global__ void __launch_bounds__(256) p2p_exchange_kernel(const P2PPlanDev pl, double *__restrict__ x_ext, int nloc,
-                                                           const int *__restrict__ send_idx, unsigned *sig, unsigned target) {
+                                                           const int *__restrict__ send_idx, unsigned *sig, unsigned target,
+                                                           const double *__restrict__ sd, const double *__restrict__ sf) {
     __shared__ bool s_last;
     if (sig) {
         if (threadIdx.x == 0) {
@@ -191,7 +194,8 @@ __global__ void __launch_bounds__(256) p2p_exchange_kernel(const P2PPlanDev pl, 
     for (int nb = 0; nb < pl.nnb; ++nb) {
         double *dst = pl.rdst[par][nb];
         const int *idx = send_idx + pl.soff[nb];
-        for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < pl.scnt[nb]; j += stride) dst[j] = x_ext[idx[j]];
+        if (sd) { for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < pl.scnt[nb]; j += stride) { const int i = idx[j]; dst[j] = sd[i] * sf[i]; } }
+        else { for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < pl.scnt[nb]; j += stride) dst[j] = x_ext[idx[j]]; }
     }
     __threadfence_system();
     __syncthreads();
@@ -215,10 +219,10 @@ __global__ void __launch_bounds__(256) p2p_exchange_kernel(const P2PPlanDev pl, 
 }
 
 static famg_status p2p_exchange(famg_comm *cm, const HaloPlan &h, double *x_ext, cudaStream_t st = nullptr, unsigned *sig = nullptr,
-                                unsigned target = 0) {
+                                unsigned target = 0, int max_ctas = 64, const double *sd = nullptr, const double *sf = nullptr) {
     const int work = std::max(h.total_send, h.nghost);
-    const int grid = std::max(1, std::min(sig ? 32 : 64, (work + 1023) / 1024));  // co-resident with the producer kernel when signalled
-    p2p_exchange_kernel<<<grid, 256, 0, st ? st : cm->ctx->stream>>>(h.dev, x_ext, h.nloc, h.d_send_idx, sig, target);
+    const int grid = std::max(1, std::min(max_ctas, (work + 1023) / 1024));  // co-resident with the producer kernel when signalled
+    p2p_exchange_kernel<<<grid, 256, 0, st ? st : cm->ctx->stream>>>(h.dev, x_ext, h.nloc, h.d_send_idx, sig, target, sd, sf);
     count_launch(cm->ctx);
     KERNEL_CHECK();
     return FAMG_OK;
@@ -410,12 +414,14 @@ static famg_status exch_fork(famg_dist_mg *dm, cudaEvent_t *ev_b) {
     CUDA_TRY(cudaEventRecord(*ev_b, ctx->stream));
     return FAMG_OK;
 }
-static famg_status exch_launch(famg_dist_mg *dm, cudaEvent_t ev_b, const HaloPlan &h, double *x_ext, unsigned *sig, unsigned target) {
+static famg_status exch_launch(famg_dist_mg *dm, cudaEvent_t ev_b, const HaloPlan &h, double *x_ext, unsigned *sig, unsigned target,
+                               const double *sd = nullptr, const double *sf = nullptr) {
     famg_comm *cm = dm->comm;
     famg_ctx *ctx = cm->ctx;
     CUDA_TRY(cudaStreamWaitEvent(ctx->comm_stream, ev_b, 0));
     ctx->comm_used.store(true, std::memory_order_relaxed);
-    FAMG_TRY(p2p_exchange(cm, h, x_ext, ctx->comm_stream, sig, target));
+    // next to a running producer the exchange kernel only gets the CTA slots that kernel left free
+    FAMG_TRY(p2p_exchange(cm, h, x_ext, ctx->comm_stream, sig, target, (sig || sd) ? std::max(dm->reserve_ctas, 1) : 64, sd, sf));
     CUDA_TRY(cudaEventRecord(dm->pending_ev, ctx->comm_stream));
     dm->pending = true;
     return FAMG_OK;
@@ -511,8 +517,16 @@ static famg_status dist_cycle_push(famg_dist_mg *dm, int level, double *va, cons
     int pre = nu;
     if (zero_guess) {
         if (((nu - 1) + nu) & 1) std::swap(cur, oth);
-        FAMG_TRY(vec_scale_rows(ctx, L.d, f, 0, cur, 0, nloc, 1));
-        FAMG_TRY(exch_async(dm, *pa, cur));
+        if (dm->overlap_mode == 2 && pa->any && cm->nranks > 1) {
+            // v = d .* f: the exchange kernel forms the entries the peers need from d and f itself, next to the scaling kernel
+            cudaEvent_t ev_b = nullptr;
+            FAMG_TRY(exch_fork(dm, &ev_b));
+            FAMG_TRY(vec_scale_rows(ctx, L.d, f, 0, cur, 0, nloc, 1));
+            FAMG_TRY(exch_launch(dm, ev_b, *pa, cur, nullptr, 0, L.d, f));
+        } else {
+            FAMG_TRY(vec_scale_rows(ctx, L.d, f, 0, cur, 0, nloc, 1));
+            FAMG_TRY(exch_async(dm, *pa, cur));
+        }
         pre -= 1;
     } else {
         FAMG_TRY(exch_async(dm, *pa, cur));  // W-cycle revisit: the iterate was produced without a push for this plan

@@ -177,7 +177,7 @@ struct famg_dist_mg {
     bool overlap = true;
     int overlap_mode = 2;       // FAMG_OVERLAP: 0 exchange in front of every apply (round-1 order), 1 producer-side exchange after
                                 // the producing kernel, 2 producer-side exchange running next to the producing kernel
-    int reserve_ctas = 32;      // CTA slots the persistent producer leaves to the exchange kernel (FAMG_RESERVE_CTAS)
+    int reserve_ctas = 16;      // CTA slots the persistent producer leaves to the exchange kernel, which uses at most as many (FAMG_RESERVE_CTAS)
     unsigned *d_sig = nullptr;  // finished-boundary-chunk counter of the producer kernel in flight
     bool pending = false;       // an exchange is in flight on the communication stream
     cudaEvent_t pending_ev = nullptr;
