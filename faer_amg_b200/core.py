@@ -69,6 +69,10 @@ class Context:
         """Kernel-selection knobs for A/B measurements (see famg_ctx_set_option)."""
         call("famg_ctx_set_option", self._h, key.encode(), int(value))
 
+    def trace_dump(self, path: str):
+        """Text dump of the in-kernel timeline collected since ``set_option("trace", 1)``."""
+        call("famg_ctx_trace_dump", self._h, path.encode())
+
     def launch_count(self) -> int:
         n = C.c_int64()
         call("famg_ctx_launch_count", self._h, C.byref(n))

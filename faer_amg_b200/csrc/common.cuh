@@ -59,6 +59,10 @@ struct famg_ctx {
     cudaEvent_t ev_release = nullptr;    // orders operator frees after work queued on comm_stream
     std::atomic<bool> comm_used{false};  // set once anything has been queued on comm_stream
     std::atomic<int64_t> option_epoch{0};  // bumped by famg_ctx_set_option: captured graphs are keyed on it
+    // in-kernel timeline (set_option("trace", 1)): [0] = record count, then (tag, globaltimer ns) pairs written by the
+    // traced kernels; trace_desc[id] describes launch `id` (ids are baked into captured graphs)
+    unsigned long long *d_trace = nullptr;
+    std::vector<std::string> trace_desc;
     std::atomic<int64_t> launches{0};
     // small persistent scratch: scalars for dots / norms, pinned host mirror
     double *d_scalars = nullptr;  // 64 doubles
@@ -164,6 +168,24 @@ void pool_free(famg_ctx *ctx, void *p, size_t bytes);
 void pool_trim(famg_ctx *ctx);
 
 inline void count_launch(famg_ctx *ctx, int n = 1) { ctx->launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---------------------------------------------------------------- in-kernel timeline
+constexpr unsigned long long TRACE_CAP = 1ull << 18;  // records
+enum TraceKind { TR_BEGIN = 1, TR_END = 2, TR_SIG_OK = 3, TR_PACKED = 4, TR_FLAG_OK = 5 };
+// new launch id with a description, or -1 when tracing is off
+int trace_new_id(famg_ctx *ctx, const char *fmt, ...);
+#ifdef __CUDACC__
+__device__ __forceinline__ void trace_rec(unsigned long long *tr, unsigned kind, int id) {
+    if (!tr) return;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    const unsigned long long slot = atomicAdd(tr, 1ull);
+    if (slot < TRACE_CAP) {
+        tr[1 + 2 * slot] = ((unsigned long long)kind << 48) | ((unsigned long long)(unsigned)id << 16) | (unsigned long long)(blockIdx.x & 0xffffu);
+        tr[2 + 2 * slot] = t;
+    }
+}
+#endif
 
 // ---------------------------------------------------------------- device primitives (scan.cu)
 // exclusive scan of n ints; out[n] = total (out has n+1 entries). in may alias out.

@@ -15,6 +15,18 @@ void set_error(const char *fmt, ...) {
 }
 const char *get_error() { return g_err; }
 
+int trace_new_id(famg_ctx *ctx, const char *fmt, ...) {
+    if (!ctx->d_trace) return -1;
+    char buf[256];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->trace_desc.emplace_back(buf);
+    return (int)ctx->trace_desc.size() - 1;
+}
+
 // ---------------------------------------------------------------- scan
 // Three-phase exclusive scan (block sums -> recursive scan -> add offsets). Deterministic.
 constexpr int SCAN_THREADS = 256;
@@ -350,7 +362,7 @@ famg_status famg_ctx_destroy(famg_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->comm_stream);
     pool_trim(ctx);
-    cudaFree(ctx->d_scalars); cudaFreeHost(ctx->h_scalars); cudaFree(ctx->d_partials); cudaFree(ctx->pcg_ws);
+    cudaFree(ctx->d_scalars); cudaFreeHost(ctx->h_scalars); cudaFree(ctx->d_partials); cudaFree(ctx->pcg_ws); cudaFree(ctx->d_trace);
     if (ctx->ev_release) cudaEventDestroy(ctx->ev_release);
     cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->comm_stream);
     delete ctx;
@@ -395,10 +407,42 @@ famg_status famg_ctx_set_option(famg_ctx *ctx, const char *key, int64_t value) {
     } else if (!strcmp(key, "spmm_cb")) {
         if (value != 1 && value != 2) FAMG_FAIL(FAMG_ERR_INVALID, "spmm_cb must be 1 or 2");
         ctx->spmm_cb = (int)value;
+    } else if (!strcmp(key, "trace")) {
+        CUDA_TRY(cudaSetDevice(ctx->device));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (value && !ctx->d_trace) {
+            CUDA_TRY(cudaMalloc((void **)&ctx->d_trace, sizeof(unsigned long long) * (1 + 2 * TRACE_CAP)));
+        }
+        if (ctx->d_trace) CUDA_TRY(cudaMemset(ctx->d_trace, 0, sizeof(unsigned long long)));  // value == 0 / repeated 1: restart the record list
     } else {
         FAMG_FAIL(FAMG_ERR_INVALID, "unknown option '%s'", key);
     }
     ctx->option_epoch.fetch_add(1);  // kernel selection changed: graphs captured before must not be replayed
+    return FAMG_OK;
+}
+
+// Writes the in-kernel timeline collected since set_option("trace", 1) as text: one line per record,
+// "<launch id> <kind> <block> <globaltimer ns> <description of the launch>"; kinds: 1 kernel begin, 2 end, 3 exchange
+// kernel saw the producer's boundary rows, 4 its entries are packed into the neighbours, 5 the neighbours' entries arrived.
+famg_status famg_ctx_trace_dump(famg_ctx *ctx, const char *path) {
+    if (!ctx || !path) FAMG_FAIL(FAMG_ERR_INVALID, "null argument");
+    if (!ctx->d_trace) FAMG_FAIL(FAMG_ERR_INVALID, "tracing is off: famg_ctx_set_option(ctx, \"trace\", 1) first");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    unsigned long long n = 0;
+    CUDA_TRY(cudaMemcpy(&n, ctx->d_trace, sizeof(n), cudaMemcpyDeviceToHost));
+    n = std::min(n, TRACE_CAP);
+    std::vector<unsigned long long> rec(2 * (size_t)n);
+    if (n) CUDA_TRY(cudaMemcpy(rec.data(), ctx->d_trace + 1, sizeof(unsigned long long) * 2 * n, cudaMemcpyDeviceToHost));
+    FILE *f = fopen(path, "w");
+    if (!f) FAMG_FAIL(FAMG_ERR_INVALID, "cannot open %s", path);
+    for (unsigned long long i = 0; i < n; ++i) {
+        const unsigned long long tag = rec[2 * i];
+        const int id = (int)((tag >> 16) & 0xffffffffull);
+        const char *d = id >= 0 && id < (int)ctx->trace_desc.size() ? ctx->trace_desc[(size_t)id].c_str() : "?";
+        fprintf(f, "%d %d %d %llu %s\n", id, (int)(tag >> 48), (int)(tag & 0xffffull), rec[2 * i + 1], d);
+    }
+    fclose(f);
     return FAMG_OK;
 }
 

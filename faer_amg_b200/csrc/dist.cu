@@ -177,8 +177,10 @@ __device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned *p) {
 // by a kernel running next to this one: the entries to send are formed here from the operands (same product, same bits).
 __global__ void __launch_bounds__(256) p2p_exchange_kernel(const P2PPlanDev pl, double *__restrict__ x_ext, int nloc,
                                                            const int *__restrict__ send_idx, unsigned *sig, unsigned target,
-                                                           const double *__restrict__ sd, const double *__restrict__ sf) {
+                                                           const double *__restrict__ sd, const double *__restrict__ sf,
+                                                           unsigned long long *trace, int trace_id) {
     __shared__ bool s_last;
+    if (threadIdx.x == 0) trace_rec(trace, TR_BEGIN, trace_id);
     if (sig) {
         if (threadIdx.x == 0) {
             const unsigned long long t0 = global_timer_ns();
@@ -188,6 +190,7 @@ __global__ void __launch_bounds__(256) p2p_exchange_kernel(const P2PPlanDev pl, 
         }
         __syncthreads();
     }
+    if (threadIdx.x == 0) trace_rec(trace, TR_SIG_OK, trace_id);
     const unsigned long long e = *pl.epoch + 1ull;
     const int par = (int)(e & 1ull);
     const int stride = gridDim.x * blockDim.x;
@@ -206,6 +209,7 @@ __global__ void __launch_bounds__(256) p2p_exchange_kernel(const P2PPlanDev pl, 
         if (threadIdx.x < pl.nnb) st_release_sys(pl.rflag[threadIdx.x], e);
         if (threadIdx.x == 0) { *pl.done = 0u; *pl.epoch = e; if (sig) *sig = 0u; }  // every CTA is past its wait on *sig
     }
+    if (threadIdx.x == 0) trace_rec(trace, TR_PACKED, trace_id);
     if (threadIdx.x < pl.nnb) {
         const unsigned long long t0 = global_timer_ns();
         while (ld_acquire_sys(pl.lflag[threadIdx.x]) < e) {
@@ -213,16 +217,22 @@ __global__ void __launch_bounds__(256) p2p_exchange_kernel(const P2PPlanDev pl, 
         }
     }
     __syncthreads();
+    if (threadIdx.x == 0) trace_rec(trace, TR_FLAG_OK, trace_id);
     const double *src = pl.lrecv[par];
     double *tail = x_ext + nloc;
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < pl.nghost; j += stride) tail[j] = __ldcg(src + j);
+    __syncthreads();
+    if (threadIdx.x == 0) trace_rec(trace, TR_END, trace_id);
 }
 
 static famg_status p2p_exchange(famg_comm *cm, const HaloPlan &h, double *x_ext, cudaStream_t st = nullptr, unsigned *sig = nullptr,
                                 unsigned target = 0, int max_ctas = 64, const double *sd = nullptr, const double *sf = nullptr) {
     const int work = std::max(h.total_send, h.nghost);
     const int grid = std::max(1, std::min(max_ctas, (work + 1023) / 1024));  // co-resident with the producer kernel when signalled
-    p2p_exchange_kernel<<<grid, 256, 0, st ? st : cm->ctx->stream>>>(h.dev, x_ext, h.nloc, h.d_send_idx, sig, target, sd, sf);
+    famg_ctx *ctx = cm->ctx;
+    const int tid = ctx->d_trace ? trace_new_id(ctx, "exchange send=%d ghost=%d ctas=%d%s%s", h.total_send, h.nghost, grid, sig ? " signalled" : "",
+                                                sd ? " scaled-pack" : "") : -1;
+    p2p_exchange_kernel<<<grid, 256, 0, st ? st : cm->ctx->stream>>>(h.dev, x_ext, h.nloc, h.d_send_idx, sig, target, sd, sf, ctx->d_trace, tid);
     count_launch(cm->ctx);
     KERNEL_CHECK();
     return FAMG_OK;

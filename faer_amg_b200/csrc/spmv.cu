@@ -58,6 +58,8 @@ struct SpmvKernelParams {
     // packing when the count is complete
     int nsig;
     unsigned *sig;
+    unsigned long long *trace;  // in-kernel timeline (CTA 0 stamps its begin / end), nullptr when off
+    int trace_id;
 };
 
 
@@ -164,6 +166,7 @@ __global__ void __launch_bounds__(SPMV_THREADS, CB == 1 ? 4 : 3) spmv_kernel(con
     __shared__ double s_red[SPMV_THREADS / 32];
 
     const int tid = threadIdx.x;
+    if (p.trace && tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) trace_rec(p.trace, TR_BEGIN, p.trace_id);
     int r0, r1;
     chunk_rows<ROWS>(p, blockIdx.x, r0, r1);
     const int q0 = __ldg(p.row_ptr + r0);
@@ -272,6 +275,7 @@ __global__ void __launch_bounds__(SPMV_THREADS, CB == 1 ? 4 : 3) spmv_kernel(con
         }
     }
     }  // CB == 1
+    if (p.trace && tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) trace_rec(p.trace, TR_END, p.trace_id);
 }
 
 // ===================================================================================================
@@ -340,6 +344,7 @@ __global__ void __launch_bounds__(TMA_THREADS, CB == 1 ? TMA_CTAS : 3) spmv_tma_
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
+    if (p.trace && tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) trace_rec(p.trace, TR_BEGIN, p.trace_id);
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < TMA_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], TMA_CONSUMERS / 32); }
@@ -461,6 +466,7 @@ __global__ void __launch_bounds__(TMA_THREADS, CB == 1 ? TMA_CTAS : 3) spmv_tma_
         }
         c = cn; q0 = nq0; q1 = nq1; a = na; e = ne;
     }
+    if (p.trace && tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) trace_rec(p.trace, TR_END, p.trace_id);
     if (DOT) {
         double v = dot_acc;
 #pragma unroll
@@ -549,6 +555,9 @@ famg_status spmv_launch(const SpmvArgs &args, int *num_ctas) {
     kp.b = args.b; kp.ldb = args.ldb; kp.d = args.d; kp.k = args.k;
     kp.dot_partials = args.dot_partials;
     kp.sig = args.sig; kp.nsig = args.sig ? args.sig_lo : 0;
+    kp.trace = ctx->d_trace;
+    kp.trace_id = ctx->d_trace ? trace_new_id(ctx, "spmv epi=%d rows=%lld nnz=%lld tpr=%d%s", args.epi, (long long)a->nrows, (long long)a->nnz,
+                                              a->tpr, args.sig ? " signalled" : "") : -1;
     if (args.sig) {  // boundary-first row order (see SpmvArgs::sig)
         if (args.k != 1 || args.sig_lo < 0 || args.sig_hi < args.sig_lo || args.sig_hi > (int)a->nrows || args.row_begin != 0 || args.row_end >= 0 ||
             args.row2_end > args.row2_begin)

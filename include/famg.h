@@ -372,6 +372,10 @@ famg_status famg_dist_mg_create_levels(famg_comm *c, int nlevels, famg_dmat *con
  * (right-hand sides per row walk for k > 1: 1 | 2).  Changing an option invalidates captured cycle graphs.
  * One solve at a time per context: PCG work vectors and reduction scratch are context-owned. */
 famg_status famg_ctx_set_option(famg_ctx *ctx, const char *key, int64_t value);
+/* In-kernel timeline: famg_ctx_set_option(ctx, "trace", 1) makes the SpMV-family and halo-exchange kernels launched (or
+ * captured) afterwards stamp %globaltimer at their begin / end and at the stages of an exchange; famg_ctx_trace_dump
+ * writes the records as text (see csrc/core.cu) and "trace" = 1 again restarts the list.  Diagnostics only. */
+famg_status famg_ctx_trace_dump(famg_ctx *ctx, const char *path);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 famg_status famg_ctx_launch_count(const famg_ctx *ctx, int64_t *count);
 /* time `reps` back-to-back launches of one fused kernel class with CUDA events on the context
