@@ -209,6 +209,8 @@ struct SpmvArgs {
     // producer-side halo exchange: all rows are computed, [sig_hi, nrows) and [0, sig_lo) first; every consumer warp adds
     // 1 to *sig per finished chunk of those rows (8 per chunk of 256 / tpr rows): spmv_signal_target() in total
     unsigned *sig = nullptr; int sig_lo = 0, sig_hi = 0;
+    // fused push (with sig): device P2PPlanDev of the plan through which y is consumed and its per-boundary-row push map
+    const void *push_plan = nullptr; const int *push_map = nullptr;
     cudaStream_t stream = nullptr;               // default: ctx stream
 };
 famg_status spmv_launch(const SpmvArgs &args, int *num_ctas = nullptr);

@@ -48,20 +48,6 @@ __global__ void pack_kernel(const double *__restrict__ x, const int *__restrict_
 }
 
 // ---------------------------------------------------------------- peer-memory exchange kernels
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long global_timer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-
 // Multi-CTA pack: every CTA stores a slice of each neighbour's entries into that neighbour's
 // receive buffer; the CTA that finishes last publishes the epoch (flags) -- the fine-level halo is
 // one xy-plane (0.5-2 MB), too much for a single SM's store throughput on the critical path.
@@ -223,6 +209,65 @@ __global__ void __launch_bounds__(256) p2p_exchange_kernel(const P2PPlanDev pl, 
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < pl.nghost; j += stride) tail[j] = __ldcg(src + j);
     __syncthreads();
     if (threadIdx.x == 0) trace_rec(trace, TR_END, trace_id);
+}
+
+// Receiving half of a fused exchange: the producer kernel on every rank has pushed its boundary rows into the peers' receive
+// buffers and published the epoch; wait for the neighbours' flags, move the ghosts into the vector's tail, advance the epoch.
+__global__ void __launch_bounds__(256) p2p_recv_kernel(const P2PPlanDev pl, double *__restrict__ tail, unsigned long long *trace, int trace_id) {
+    __shared__ bool s_last;
+    if (threadIdx.x == 0) trace_rec(trace, TR_BEGIN, trace_id);
+    const unsigned long long e = *pl.epoch + 1ull;
+    if (threadIdx.x < pl.nnb) {
+        const unsigned long long t0 = global_timer_ns();
+        while (ld_acquire_sys(pl.lflag[threadIdx.x]) < e) {
+            if (global_timer_ns() - t0 > 20000000000ull) { atomicExch(pl.err, 1); break; }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) trace_rec(trace, TR_FLAG_OK, trace_id);
+    const double *src = pl.lrecv[e & 1ull];
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < pl.nghost; j += gridDim.x * blockDim.x) tail[j] = __ldcg(src + j);
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(pl.done, 1u) + 1u == gridDim.x;  // every CTA has read the epoch by now
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) { *pl.done = 0u; *pl.epoch = e; }
+    if (threadIdx.x == 0) trace_rec(trace, TR_END, trace_id);
+}
+
+// v = d .* f (first sweep from a zero guess) with the fused push: the entries the peers need are formed, stored to the
+// neighbours and published first, then the whole vector is written.
+__global__ void __launch_bounds__(256) scale_push_kernel(const double *__restrict__ d, const double *__restrict__ f, double *__restrict__ v,
+                                                         int n, const P2PPlanDev *__restrict__ pl, const int *__restrict__ push_map, int push_lo,
+                                                         int push_hi, unsigned *sig) {
+    const int nb_rows = push_lo + (n - push_hi);
+    const unsigned long long e = *pl->epoch + 1ull;
+    for (int mi = blockIdx.x * blockDim.x + threadIdx.x; mi < nb_rows; mi += gridDim.x * blockDim.x) {
+        const int m = push_map[mi];
+        if (m < 0) continue;
+        const int row = mi < push_lo ? mi : push_hi + (mi - push_lo);
+        pl->rdst[e & 1ull][m >> PUSH_SLOT_BITS][m & ((1 << PUSH_SLOT_BITS) - 1)] = d[row] * f[row];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned old = atomicAdd(sig, 1u);
+        if (old + 1u == gridDim.x) {
+            __threadfence_system();
+            for (int nb = 0; nb < pl->nnb; ++nb) st_release_sys(pl->rflag[nb], e);
+            *sig = 0u;
+        }
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v[i] = d[i] * f[i];
+}
+
+static famg_status p2p_recv(famg_comm *cm, const HaloPlan &h, double *x_ext) {
+    famg_ctx *ctx = cm->ctx;
+    const int grid = std::max(1, std::min(32, (h.nghost + 2047) / 2048));
+    const int tid = ctx->d_trace ? trace_new_id(ctx, "recv ghost=%d ctas=%d", h.nghost, grid) : -1;
+    p2p_recv_kernel<<<grid, 256, 0, ctx->stream>>>(h.dev, x_ext + h.nloc, ctx->d_trace, tid);
+    count_launch(ctx);
+    KERNEL_CHECK();
+    return FAMG_OK;
 }
 
 static famg_status p2p_exchange(famg_comm *cm, const HaloPlan &h, double *x_ext, cudaStream_t st = nullptr, unsigned *sig = nullptr,
@@ -466,6 +511,16 @@ static famg_status dist_apply_push(famg_dist_mg *dm, const DistOp &op, int epi, 
         if (num_partials) *num_partials = n;
         return FAMG_OK;
     }
+    if (dm->overlap_mode == 3 && next->fusable && spmv_signal_target(op.local, next->push_lo, next->push_hi) > 0) {
+        // Fused push: the kernel computes the rows the peers need first and stores them straight into the neighbours' receive
+        // buffers; the warp finishing the last of them publishes the epoch.  What is left of the exchange is a small
+        // kernel after it that finds the neighbours' flags already set and moves the ghosts into the tail.
+        g.sig = dm->d_sig; g.sig_lo = next->push_lo; g.sig_hi = next->push_hi;
+        g.push_plan = next->d_dev; g.push_map = next->d_push_map;
+        FAMG_TRY(spmv_launch(g, &n));
+        if (num_partials) *num_partials = n;
+        return p2p_recv(dm->comm, *next, y);
+    }
     if (dm->overlap_mode != 2) {  // exchange after the whole apply (no overlap)
         FAMG_TRY(spmv_launch(g, &n));
         if (num_partials) *num_partials = n;
@@ -527,7 +582,13 @@ static famg_status dist_cycle_push(famg_dist_mg *dm, int level, double *va, cons
     int pre = nu;
     if (zero_guess) {
         if (((nu - 1) + nu) & 1) std::swap(cur, oth);
-        if (dm->overlap_mode == 2 && pa->any && cm->nranks > 1) {
+        if (dm->overlap_mode == 3 && pa->fusable && pa->any && cm->nranks > 1 && nloc > 0) {
+            const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(nloc, 1024), 8 * (int64_t)ctx->num_sms));
+            scale_push_kernel<<<grid, 256, 0, ctx->stream>>>(L.d, f, cur, (int)nloc, pa->d_dev, pa->d_push_map, pa->push_lo, pa->push_hi, dm->d_sig);
+            count_launch(ctx);
+            KERNEL_CHECK();
+            FAMG_TRY(p2p_recv(cm, *pa, cur));
+        } else if (dm->overlap_mode == 2 && pa->any && cm->nranks > 1) {
             // v = d .* f: the exchange kernel forms the entries the peers need from d and f itself, next to the scaling kernel
             cudaEvent_t ev_b = nullptr;
             FAMG_TRY(exch_fork(dm, &ev_b));
@@ -713,6 +774,29 @@ static famg_status p2p_setup(famg_dist_mg *d) {
             v.soff[nb] = h->send_off[p]; v.scnt[nb] = h->send_cnt[p];
         }
         h->p2p = h->any && v.nnb > 0;
+        // fused push: device copy of the plan and the (neighbour, slot) of every boundary row
+        if (h->p2p) {
+            const int nb_rows = h->push_lo + (h->nloc - h->push_hi);
+            std::vector<int> map((size_t)std::max(nb_rows, 1), -1);
+            bool fusable = (int)h->send_idx_host.size() == h->total_send && h->total_send > 0;
+            for (int nb = 0; nb < v.nnb && fusable; ++nb) {
+                if (v.scnt[nb] >= (1 << PUSH_SLOT_BITS)) { fusable = false; break; }
+                for (int j = 0; j < v.scnt[nb]; ++j) {
+                    const int i = h->send_idx_host[(size_t)(v.soff[nb] + j)];
+                    const int mi = i < h->push_lo ? i : (i >= h->push_hi ? h->push_lo + (i - h->push_hi) : -1);
+                    if (mi < 0 || mi >= nb_rows || map[(size_t)mi] != -1) { fusable = false; break; }  // a row two peers need: pack kernel instead
+                    map[(size_t)mi] = (nb << PUSH_SLOT_BITS) | j;
+                }
+            }
+            for (int nb = 0; nb < v.nnb && fusable; ++nb) fusable = v.scnt[nb] > 0;  // somebody has to publish towards every neighbour
+            if (fusable) {
+                FAMG_TRY(dev_alloc(&h->d_dev, 1));
+                FAMG_TRY(dev_alloc(&h->d_push_map, (int64_t)map.size()));
+                CUDA_TRY(cudaMemcpy(h->d_dev, &v, sizeof(v), cudaMemcpyHostToDevice));
+                CUDA_TRY(cudaMemcpy(h->d_push_map, map.data(), sizeof(int) * map.size(), cudaMemcpyHostToDevice));
+            }
+            h->fusable = fusable;
+        }
     }
     {   // collective descriptors
         P2PCollDev &c = d->coll;
@@ -825,7 +909,7 @@ static famg_status dist_mg_finish(famg_dist_mg *d, int diag_kind, double omega, 
     famg_ctx *ctx = c->ctx;
     const int lrep = d->lrep;
     if (const char *v = getenv("FAMG_DIST_GRAPH")) d->use_graph = atoi(v) != 0;
-    if (const char *v = getenv("FAMG_OVERLAP")) { d->overlap_mode = std::min(std::max(atoi(v), 0), 2); d->overlap = d->overlap_mode != 0; }
+    if (const char *v = getenv("FAMG_OVERLAP")) { d->overlap_mode = std::min(std::max(atoi(v), 0), 3); d->overlap = d->overlap_mode != 0; }
     if (const char *v = getenv("FAMG_OVERLAP_MIN_ROWS")) d->split_min_rows = std::max(atoi(v), 1);
     if (const char *v = getenv("FAMG_RESERVE_CTAS")) d->reserve_ctas = std::max(atoi(v), 0);
     FAMG_TRY(mg_ensure_workspace(d->global, 1));

@@ -4,6 +4,7 @@
 #include <nccl.h>
 
 #include "mg_internal.cuh"
+#include "p2p_dev.cuh"
 
 namespace famg {
 
@@ -49,28 +50,7 @@ struct famg_comm {
 
 namespace famg {
 
-// ---------------------------------------------------------------- halo plans
-// Peer-memory halo exchange (NVLink loads/stores instead of NCCL send/recv): every rank owns an
-// "arena" exported with CUDA IPC; per plan it holds one flag per peer, an epoch counter and two
-// receive buffers (parity = epoch & 1).  A pack kernel stores this rank's boundary entries straight
-// into its neighbours' receive buffers, fences, and publishes the epoch in their flag slots; the
-// consumer spins on its own flag slots (acquire, with a 20 s timeout) and moves the ghosts into the
-// vector's tail.  Epochs live in device memory, so the sequence replays inside CUDA graphs.
-constexpr int P2P_MAX_NB = 8;
-struct P2PPlanDev {
-    int nnb;                                  // neighbours (peers we exchange flags with, both ways)
-    int nghost;
-    double *rdst[2][P2P_MAX_NB];              // where my entries go on neighbour nb (per parity)
-    unsigned long long *rflag[P2P_MAX_NB];    // my slot in neighbour nb's flag array
-    const unsigned long long *lflag[P2P_MAX_NB];  // neighbour nb's slot in my flag array
-    int soff[P2P_MAX_NB], scnt[P2P_MAX_NB];   // my pack-list range for neighbour nb
-    unsigned long long *epoch;                // this plan's exchange counter (device)
-    unsigned int *done;                       // blocks of the pack kernel that have finished their stores
-    int total_send;
-    const double *lrecv[2];                   // my receive buffers
-    int *err;                                 // set on spin timeout
-};
-
+// ---------------------------------------------------------------- halo plans (P2PPlanDev: p2p_dev.cuh)
 // Small collectives over the same arenas: sum-all-reduce of <= 4 doubles (PCG dot products) and the
 // all-gather of the restricted residual at the replicated-level transition.  Every rank stores its
 // contribution into every peer's slot, publishes the epoch, waits for all peers, then reduces in
@@ -107,6 +87,12 @@ struct HaloPlan {
     // rows outside [push_lo, push_hi) hold every entry some peer needs (the send list): a producer computes them
     // first, so that the exchange of its output can start while the remaining rows are still being computed
     int push_lo = 0, push_hi = 0;
+    std::vector<int> send_idx_host;  // the send list (local ids, grouped by peer)
+    // fused push (set up with the peer-memory arenas): device copy of `dev`, and per boundary row -- rows [0, push_lo) then
+    // [push_hi, nloc) -- the (neighbour, slot) its value goes to, or -1.  fusable: every sent row has exactly one destination.
+    P2PPlanDev *d_dev = nullptr;
+    int *d_push_map = nullptr;
+    bool fusable = false;
 };
 
 // One (virtual) rank's share of a row-partitioned operator.  Columns are global indices until the
@@ -175,8 +161,9 @@ struct famg_dist_mg {
     // producer-side halo exchange on the communication stream, overlapped with the rows nobody is waiting for
     // (peer-memory mode; FAMG_OVERLAP=0 keeps the exchange in front of every apply)
     bool overlap = true;
-    int overlap_mode = 2;       // FAMG_OVERLAP: 0 exchange in front of every apply (round-1 order), 1 producer-side exchange after
-                                // the producing kernel, 2 producer-side exchange running next to the producing kernel
+    int overlap_mode = 3;       // FAMG_OVERLAP: 0 exchange in front of every apply (round-1 order), 1 producer-side exchange after
+                                // the producing kernel, 2 producer-side exchange running next to the producing kernel, 3 fused
+                                // push: the producing kernel stores its boundary rows into the neighbours and publishes them
     int reserve_ctas = 16;      // CTA slots the persistent producer leaves to the exchange kernel, which uses at most as many (FAMG_RESERVE_CTAS)
     unsigned *d_sig = nullptr;  // finished-boundary-chunk counter of the producer kernel in flight
     bool pending = false;       // an exchange is in flight on the communication stream

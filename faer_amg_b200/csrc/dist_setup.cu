@@ -209,7 +209,10 @@ __global__ void shift_rowptr_kernel(const int *__restrict__ in, int *__restrict_
 }
 
 // ================================================================================ helpers
-void halo_free(HaloPlan &h) { cudaFree(h.d_send_idx); cudaFree(h.d_sendbuf); h.d_send_idx = nullptr; h.d_sendbuf = nullptr; }
+void halo_free(HaloPlan &h) {
+    cudaFree(h.d_send_idx); cudaFree(h.d_sendbuf); cudaFree(h.d_dev); cudaFree(h.d_push_map);
+    h.d_send_idx = nullptr; h.d_sendbuf = nullptr; h.d_dev = nullptr; h.d_push_map = nullptr;
+}
 void distop_free(DistOp &o) {
     if (o.local) csr_release(o.local);
     o.local = nullptr;
@@ -386,6 +389,7 @@ famg_status dmat_finalize(famg_dmat *m, bool replicated_cols) {
             if (v < h.nloc / 2) h.push_lo = std::max(h.push_lo, v + 1); else h.push_hi = std::min(h.push_hi, v);
         }
         if (h.push_hi < h.push_lo) h.push_hi = h.push_lo;
+        h.send_idx_host.swap(sidx);
     }
     pool_free(ctx, lo_hi, 256);
     m->finalized = true;

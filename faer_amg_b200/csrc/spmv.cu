@@ -23,6 +23,7 @@
 // Compiled with -fmad=false: products and sums are rounded separately, like the reference's
 // scalar `dst += a*b` loops.
 #include "common.cuh"
+#include "p2p_dev.cuh"
 
 namespace famg {
 
@@ -58,10 +59,49 @@ struct SpmvKernelParams {
     // packing when the count is complete
     int nsig;
     unsigned *sig;
+    // fused push: the rows of the signalled chunks also go straight into the neighbours' receive buffers, and the warp
+    // that completes the count (sig_target) publishes the epoch in their flag slots -- no pack kernel at all
+    const P2PPlanDev *push_plan;
+    const int *push_map;
+    int push_lo;
+    unsigned sig_target;
     unsigned long long *trace;  // in-kernel timeline (CTA 0 stamps its begin / end), nullptr when off
     int trace_id;
 };
 
+
+
+// End of a signalled chunk (warp-uniform call): count it; with a push plan, first store this row's value into the
+// neighbour that needs it, and let the warp that completes the count publish the exchange.  Out of line: the rare
+// path must not cost the row walk any registers.
+__device__ __noinline__ void chunk_signal(const P2PPlanDev *pl, const int *push_map, int push_lo, int push_hi, unsigned *sig,
+                                          unsigned sig_target, const double *y, int row, bool owner) {
+    if (pl != nullptr) {
+        if (owner) {
+            const int mi = row < push_lo ? row : row - push_hi + push_lo;
+            const int m = __ldg(push_map + mi);
+            if (m >= 0) {
+                const unsigned long long e = *pl->epoch + 1ull;
+                pl->rdst[e & 1ull][m >> PUSH_SLOT_BITS][m & ((1 << PUSH_SLOT_BITS) - 1)] = y[row];
+            }
+        }
+        __syncwarp();
+        __threadfence_system();
+        if ((threadIdx.x & 31) == 0) {
+            const unsigned old = atomicAdd(sig, 1u);
+            if (old + 1u == sig_target) {  // every boundary row is stored here and pushed to its neighbour
+                __threadfence_system();
+                const unsigned long long e = *pl->epoch + 1ull;
+                for (int nb = 0; nb < pl->nnb; ++nb) st_release_sys(pl->rflag[nb], e);
+                *sig = 0u;
+            }
+        }
+        return;
+    }
+    __syncwarp();
+    __threadfence();
+    if ((threadIdx.x & 31) == 0) atomicAdd(sig, 1u);
+}
 
 // chunk index -> [r0, r1) over the (up to two) row ranges of a launch
 template <int ROWS>
@@ -255,11 +295,8 @@ __global__ void __launch_bounds__(SPMV_THREADS, CB == 1 ? 4 : 3) spmv_kernel(con
         }
         if (active && lane == 0) epi_store<EPI, DOT>(yc, row, s, ops, dot_acc);
     }
-    if ((int)blockIdx.x < p.nsig) {  // warp-uniform
-        __syncwarp();
-        __threadfence();
-        if ((tid & 31) == 0) atomicAdd(p.sig, 1u);
-    }
+    if ((int)blockIdx.x < p.nsig)  // warp-uniform; signalled launches: row_begin == push_hi
+        chunk_signal(p.push_plan, p.push_map, p.push_lo, p.row_begin, p.sig, p.sig_target, p.y, row, active && lane == 0);
     if (DOT) {
         // deterministic CTA reduction of x_i * (A x)_i -> one partial per CTA
         double v = dot_acc;
@@ -454,11 +491,8 @@ __global__ void __launch_bounds__(TMA_THREADS, CB == 1 ? TMA_CTAS : 3) spmv_tma_
             }
             if (active && lane == 0) epi_store<EPI, DOT>(yc, row, s, ops, dot_acc);
         }
-        if (c < p.nsig) {  // warp-uniform: this chunk's rows are awaited by the exchange kernel
-            __syncwarp();
-            __threadfence();
-            if ((tid & 31) == 0) atomicAdd(p.sig, 1u);
-        }
+        if (c < p.nsig)  // warp-uniform: this chunk's rows are awaited by the peers (signalled launches: row_begin == push_hi)
+            chunk_signal(p.push_plan, p.push_map, p.push_lo, p.row_begin, p.sig, p.sig_target, p.y, row, active && lane == 0);
         if (staged) {
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(&empty[stage]);
@@ -555,6 +589,8 @@ famg_status spmv_launch(const SpmvArgs &args, int *num_ctas) {
     kp.b = args.b; kp.ldb = args.ldb; kp.d = args.d; kp.k = args.k;
     kp.dot_partials = args.dot_partials;
     kp.sig = args.sig; kp.nsig = args.sig ? args.sig_lo : 0;
+    kp.push_plan = args.sig ? (const P2PPlanDev *)args.push_plan : nullptr; kp.push_map = args.push_map; kp.push_lo = args.sig_lo;
+    kp.sig_target = args.sig ? spmv_signal_target(a, args.sig_lo, args.sig_hi) : 0u;
     kp.trace = ctx->d_trace;
     kp.trace_id = ctx->d_trace ? trace_new_id(ctx, "spmv epi=%d rows=%lld nnz=%lld tpr=%d%s", args.epi, (long long)a->nrows, (long long)a->nnz,
                                               a->tpr, args.sig ? " signalled" : "") : -1;

@@ -56,8 +56,8 @@ def main():
             dh = DistHierarchy(comm, a0, nn, DistGeometricPartitioner(dims), coarsest_dim=1000, replicate_below=rep_below)
         except ValueError:
             break
-        for mode, graph in (("2", "1"), ("1", "1"), ("0", "1"), ("2", "0")):
-            if rep_below != 4096 and mode == "1":
+        for mode, graph in (("3", "1"), ("2", "1"), ("0", "1"), ("3", "0")):
+            if rep_below != 4096 and mode == "2":
                 continue
             os.environ["FAMG_OVERLAP"] = mode
             os.environ["FAMG_DIST_GRAPH"] = graph
