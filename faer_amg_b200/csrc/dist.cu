@@ -789,6 +789,9 @@ static famg_status p2p_setup(famg_dist_mg *d) {
                 }
             }
             for (int nb = 0; nb < v.nnb && fusable; ++nb) fusable = v.scnt[nb] > 0;  // somebody has to publish towards every neighbour
+            // Measured on 8 B200 (profiles/r2_timeline_*): when most rows of a slab are boundary rows (thin slabs of the coarse
+            // levels) the per-warp system fences and counter updates cost the producer more than the pack kernel they replace.
+            if (fusable && (int64_t)nb_rows * 100 > (int64_t)h->nloc * d->fuse_max_boundary_pct) fusable = false;
             if (fusable) {
                 FAMG_TRY(dev_alloc(&h->d_dev, 1));
                 FAMG_TRY(dev_alloc(&h->d_push_map, (int64_t)map.size()));
@@ -912,6 +915,7 @@ static famg_status dist_mg_finish(famg_dist_mg *d, int diag_kind, double omega, 
     if (const char *v = getenv("FAMG_OVERLAP")) { d->overlap_mode = std::min(std::max(atoi(v), 0), 3); d->overlap = d->overlap_mode != 0; }
     if (const char *v = getenv("FAMG_OVERLAP_MIN_ROWS")) d->split_min_rows = std::max(atoi(v), 1);
     if (const char *v = getenv("FAMG_RESERVE_CTAS")) d->reserve_ctas = std::max(atoi(v), 0);
+    if (const char *v = getenv("FAMG_FUSE_MAX_BOUNDARY_PCT")) d->fuse_max_boundary_pct = std::max(atoi(v), 0);
     FAMG_TRY(mg_ensure_workspace(d->global, 1));
     famg_status st = FAMG_OK;
     for (int l = 0; l < lrep && st == FAMG_OK; ++l) {

@@ -164,6 +164,7 @@ struct famg_dist_mg {
     int overlap_mode = 3;       // FAMG_OVERLAP: 0 exchange in front of every apply (round-1 order), 1 producer-side exchange after
                                 // the producing kernel, 2 producer-side exchange running next to the producing kernel, 3 fused
                                 // push: the producing kernel stores its boundary rows into the neighbours and publishes them
+    int fuse_max_boundary_pct = 20;  // fused push only for plans whose boundary rows are at most this share of the slab (FAMG_FUSE_MAX_BOUNDARY_PCT)
     int reserve_ctas = 16;      // CTA slots the persistent producer leaves to the exchange kernel, which uses at most as many (FAMG_RESERVE_CTAS)
     unsigned *d_sig = nullptr;  // finished-boundary-chunk counter of the producer kernel in flight
     bool pending = false;       // an exchange is in flight on the communication stream
