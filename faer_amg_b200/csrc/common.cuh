@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <map>
 #include <mutex>
 #include <string>
@@ -168,6 +169,15 @@ void pool_free(famg_ctx *ctx, void *p, size_t bytes);
 void pool_trim(famg_ctx *ctx);
 
 inline void count_launch(famg_ctx *ctx, int n = 1) { ctx->launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---------------------------------------------------------------- setup phase timer (FAMG_SETUP_TRACE=1 -> stderr)
+struct PhaseTimer {
+    famg_ctx *ctx; const char *what; bool on; double t0 = 0;
+    static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+    static bool enabled() { static const bool e = getenv("FAMG_SETUP_TRACE") != nullptr; return e; }
+    PhaseTimer(famg_ctx *c, const char *w) : ctx(c), what(w), on(enabled()) { if (on) { cudaStreamSynchronize(ctx->stream); t0 = now(); } }
+    ~PhaseTimer() { if (on) { cudaStreamSynchronize(ctx->stream); fprintf(stderr, "[setup]   %-34s %9.3f ms\n", what, now() - t0); } }
+};
 
 // ---------------------------------------------------------------- in-kernel timeline
 constexpr unsigned long long TRACE_CAP = 1ull << 18;  // records

@@ -878,6 +878,7 @@ famg_status famg_dist_coarsen(famg_dmat *a, const int64_t *n_aggs, const uint64_
 #define CO_TRY(expr) do { famg_status s__ = (expr); if (s__ != FAMG_OK) return fail(s__); } while (0)
     // tentative prolongator of the rank's own aggregates (interpolation/mod.rs:747-809), global coarse ids
     for (int li = 0; li < nl; ++li) {
+        PhaseTimer pt(ctx, "tentative P (host) + upload");
         const int r = cm->vrank(li);
         const int64_t nloc = a->rsplit[(size_t)r + 1] - a->rsplit[(size_t)r];
         famg_csr *p0 = nullptr;
@@ -891,7 +892,8 @@ famg_status famg_dist_coarsen(famg_dmat *a, const int64_t *n_aggs, const uint64_
     }
     // P <- (I - w D^-1 A) P  (interpolation/mod.rs:812-818, 927-946)
     for (int s = 0; s < smoothing_steps; ++s) {
-        CO_TRY(ext_rows(cm, aops, cur, ext));
+        { PhaseTimer pt(ctx, "ghost rows of P0"); CO_TRY(ext_rows(cm, aops, cur, ext)); }
+        PhaseTimer pt(ctx, "SpGEMM (I - w D^-1 A) P0");
         for (int li = 0; li < nl; ++li) {
             famg_csr *next = nullptr;
             CO_TRY(spgemm_impl(aops[(size_t)li]->local, ext[(size_t)li], cur[(size_t)li], omega, &next));
@@ -905,24 +907,25 @@ famg_status famg_dist_coarsen(famg_dmat *a, const int64_t *n_aggs, const uint64_
     {
         std::vector<famg_csr *> pl((size_t)nl);
         for (int li = 0; li < nl; ++li) pl[(size_t)li] = P->part[(size_t)li].local;
-        CO_TRY(ext_rows(cm, aops, pl, ext));
+        { PhaseTimer pt(ctx, "ghost rows of P"); CO_TRY(ext_rows(cm, aops, pl, ext)); }
+        PhaseTimer pt(ctx, "SpGEMM A P");
         for (int li = 0; li < nl; ++li) CO_TRY(spgemm_impl(aops[(size_t)li]->local, ext[(size_t)li], nullptr, 0.0, &ap[(size_t)li]));
         drop(ext);
     }
     // R = P^T by coarse owner (:824-827), then its halo plan over the fine split
-    CO_TRY(dist_transpose(P, &R));
-    CO_TRY(dmat_finalize(R, false));
+    { PhaseTimer pt(ctx, "R = P^T (transpose + exchange)"); CO_TRY(dist_transpose(P, &R)); }
+    { PhaseTimer pt(ctx, "halo plan of R"); CO_TRY(dmat_finalize(R, false)); }
     // A_c = R (A P)  (:828 outer)
     {
         std::vector<DistOp *> rops((size_t)nl);
         for (int li = 0; li < nl; ++li) rops[(size_t)li] = &R->part[(size_t)li];
-        CO_TRY(ext_rows(cm, rops, ap, ext));
+        { PhaseTimer pt(ctx, "ghost rows of AP"); CO_TRY(ext_rows(cm, rops, ap, ext)); }
         AC = dmat_new(cm, nc, nc, cs, cs);
+        PhaseTimer pt(ctx, "SpGEMM R (AP)");
         for (int li = 0; li < nl; ++li) CO_TRY(spgemm_impl(rops[(size_t)li]->local, ext[(size_t)li], nullptr, 0.0, &AC->part[(size_t)li].local));
         drop(ext);
     }
     drop(ap);
-    for (int li = 0; li < nl; ++li) CO_TRY(csr_finalize_plan(P->part[(size_t)li].local));
 #undef CO_TRY
     *p_out = P; *r_out = R; *ac_out = AC;
     return FAMG_OK;

@@ -372,31 +372,45 @@ class DistHierarchy:
         from .hierarchy import Hierarchy, HierarchyConfig, thin_q
         from .interpolation import AggregationConfig
         from .preconditioners.smoothers import StationaryIteration, new_l1
+        import os, time
         comm = self.comm
+        trace = os.environ.get("FAMG_SETUP_TRACE") is not None and comm.rank == 0
+
+        class T:
+            def __init__(s, what): s.what = what
+            def __enter__(s):
+                if trace: comm.ctx.sync(); s.t = time.perf_counter()
+            def __exit__(s, *a):
+                if trace: comm.ctx.sync(); print(f"[setup] {s.what:36s} {1e3 * (time.perf_counter() - s.t):9.3f} ms", file=__import__("sys").stderr, flush=True)
         level = 0
         while True:
-            P, R, Ac, cnn = self._coarsen_once(level)
+            with T(f"level {level}: coarsen (partition + dist_coarsen)"):
+                P, R, Ac, cnn = self._coarsen_once(level)
             nc = Ac.info()[0]
             self.P.append(P); self.R.append(R)
             if nc // comm.nranks < self.replicate_below or nc <= self.coarsest_dim:
                 # transition to the replicated tail: gather A_c and the coarse near-null, then the reference's own loop
-                P.finalize(True)
-                g = Ac.gather()
-                nn_g = comm.allgatherv(cnn).reshape(-1, 1)
-                l1 = new_l1(g)
-                nn_dev = DeviceMat.from_host(g.ctx, nn_g)
-                StationaryIteration(g, l1, 3).apply_in_place_dev(nn_dev)  # hierarchy.rs:217-226
-                nn_q = thin_q(nn_dev.to_host())                            # :228
-                cfg = HierarchyConfig(self.coarsest_dim, AggregationConfig(self.smoothing_steps, 1, self.partitioner.tail(level + 1)))
-                self.tail = Hierarchy(SparseMatOp(g), nn_q, None, cfg)
-                if nc > self.coarsest_dim:  # the level loop's own test (hierarchy.rs:199), already decided for this level
-                    self.tail.coarsen()
+                with T(f"level {level}: gather A_c + near-null"):
+                    P.finalize(True)
+                    g = Ac.gather()
+                    nn_g = comm.allgatherv(cnn).reshape(-1, 1)
+                with T("replicated tail (reference loop)"):
+                    l1 = new_l1(g)
+                    nn_dev = DeviceMat.from_host(g.ctx, nn_g)
+                    StationaryIteration(g, l1, 3).apply_in_place_dev(nn_dev)  # hierarchy.rs:217-226
+                    nn_q = thin_q(nn_dev.to_host())                            # :228
+                    cfg = HierarchyConfig(self.coarsest_dim, AggregationConfig(self.smoothing_steps, 1, self.partitioner.tail(level + 1)))
+                    self.tail = Hierarchy(SparseMatOp(g), nn_q, None, cfg)
+                    if nc > self.coarsest_dim:  # the level loop's own test (hierarchy.rs:199), already decided for this level
+                        self.tail.coarsen()
                 return
-            Ac.finalize(False)
-            P.finalize(False)
+            with T(f"level {level}: halo plans of A_c and P"):
+                Ac.finalize(False)
+                P.finalize(False)
             nl = comm.nlocal
             arr = (f64p * nl)(*[np.ascontiguousarray(v).ctypes.data_as(f64p) for v in cnn])
-            call("famg_dist_smooth_near_null", Ac._h, 3, arr)
+            with T(f"level {level}: near-null smoothing + thin Q"):
+                call("famg_dist_smooth_near_null", Ac._h, 3, arr)
             self.A.append(Ac)
             self.near_nulls.append(cnn)
             level += 1
