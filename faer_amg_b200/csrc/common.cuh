@@ -79,12 +79,6 @@ struct famg_ctx {
     int spmv_variant = 2;
     int tma_min_rows = 1 << 17;
     int spmm_cb = 2;  // right-hand sides per row walk for k > 1 (1 | 2); FAMG_SPMM_CB / set_option("spmm_cb")
-    // exact-size free lists for multivector storage: the host-pointer entry points (LinOp::apply,
-    // famg_pcg_solve) stage through device vectors on every call, and cudaMalloc/cudaFree cost
-    // milliseconds each; work on one context is stream-ordered, so a freed block can be reused
-    // immediately by later work on the same stream.
-    std::multimap<size_t, void *> pool;
-    size_t pool_bytes = 0;
 };
 
 struct famg_csr {

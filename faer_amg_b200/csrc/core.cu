@@ -1,6 +1,8 @@
 // core.cu -- context, CSR container, device multivectors, scan primitive.
 #include <cstdarg>
 
+#include <omp.h>
+
 #include "common.cuh"
 
 namespace famg {
@@ -97,7 +99,7 @@ famg_status exclusive_scan_i32(famg_ctx *ctx, const int *in, int *out, int64_t n
     }
     int64_t ntiles = ceil_div(n, SCAN_TILE);
     int *tile_sums = nullptr;
-    FAMG_TRY(dev_alloc(&tile_sums, ntiles + 1));
+    FAMG_TRY(pool_alloc(ctx, sizeof(int) * (size_t)(ntiles + 1), (void **)&tile_sums));
     scan_tile_kernel<<<(unsigned)ntiles, SCAN_THREADS, 0, ctx->stream>>>(in, out, tile_sums, n);
     count_launch(ctx);
     famg_status st = FAMG_OK;
@@ -112,8 +114,8 @@ famg_status exclusive_scan_i32(famg_ctx *ctx, const int *in, int *out, int64_t n
             count_launch(ctx, 2);
         }
     }
-    cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(tile_sums);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);  // callers read the total right away
+    pool_free(ctx, tile_sums, 0);
     if (st != FAMG_OK) return st;
     if (e != cudaSuccess) FAMG_FAIL(FAMG_ERR_CUDA, "scan failed: %s", cudaGetErrorString(e));
     KERNEL_CHECK();
@@ -127,8 +129,6 @@ static famg_status stream_alloc(famg_ctx *ctx, void **p, size_t bytes) {
     if (e == cudaErrorMemoryAllocation) {  // give cached blocks back and retry once
         cudaGetLastError();
         pool_trim(ctx);
-        cudaMemPool_t mp;
-        if (cudaDeviceGetDefaultMemPool(&mp, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(mp, 0);
         e = cudaMallocAsync(p, bytes ? bytes : 1, ctx->stream);
     }
     if (e != cudaSuccess) {
@@ -250,53 +250,22 @@ famg_status ensure_partials(famg_ctx *ctx, int64_t count) {
     return FAMG_OK;
 }
 
-famg_status pool_alloc(famg_ctx *ctx, size_t bytes, void **p) {
-    {
-        std::lock_guard<std::mutex> lk(ctx->mu);
-        auto it = ctx->pool.find(bytes);
-        if (it != ctx->pool.end()) {
-            *p = it->second;
-            ctx->pool.erase(it);
-            ctx->pool_bytes -= bytes;
-            return FAMG_OK;
-        }
-    }
-    cudaError_t e = cudaMalloc(p, bytes);
-    if (e == cudaErrorMemoryAllocation) {  // give cached blocks back and retry once
-        cudaGetLastError();
-        pool_trim(ctx);
-        cudaMemPool_t mp;
-        if (cudaDeviceGetDefaultMemPool(&mp, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(mp, 0);  // cached operator storage
-        e = cudaMalloc(p, bytes);
-    }
-    if (e != cudaSuccess) {
-        *p = nullptr;
-        set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
-        return e == cudaErrorMemoryAllocation ? FAMG_ERR_ALLOC : FAMG_ERR_CUDA;
-    }
-    return FAMG_OK;
-}
+// Temporaries and multivector storage come from the device's stream-ordered caching pool, like operator storage:
+// allocation and release are ordered on the context stream, never synchronise the device and never hand memory back to
+// the driver.  (Round 1 kept an exact-size free list in front of cudaMalloc / cudaFree; every new size -- and a
+// hierarchy build on row slabs has many -- paid a synchronising driver call, with sporadic stalls of 0.1-1.5 s measured
+// inside transposes and scans: profiles/r2_setup_phases.md.)
+famg_status pool_alloc(famg_ctx *ctx, size_t bytes, void **p) { return stream_alloc(ctx, p, bytes); }
 
 void pool_free(famg_ctx *ctx, void *p, size_t bytes) {
-    if (!p) return;
-    constexpr size_t POOL_CAP = (size_t)8 << 30;
-    std::unique_lock<std::mutex> lk(ctx->mu);
-    if (ctx->pool_bytes + bytes > POOL_CAP) {
-        lk.unlock();
-        cudaStreamSynchronize(ctx->stream);
-        cudaFree(p);
-        return;
-    }
-    ctx->pool.emplace(bytes, p);
-    ctx->pool_bytes += bytes;
+    (void)bytes;
+    if (p) cudaFreeAsync(p, ctx->stream);
 }
 
 void pool_trim(famg_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    for (auto &kv : ctx->pool) cudaFree(kv.second);
-    ctx->pool.clear();
-    ctx->pool_bytes = 0;
+    cudaMemPool_t mp;
+    if (cudaDeviceGetDefaultMemPool(&mp, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(mp, 0);
 }
 
 famg_status vec_wrap(famg_ctx *ctx, double *p, int64_t nrows, int64_t ncols, int64_t ld, famg_vec *out) {
@@ -443,6 +412,12 @@ famg_status famg_ctx_trace_dump(famg_ctx *ctx, const char *path) {
         fprintf(f, "%d %d %d %llu %s\n", id, (int)(tag >> 48), (int)(tag & 0xffffull), rec[2 * i + 1], d);
     }
     fclose(f);
+    return FAMG_OK;
+}
+
+famg_status famg_set_num_threads(int n) {
+    if (n < 1) FAMG_FAIL(FAMG_ERR_INVALID, "thread count must be positive");
+    omp_set_num_threads(n);
     return FAMG_OK;
 }
 

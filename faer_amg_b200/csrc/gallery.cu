@@ -81,8 +81,8 @@ static famg_status gallery_build(famg_ctx *ctx, int64_t nx, int64_t ny, int64_t 
     if (ncols >= INT32_MAX) FAMG_FAIL(FAMG_ERR_UNSUPPORTED, "grid too large for 32-bit indices");
     const int64_t row0 = z0 * nx * ny, n = (z1 - z0) * nx * ny;
     int *cnt = nullptr, *rp = nullptr;
-    FAMG_TRY(dev_alloc(&cnt, n + 1));
-    famg_status st = dev_alloc(&rp, n + 1);
+    FAMG_TRY(pool_alloc(ctx, sizeof(int) * (size_t)(n + 1), (void **)&cnt));
+    famg_status st = pool_alloc(ctx, sizeof(int) * (size_t)(n + 1), (void **)&rp);
     const unsigned grid = (unsigned)std::max<int64_t>(ceil_div(n, 256), 1);
     if (st == FAMG_OK) {
         if (stencil == 7) g7_count_kernel<<<grid, 256, 0, ctx->stream>>>((int)nx, (int)ny, (int)nz, row0, n, cnt);
@@ -106,8 +106,7 @@ static famg_status gallery_build(famg_ctx *ctx, int64_t nx, int64_t ny, int64_t 
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { set_error("gallery: %s", cudaGetErrorString(e)); st = FAMG_ERR_CUDA; }
     }
-    cudaStreamSynchronize(ctx->stream);
-    cudaFree(cnt); cudaFree(rp);
+    pool_free(ctx, cnt, 0); pool_free(ctx, rp, 0);
     if (st == FAMG_OK) st = csr_finalize_plan(a);
     if (st != FAMG_OK) { if (a) csr_release(a); return st; }
     *out = a;

@@ -697,8 +697,8 @@ static famg_status sg_run_pass(famg_ctx *ctx, SgArgs base, const int *d_size, in
         int h = 1;
         while (h < 2 * max_size) h <<= 1;
         const int grid = std::min(global_count, 2 * ctx->num_sms);
-        if (*scratch) { cudaStreamSynchronize(ctx->stream); cudaFree(*scratch); *scratch = nullptr; }
-        FAMG_TRY(dev_alloc(scratch, (int64_t)grid * (h + h / 2)));
+        if (*scratch) { pool_free(ctx, *scratch, 0); *scratch = nullptr; }
+        FAMG_TRY(pool_alloc(ctx, sizeof(int) * (size_t)grid * (size_t)(h + h / 2), (void **)scratch));
         SgArgs s = base;
         s.perm = d_perm + global_off; s.count = global_count; s.hmask = h - 1;
         s.g_table = *scratch; s.g_list = *scratch + (size_t)grid * h;
@@ -723,13 +723,14 @@ famg_status spgemm_impl(const famg_csr *a, const famg_csr *b, const famg_csr *p_
     const size_t words = (size_t)6 * (m + 2) + 32;
     int *blk = nullptr, *scratch = nullptr;
     famg_csr *c = nullptr;
-    famg_status st = pool_alloc(ctx, words * sizeof(int), (void **)&blk);
+    famg_status st;
+    { PhaseTimer pt(ctx, "    spgemm: scratch"); st = pool_alloc(ctx, words * sizeof(int), (void **)&blk); }
     if (st != FAMG_OK) return st;
     int *ub = blk, *size = ub + (m + 2), *cls = size + (m + 2), *perm = cls + (m + 2), *row_nnz = perm + (m + 2),
         *rp = row_nnz + (m + 2), *counters = rp + (m + 2);
     auto cleanup = [&]() {
         pool_free(ctx, blk, words * sizeof(int));
-        if (scratch) { cudaStreamSynchronize(ctx->stream); cudaFree(scratch); }
+        if (scratch) pool_free(ctx, scratch, 0);
     };
 #define SG_TRY(expr) do { st = (expr); if (st != FAMG_OK) { cleanup(); if (c) csr_release(c); return st; } } while (0)
     SgArgs base{};
@@ -737,10 +738,12 @@ famg_status spgemm_impl(const famg_csr *a, const famg_csr *b, const famg_csr *p_
     base.ep.enabled = 0;
     int total = 0;
     if (m > 0) {
+        PhaseTimer pt(ctx, "    spgemm: bounds + count pass");
         sg_ub_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, ctx->stream>>>(A, B, m, (int)b->ncols, ub, size);
         count_launch(ctx);
         SG_TRY((sg_run_pass<false>(ctx, base, size, m, (int)b->ncols, cls, perm, counters, &scratch)));
     }
+    PhaseTimer pt_alloc(ctx, "    spgemm: scan + allocate C");
     SG_TRY(exclusive_scan_i32(ctx, row_nnz, rp, m));
     {
         cudaError_t e = cudaMemcpy(&total, rp + m, sizeof(int), cudaMemcpyDeviceToHost);
@@ -756,7 +759,9 @@ famg_status spgemm_impl(const famg_csr *a, const famg_csr *b, const famg_csr *p_
         base.ep.p = SgMat{p_for_smoothing->row_ptr, p_for_smoothing->col, p_for_smoothing->val};
         base.ep.error_flag = err_flag;
     }
+    pt_alloc.~PhaseTimer(); pt_alloc.on = false;
     if (m > 0) {
+        PhaseTimer pt(ctx, "    spgemm: fill pass");
         sg_size2_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, ctx->stream>>>(row_nnz, ub, m, size);
         count_launch(ctx);
         SG_TRY((sg_run_pass<true>(ctx, base, size, m, (int)b->ncols, cls, perm, counters, &scratch)));
@@ -814,10 +819,10 @@ famg_status transpose_impl(const famg_csr *a, famg_csr **out) {
     famg_csr *t = nullptr;
     FAMG_TRY(csr_alloc(ctx, n, m, nnz, &t));
     int *counts = nullptr, *cursor = nullptr, *t_col = nullptr; double *t_val = nullptr;
-    famg_status st = dev_alloc(&counts, n + 1);
-    if (st == FAMG_OK) st = dev_alloc(&cursor, n + 1);
-    if (st == FAMG_OK) st = dev_alloc(&t_col, nnz);
-    if (st == FAMG_OK) st = dev_alloc(&t_val, nnz);
+    famg_status st = pool_alloc(ctx, sizeof(int) * (size_t)(n + 1), (void **)&counts);
+    if (st == FAMG_OK) st = pool_alloc(ctx, sizeof(int) * (size_t)(n + 1), (void **)&cursor);
+    if (st == FAMG_OK) st = pool_alloc(ctx, sizeof(int) * (size_t)std::max(nnz, 1), (void **)&t_col);
+    if (st == FAMG_OK) st = pool_alloc(ctx, sizeof(double) * (size_t)std::max(nnz, 1), (void **)&t_val);
     if (st == FAMG_OK) {
         cudaMemsetAsync(counts, 0, sizeof(int) * (n + 1), ctx->stream);
         if (nnz) {
@@ -835,8 +840,7 @@ famg_status transpose_impl(const famg_csr *a, famg_csr **out) {
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { set_error("transpose: %s", cudaGetErrorString(e)); st = FAMG_ERR_CUDA; }
     }
-    cudaStreamSynchronize(ctx->stream);
-    cudaFree(counts); cudaFree(cursor); cudaFree(t_col); cudaFree(t_val);
+    pool_free(ctx, counts, 0); pool_free(ctx, cursor, 0); pool_free(ctx, t_col, 0); pool_free(ctx, t_val, 0);  // stream-ordered
     if (st == FAMG_OK) st = csr_finalize_plan(t);
     if (st != FAMG_OK) { csr_release(t); return st; }
     *out = t;

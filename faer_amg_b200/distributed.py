@@ -133,6 +133,11 @@ class Comm:
         import torch.distributed as dist
         if not dist.is_initialized() or dist.get_world_size() == 1:
             return cls(ctx, 1, 0, None)
+        # torchrun exports OMP_NUM_THREADS=1: give every rank its share of the host cores for the host-side setup pieces
+        import os
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        local = int(os.environ.get("LOCAL_WORLD_SIZE", dist.get_world_size()))
+        call("famg_set_num_threads", max(1, cores // max(local, 1)))
         return cls(ctx, dist.get_world_size(), dist.get_rank(), broadcast_unique_id())
 
     def allreduce_sum(self, vals) -> np.ndarray:

@@ -376,6 +376,9 @@ famg_status famg_ctx_set_option(famg_ctx *ctx, const char *key, int64_t value);
  * captured) afterwards stamp %globaltimer at their begin / end and at the stages of an exchange; famg_ctx_trace_dump
  * writes the records as text (see csrc/core.cu) and "trace" = 1 again restarts the list.  Diagnostics only. */
 famg_status famg_ctx_trace_dump(famg_ctx *ctx, const char *path);
+/* OpenMP threads of the host-side setup pieces (tentative prolongator, CSR validation, partitioner).  Launchers such as
+ * torchrun export OMP_NUM_THREADS=1 to every rank; a rank may claim its share of the host cores here. */
+famg_status famg_set_num_threads(int n);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 famg_status famg_ctx_launch_count(const famg_ctx *ctx, int64_t *count);
 /* time `reps` back-to-back launches of one fused kernel class with CUDA events on the context
