@@ -48,6 +48,7 @@ SIGNATURES = {
     "famg_ctx_set_option": [vp, C.c_char_p, i64],
     "famg_ctx_trace_dump": [vp, C.c_char_p],
     "famg_set_num_threads": [cint],
+    "famg_ctx_reserve": [vp, i64],
     "famg_csr_create": [vp, i64, i64, u64p, u64p, f64p, vpp],
     "famg_csr_create_from_triplets": [vp, i64, i64, i64, u64p, u64p, f64p, vpp],
     "famg_csr_retain": [vp],

@@ -69,6 +69,10 @@ class Context:
         """Kernel-selection knobs for A/B measurements (see famg_ctx_set_option)."""
         call("famg_ctx_set_option", self._h, key.encode(), int(value))
 
+    def reserve(self, nbytes: int):
+        """Pre-size the device memory pool (see famg_ctx_reserve)."""
+        call("famg_ctx_reserve", self._h, int(nbytes))
+
     def trace_dump(self, path: str):
         """Text dump of the in-kernel timeline collected since ``set_option("trace", 1)``."""
         call("famg_ctx_trace_dump", self._h, path.encode())

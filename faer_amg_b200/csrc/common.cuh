@@ -126,8 +126,32 @@ namespace famg {
 famg_status pc_apply(int pc_kind, void *precond, famg_vec *z, const famg_vec *r);
 
 // ---------------------------------------------------------------- allocation helpers
+// Long-lived device buffers (smoother diagonals, level workspaces, halo lists): carved out of the current device's
+// caching pool like everything else (allocation ordered on the legacy stream, where nothing is ever queued: available at
+// once; released with cudaFree, which hands the block back to the pool).  Plain cudaMalloc / cudaFree cost milliseconds
+// each on the measured boxes and dozens of them sat in every distributed hierarchy build.
 template <typename T>
 famg_status dev_alloc(T **p, int64_t count) {
+    *p = nullptr;
+    size_t bytes = sizeof(T) * (size_t)(count > 0 ? count : 1);
+    cudaError_t e = cudaMallocAsync((void **)p, bytes, (cudaStream_t)0);
+    if (e == cudaErrorMemoryAllocation) {  // give cached blocks back to the driver and retry once
+        cudaGetLastError();
+        int dev = 0;
+        cudaMemPool_t mp;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&mp, dev) == cudaSuccess) { cudaDeviceSynchronize(); cudaMemPoolTrimTo(mp, 0); }
+        e = cudaMallocAsync((void **)p, bytes, (cudaStream_t)0);
+    }
+    if (e != cudaSuccess) {
+        *p = nullptr;
+        set_error("device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        return e == cudaErrorMemoryAllocation ? FAMG_ERR_ALLOC : FAMG_ERR_CUDA;
+    }
+    return FAMG_OK;
+}
+// memory that is exported with CUDA IPC (the peer-memory arenas) has to come from cudaMalloc
+template <typename T>
+famg_status dev_alloc_ipc(T **p, int64_t count) {
     *p = nullptr;
     size_t bytes = sizeof(T) * (size_t)(count > 0 ? count : 1);
     cudaError_t e = cudaMalloc((void **)p, bytes);

@@ -415,6 +415,19 @@ famg_status famg_ctx_trace_dump(famg_ctx *ctx, const char *path) {
     return FAMG_OK;
 }
 
+// Pre-sizes the context's stream-ordered pool: one allocation of `bytes`, released straight back to the pool, which keeps
+// the physical memory (release threshold = max).  Later operator / temporary allocations are carved out of it instead of
+// mapping new physical memory in the middle of a hierarchy build (0.2-0.3 ms per MB on the measured boxes).
+famg_status famg_ctx_reserve(famg_ctx *ctx, int64_t bytes) {
+    if (!ctx || bytes < 0) FAMG_FAIL(FAMG_ERR_INVALID, "bad argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    void *p = nullptr;
+    FAMG_TRY(stream_alloc(ctx, &p, (size_t)bytes));
+    CUDA_TRY(cudaFreeAsync(p, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return FAMG_OK;
+}
+
 famg_status famg_set_num_threads(int n) {
     if (n < 1) FAMG_FAIL(FAMG_ERR_INVALID, "thread count must be positive");
     omp_set_num_threads(n);

@@ -714,7 +714,7 @@ static famg_status p2p_setup(famg_dist_mg *d) {
     coll_off[4] = off; off = align(off + sizeof(double) * (n_rep + 2));
     coll_off[5] = off; off = align(off + sizeof(double) * (n_rep + 2));
     d->arena_bytes = off;
-    FAMG_TRY(dev_alloc(&d->arena, (int64_t)off));
+    FAMG_TRY(dev_alloc_ipc(&d->arena, (int64_t)off));
     CUDA_TRY(cudaMemset(d->arena, 0, off));
     FAMG_TRY(dev_alloc(&d->d_p2p_err, 1));
     CUDA_TRY(cudaMemset(d->d_p2p_err, 0, sizeof(int)));

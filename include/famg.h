@@ -376,6 +376,10 @@ famg_status famg_ctx_set_option(famg_ctx *ctx, const char *key, int64_t value);
  * captured) afterwards stamp %globaltimer at their begin / end and at the stages of an exchange; famg_ctx_trace_dump
  * writes the records as text (see csrc/core.cu) and "trace" = 1 again restarts the list.  Diagnostics only. */
 famg_status famg_ctx_trace_dump(famg_ctx *ctx, const char *path);
+/* Pre-size the context's device memory pool (operators, temporaries and multivectors are carved out of it): one
+ * allocation of `bytes` handed straight back to the pool, which keeps the physical memory.  Avoids mapping new physical
+ * memory in the middle of a hierarchy build. */
+famg_status famg_ctx_reserve(famg_ctx *ctx, int64_t bytes);
 /* OpenMP threads of the host-side setup pieces (tentative prolongator, CSR validation, partitioner).  Launchers such as
  * torchrun export OMP_NUM_THREADS=1 to every rank; a rank may claim its share of the host cores here. */
 famg_status famg_set_num_threads(int n);
