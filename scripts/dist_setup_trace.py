@@ -14,20 +14,22 @@ from faer_amg_b200.distributed import Comm, DistGeometricPartitioner, DistHierar
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-dims = (n, n, n)
+g = [int(v) for v in sys.argv[1:4]] if len(sys.argv) > 3 else [int(sys.argv[1]) if len(sys.argv) > 1 else 256] * 3
+dims = tuple(g)
+n = dims[0]
 ctx = F.Context.default(local)
 comm = Comm.from_torch(ctx)
 rs = fine_plane_splits(dims, world)
-plane = n * n
+plane = dims[0] * dims[1]
+ntot = dims[0] * dims[1] * dims[2]
 for rep in range(3):
     dist.barrier()
     if rank == 0:
         print(f"[setup] ---- build {rep}", file=sys.stderr, flush=True)
     t0 = time.perf_counter()
-    slab = F.gallery.poisson7_slab(ctx, n, n, n, int(rs[rank]) // plane, int(rs[rank + 1]) // plane)
-    a0 = DistMat.from_slabs(comm, [slab], n ** 3)
-    nn = [np.full(int(rs[rank + 1] - rs[rank]), 1.0 / np.sqrt(n ** 3))]
+    slab = F.gallery.poisson7_slab(ctx, dims[0], dims[1], dims[2], int(rs[rank]) // plane, int(rs[rank + 1]) // plane)
+    a0 = DistMat.from_slabs(comm, [slab], ntot)
+    nn = [np.full(int(rs[rank + 1] - rs[rank]), 1.0 / np.sqrt(ntot))]
     ctx.sync(); t1 = time.perf_counter()
     dh = DistHierarchy(comm, a0, nn, DistGeometricPartitioner(dims), coarsest_dim=1000, replicate_below=4096)
     ctx.sync(); t2 = time.perf_counter()
