@@ -149,6 +149,14 @@ SIGNATURES = {
     "famg_dmat_gather": [vp, vpp],
     "famg_dist_coarsen": [vp, i64p, C.POINTER(u64p), C.POINTER(u64p), C.POINTER(f64p), cint, f64, vpp, vpp, vpp, C.POINTER(f64p)],
     "famg_dist_smooth_near_null": [vp, cint, C.POINTER(f64p)],
+    "famg_dist_coarsen_dev": [vp, vpp, vpp, cint, f64, vpp, vpp, vpp, vpp],
+    "famg_dist_smooth_near_null_dev": [vp, cint, vpp],
+    "famg_partition_geometric_dev": [vp, i64, i64, i64, i64, i64, i64, vpp, i64p],
+    "famg_partition_upload": [vp, i64, i64, u64p, u64p, vpp],
+    "famg_partition_dims": [vp, i64p, i64p],
+    "famg_partition_download": [vp, u64p, u64p],
+    "famg_partition_destroy": [vp],
+    "famg_tentative_p_dev": [vp, vp, vpp, vp],
     "famg_dist_mg_create_levels": [vp, cint, vpp, vpp, vpp, cint, f64, vp, vpp],
 }
 

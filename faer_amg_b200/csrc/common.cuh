@@ -114,6 +114,13 @@ struct famg_smoother {
     famg_csr *minv = nullptr; // SM_SPARSE_INV: block-diagonal M^-1 as CSR
 };
 
+struct famg_partition {        // device-resident aggregates (aggregates.cu)
+    famg_ctx *ctx = nullptr;
+    int64_t n_nodes = 0, n_aggs = 0;
+    int *agg_ptr = nullptr;    // n_aggs + 1
+    int *agg_nodes = nullptr;  // n_nodes, ascending inside an aggregate
+};
+
 struct famg_composite {
     famg_ctx *ctx = nullptr;
     famg_csr *a = nullptr;  // retained
@@ -280,6 +287,10 @@ famg_status smoother_apply_dev(const famg_smoother *s, const double *in, int64_t
 // Diag smoother entries of the rows of `a` (rectangular row slabs allowed: the diagonal of local row i is
 // the entry with column id i; rows need not be sorted).  kind: FAMG_DIAG_L1 | FAMG_DIAG_JACOBI.
 famg_status diag_from_rows(const famg_csr *a, int kind, double omega, double *d_out);
+
+// tentative prolongator of a scalar problem with one near-null vector from device aggregates (aggregates.cu);
+// nn: n_nodes doubles, coarse_nn: n_aggs doubles, both device
+famg_status tentative_p1_dev(const famg_partition *part, const double *nn, famg_csr **p_out, double *coarse_nn);
 
 // sparse products (spgemm.cu)
 famg_status spgemm_impl(const famg_csr *a, const famg_csr *b, const famg_csr *p_for_smoothing, double omega, famg_csr **out,

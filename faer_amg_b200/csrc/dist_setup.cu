@@ -21,6 +21,7 @@
 // Exchanges are bulk-synchronous all-to-alls (xchg_*): grouped ncclSend/ncclRecv between processes,
 // plain device copies when one process hosts all virtual ranks (single-GPU test mode).
 #include <cmath>
+#include <functional>
 
 #include "dist_internal.cuh"
 
@@ -842,12 +843,10 @@ famg_status famg_dmat_gather(const famg_dmat *m, famg_csr **out) {
 
 // One coarsening step on row slabs (smoothed_aggregation, interpolation/mod.rs:730-836, block_size 1, one
 // near-null vector).  `a` must be finalized (halo plan built).  Aggregates are local to the rank: agg_nodes are
-// local row ids; coarse ids are assigned rank after rank.
-famg_status famg_dist_coarsen(famg_dmat *a, const int64_t *n_aggs, const uint64_t *const *agg_ptr, const uint64_t *const *agg_nodes,
-                              const double *const *near_null, int smoothing_steps, double omega, famg_dmat **p_out, famg_dmat **r_out,
-                              famg_dmat **ac_out, double *const *coarse_nn) {
-    if (!a || !n_aggs || !agg_ptr || !agg_nodes || !near_null || !p_out || !r_out || !ac_out || !coarse_nn || smoothing_steps < 0)
-        FAMG_FAIL(FAMG_ERR_INVALID, "bad argument");
+// local row ids; coarse ids are assigned rank after rank.  make_p0(li, &p0): the rank's tentative prolongator with
+// local coarse column ids (host or device construction).
+static famg_status dist_coarsen_impl(famg_dmat *a, const std::vector<int64_t> &n_aggs, const std::function<famg_status(int, famg_csr **)> &make_p0,
+                                     int smoothing_steps, double omega, famg_dmat **p_out, famg_dmat **r_out, famg_dmat **ac_out) {
     *p_out = *r_out = *ac_out = nullptr;
     famg_comm *cm = a->comm;
     famg_ctx *ctx = cm->ctx;
@@ -858,7 +857,7 @@ famg_status famg_dist_coarsen(famg_dmat *a, const int64_t *n_aggs, const uint64_
     // coarse numbering: rank after rank
     std::vector<std::vector<int64_t>> mine((size_t)nl);
     std::vector<int64_t> all;
-    for (int li = 0; li < nl; ++li) mine[(size_t)li] = {n_aggs[li]};
+    for (int li = 0; li < nl; ++li) mine[(size_t)li] = {n_aggs[(size_t)li]};
     FAMG_TRY(xchg_allgather_meta(cm, 1, mine, all));
     std::vector<int64_t> cs((size_t)nr + 1, 0);
     for (int p = 0; p < nr; ++p) cs[(size_t)p + 1] = cs[(size_t)p] + all[(size_t)p];
@@ -878,12 +877,13 @@ famg_status famg_dist_coarsen(famg_dmat *a, const int64_t *n_aggs, const uint64_
 #define CO_TRY(expr) do { famg_status s__ = (expr); if (s__ != FAMG_OK) return fail(s__); } while (0)
     // tentative prolongator of the rank's own aggregates (interpolation/mod.rs:747-809), global coarse ids
     for (int li = 0; li < nl; ++li) {
-        PhaseTimer pt(ctx, "tentative P (host) + upload");
+        PhaseTimer pt(ctx, "tentative P");
         const int r = cm->vrank(li);
         const int64_t nloc = a->rsplit[(size_t)r + 1] - a->rsplit[(size_t)r];
         famg_csr *p0 = nullptr;
-        CO_TRY(famg_tentative_p(ctx, nloc, 1, 1, 1, near_null[li], std::max<int64_t>(nloc, 1), n_aggs[li], agg_ptr[li], agg_nodes[li], &p0, coarse_nn[li]));
+        CO_TRY(make_p0(li, &p0));
         cur[(size_t)li] = p0;
+        if (p0->nrows != nloc || p0->ncols != n_aggs[(size_t)li]) { set_error("tentative prolongator of rank %d has the wrong shape", r); CO_TRY(FAMG_ERR_INVALID); }
         if (p0->nnz && cs[(size_t)r]) {
             add_const_kernel<<<(unsigned)ceil_div(p0->nnz, 256), 256, 0, ctx->stream>>>(p0->col, (int)p0->nnz, (int)cs[(size_t)r]);
             count_launch(ctx);
@@ -929,6 +929,34 @@ famg_status famg_dist_coarsen(famg_dmat *a, const int64_t *n_aggs, const uint64_
 #undef CO_TRY
     *p_out = P; *r_out = R; *ac_out = AC;
     return FAMG_OK;
+}
+
+famg_status famg_dist_coarsen(famg_dmat *a, const int64_t *n_aggs, const uint64_t *const *agg_ptr, const uint64_t *const *agg_nodes,
+                              const double *const *near_null, int smoothing_steps, double omega, famg_dmat **p_out, famg_dmat **r_out,
+                              famg_dmat **ac_out, double *const *coarse_nn) {
+    if (!a || !n_aggs || !agg_ptr || !agg_nodes || !near_null || !p_out || !r_out || !ac_out || !coarse_nn || smoothing_steps < 0)
+        FAMG_FAIL(FAMG_ERR_INVALID, "bad argument");
+    famg_comm *cm = a->comm;
+    std::vector<int64_t> na(n_aggs, n_aggs + cm->nlocal);
+    auto make = [&](int li, famg_csr **p0) -> famg_status {
+        const int r = cm->vrank(li);
+        const int64_t nloc = a->rsplit[(size_t)r + 1] - a->rsplit[(size_t)r];
+        return famg_tentative_p(cm->ctx, nloc, 1, 1, 1, near_null[li], std::max<int64_t>(nloc, 1), n_aggs[li], agg_ptr[li], agg_nodes[li], p0, coarse_nn[li]);
+    };
+    return dist_coarsen_impl(a, na, make, smoothing_steps, omega, p_out, r_out, ac_out);
+}
+
+famg_status famg_dist_coarsen_dev(famg_dmat *a, famg_partition *const *parts, const famg_vec *const *near_null, int smoothing_steps,
+                                  double omega, famg_dmat **p_out, famg_dmat **r_out, famg_dmat **ac_out, famg_vec *const *coarse_nn) {
+    if (!a || !parts || !near_null || !p_out || !r_out || !ac_out || !coarse_nn || smoothing_steps < 0) FAMG_FAIL(FAMG_ERR_INVALID, "bad argument");
+    famg_comm *cm = a->comm;
+    std::vector<int64_t> na((size_t)cm->nlocal);
+    for (int li = 0; li < cm->nlocal; ++li) {
+        if (!parts[li] || !near_null[li] || !coarse_nn[li]) FAMG_FAIL(FAMG_ERR_INVALID, "null per-rank argument");
+        na[(size_t)li] = parts[li]->n_aggs;
+    }
+    auto make = [&](int li, famg_csr **p0) -> famg_status { return famg_tentative_p_dev(parts[li], near_null[li], p0, coarse_nn[li]); };
+    return dist_coarsen_impl(a, na, make, smoothing_steps, omega, p_out, r_out, ac_out);
 }
 
 // Coarse near-null of a distributed level (hierarchy.rs:217-228): three steps of the L1 stationary iteration
@@ -997,6 +1025,25 @@ famg_status famg_dist_smooth_near_null(famg_dmat *a, int iters, double *const *n
         const int nloc = ops[(size_t)li]->halo.nloc;
         for (int i = 0; i < nloc; ++i) nn[li][i] /= norm;
     }
+    return FAMG_OK;
+}
+
+// device near-null columns: staged through the host routine (the chained sum of squares is a host loop by construction;
+// the columns of a coarse level are a few MB)
+famg_status famg_dist_smooth_near_null_dev(famg_dmat *a, int iters, famg_vec *const *nn) {
+    if (!a || !nn) FAMG_FAIL(FAMG_ERR_INVALID, "null argument");
+    const int nl = a->comm->nlocal;
+    std::vector<std::vector<double>> host((size_t)nl);
+    std::vector<double *> ptrs((size_t)nl);
+    for (int li = 0; li < nl; ++li) {
+        if (!nn[li] || nn[li]->ncols != 1 || nn[li]->nrows != a->part[(size_t)li].halo.nloc) FAMG_FAIL(FAMG_ERR_INVALID, "near-null column %d has the wrong shape", li);
+        host[(size_t)li].resize((size_t)std::max<int64_t>(nn[li]->nrows, 1));
+        ptrs[(size_t)li] = host[(size_t)li].data();
+        if (nn[li]->nrows) FAMG_TRY(famg_vec_download(nn[li], ptrs[(size_t)li], nn[li]->nrows));
+    }
+    FAMG_TRY(famg_dist_smooth_near_null(a, iters, ptrs.data()));
+    for (int li = 0; li < nl; ++li)
+        if (nn[li]->nrows) FAMG_TRY(famg_vec_upload(nn[li], ptrs[(size_t)li], nn[li]->nrows));
     return FAMG_OK;
 }
 

@@ -304,6 +304,20 @@ class DistGeometricPartitioner:
         part, _ = geometric_partition((nx, ny, z1 - z0), self.block)
         return part
 
+    def local_dev(self, ctx, level: int, row_begin: int, row_end: int):
+        """The same aggregates generated on the device (:class:`DevicePartition`)."""
+        from .partitioners import DevicePartition
+        nx, ny, nz = self.level_dims(level)
+        bz = self.block[2]
+        plane = nx * ny
+        if row_begin % plane or row_end % plane:
+            raise ValueError("row slabs of a lexicographic grid must consist of whole z-planes")
+        z0, z1 = row_begin // plane, row_end // plane
+        cz = max(nz // bz, 1)
+        if not (z0 % bz == 0 and (z1 == nz or (z1 % bz == 0 and z1 // bz < cz)) and z1 > z0):
+            raise ValueError(f"slab planes [{z0}, {z1}) of {nz} do not hold whole {bz}-plane boxes: aggregates would straddle ranks")
+        return DevicePartition.geometric(ctx, (nx, ny, z1 - z0), self.block)[0]
+
     def tail(self, level: int) -> GeometricPartitioner:
         """Partitioner of the replicated levels, whose level 0 is this hierarchy's ``level``."""
         return GeometricPartitioner(self.level_dims(level), self.block)
@@ -333,7 +347,10 @@ class DistHierarchy:
         self.A: List[DistMat] = [a0]
         self.P: List[DistMat] = []
         self.R: List[DistMat] = []
-        self.near_nulls: List[List[np.ndarray]] = [[np.ascontiguousarray(v, dtype=np.float64).reshape(-1) for v in near_null_local]]
+        self.near_nulls: List[list] = [[np.ascontiguousarray(v, dtype=np.float64).reshape(-1) for v in near_null_local]]
+        # aggregates and tentative prolongator on the device when the partitioner can (FAMG_HOST_AGGREGATES=1: host path)
+        import os
+        self.device_aggregates = hasattr(partitioner, "local_dev") and os.environ.get("FAMG_HOST_AGGREGATES") is None
         self.partitioner = partitioner
         self.coarsest_dim, self.replicate_below = coarsest_dim, replicate_below
         self.smoothing_steps, self.jacobi_weight = smoothing_steps, jacobi_weight
@@ -350,7 +367,28 @@ class DistHierarchy:
     def levels(self) -> int:
         return self.n_dist + (self.tail.levels() if self.tail is not None else 0)
 
+    def near_null_host(self, level: int) -> np.ndarray:
+        """This process' near-null slices of a distributed level, concatenated (host copy)."""
+        return np.concatenate([v.to_host().ravel() if hasattr(v, "to_host") else np.asarray(v).ravel() for v in self.near_nulls[level]])
+
+    def _coarsen_once_dev(self, level: int):
+        comm, nl = self.comm, self.comm.nlocal
+        fine = self.A[level]
+        rs = fine.row_split()
+        ctx = comm.ctx
+        parts = [self.partitioner.local_dev(ctx, level, int(rs[r]), int(rs[r + 1])) for r in comm.vranks()]
+        nn = [v if hasattr(v, "_h") else DeviceMat.from_host(ctx, v) for v in self.near_nulls[level]]
+        cnn = [DeviceMat(ctx, p.naggs(), 1) for p in parts]
+        pa = (vp * nl)(*[p._h for p in parts])
+        nv = (vp * nl)(*[v._h for v in nn])
+        cv = (vp * nl)(*[v._h for v in cnn])
+        p, r, ac = vp(), vp(), vp()
+        call("famg_dist_coarsen_dev", fine._h, pa, nv, self.smoothing_steps, float(self.jacobi_weight), C.byref(p), C.byref(r), C.byref(ac), cv)
+        return DistMat(comm, p), DistMat(comm, r), DistMat(comm, ac), cnn
+
     def _coarsen_once(self, level: int):
+        if self.device_aggregates:
+            return self._coarsen_once_dev(level)
         comm, nl = self.comm, self.comm.nlocal
         fine = self.A[level]
         rs = fine.row_split()
@@ -398,7 +436,7 @@ class DistHierarchy:
                 with T(f"level {level}: gather A_c + near-null"):
                     P.finalize(True)
                     g = Ac.gather()
-                    nn_g = comm.allgatherv(cnn).reshape(-1, 1)
+                    nn_g = comm.allgatherv([v.to_host().ravel() if hasattr(v, "to_host") else v for v in cnn]).reshape(-1, 1)
                 with T("replicated tail (reference loop)"):
                     l1 = new_l1(g)
                     nn_dev = DeviceMat.from_host(g.ctx, nn_g)
@@ -413,9 +451,12 @@ class DistHierarchy:
                 Ac.finalize(False)
                 P.finalize(False)
             nl = comm.nlocal
-            arr = (f64p * nl)(*[np.ascontiguousarray(v).ctypes.data_as(f64p) for v in cnn])
             with T(f"level {level}: near-null smoothing + thin Q"):
-                call("famg_dist_smooth_near_null", Ac._h, 3, arr)
+                if self.device_aggregates:
+                    call("famg_dist_smooth_near_null_dev", Ac._h, 3, (vp * nl)(*[v._h for v in cnn]))
+                else:
+                    arr = (f64p * nl)(*[np.ascontiguousarray(v).ctypes.data_as(f64p) for v in cnn])
+                    call("famg_dist_smooth_near_null", Ac._h, 3, arr)
             self.A.append(Ac)
             self.near_nulls.append(cnn)
             level += 1

@@ -57,17 +57,26 @@ class Hierarchy:
         cfg = self.config
         max_levels = cfg.max_levels if cfg.max_levels is not None else 1 << 62
         level, coarse_dim = 1, 1 << 62
+        nn_dev_prev = None  # the current level's near-null column on the device (device path: levels >= 1 never leave it)
         while coarse_dim > cfg.coarsest_dim and level < max_levels:
             fine = self.current_op()
             near_null = self._near_nulls[-1]
-            g = cfg.interpolation_config.build(fine, near_null, self._nn_weights[-1], level=level - 1)
+            icfg = cfg.interpolation_config
+            if hasattr(icfg, "device_path") and icfg.device_path(fine, near_null):
+                if nn_dev_prev is None:
+                    nn_dev_prev = DeviceMat.from_host(fine.mat_ref().ctx, near_null)
+                g, nn_dev = icfg.build_dev(fine, nn_dev_prev, level=level - 1)
+            else:
+                g = icfg.build(fine, near_null, self._nn_weights[-1], level=level - 1)
+                nn_dev = DeviceMat.from_host(g.coarse_mat.ctx, g.coarse_nn)
             coarse_op = SparseMatOp(g.coarse_mat, cfg.interpolation_config.candidate_dimension)
             coarse_dim = coarse_op.mat_ref().nrows
             # smooth the coarse near-null: 3-step L1 stationary iteration (:217-226), thin QR (:228)
             l1 = new_l1(coarse_op.mat_ref())
-            nn_dev = DeviceMat.from_host(g.coarse_mat.ctx, g.coarse_nn)
             StationaryIteration(coarse_op.mat_ref(), l1, 3).apply_in_place_dev(nn_dev)
             coarse_nn = thin_q(nn_dev.to_host())
+            nn_dev.upload(coarse_nn)
+            nn_dev_prev = nn_dev
             self.add_level(coarse_op, g.partition, coarse_nn, g.interpolation, g.restriction)
             level += 1
 

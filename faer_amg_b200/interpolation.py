@@ -42,6 +42,17 @@ def tentative_prolongator(ctx, n_fine: int, partition: Partition, near_null, can
     return SparseRowMat(ctx, h), coarse_nn
 
 
+def tentative_prolongator_dev(partition, near_null_dev):
+    """The same for a scalar problem with one near-null vector, on the device (``famg_tentative_p_dev``): device
+    aggregates, device near-null column; returns (P, coarse near-null as a DeviceMat).  Bit-identical to the host path."""
+    from .core import DeviceMat
+    ctx = partition.ctx
+    cnn = DeviceMat(ctx, partition.naggs(), 1)
+    h = vp()
+    call("famg_tentative_p_dev", partition._h, near_null_dev._h, C.byref(h), cnn._h)
+    return SparseRowMat(ctx, h), cnn
+
+
 def smooth_interpolation(mat: SparseRowMat, p: SparseRowMat, jacobi_weight: float = JACOBI_WEIGHT) -> SparseRowMat:
     """interpolation/mod.rs:927-946: (I - w D^-1 A) P, one SpGEMM with a fused epilogue."""
     h = vp()
@@ -98,6 +109,21 @@ class AggregationConfig:
     @classmethod
     def new_unsmoothed(cls, partitioner, candidate_dimension: int) -> "AggregationConfig":
         return cls(0, candidate_dimension, partitioner)
+
+    def device_path(self, op: SparseMatOp, near_null) -> bool:
+        """Scalar problem, one near-null vector, a partitioner that can produce its aggregates on the device: the
+        tentative prolongator is built there (no host pass over the fine grid, nothing uploaded)."""
+        nn = as_colmajor(near_null) if not hasattr(near_null, "_h") else None
+        k = near_null.ncols if nn is None else nn.shape[1]
+        return (hasattr(self.partitioner, "device") and self.candidate_dimension == 1 and op.block_size() == 1 and k == 1)
+
+    def build_dev(self, op: SparseMatOp, near_null_dev, level: int = 0):
+        """``build`` on the device path: returns (GalerkinCoarse with coarse_nn = None, coarse near-null DeviceMat)."""
+        partition = self.partitioner.device(level, op.mat_ref().ctx)
+        assert op.mat_ref().nrows == partition.nnodes()  # interpolation/mod.rs:743-745
+        p0, cnn_dev = tentative_prolongator_dev(partition, near_null_dev)
+        p, r, ac = galerkin_product(op.mat_ref(), p0, self.smoothing_steps)
+        return GalerkinCoarse(p, r, ac, None, partition), cnn_dev
 
     def build(self, op: SparseMatOp, near_null, nn_weights=None, level: int = 0) -> GalerkinCoarse:
         if self.partitioner is None:

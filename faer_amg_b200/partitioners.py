@@ -75,15 +75,87 @@ def geometric_partition(dims: Sequence[int], block: Sequence[int] = (2, 2, 2)) -
     return Partition(ptr.view(np.int64), nodes.view(np.int64), nx * ny * nz, validate=False), tuple(int(c) for c in coarse)
 
 
+class DevicePartition:
+    """Aggregate lists resident on the device (``famg_partition``): generated in place for box aggregates, or uploaded
+    from any host :class:`Partition`.  The tentative prolongator is built from it on the device."""
+
+    def __init__(self, ctx, handle):
+        self._h, self.ctx = handle, ctx
+        from ._ffi import call
+        nn, na = C.c_int64(), C.c_int64()
+        call("famg_partition_dims", handle, C.byref(nn), C.byref(na))
+        self._nnodes, self._naggs = nn.value, na.value
+        self._host = None
+
+    @classmethod
+    def geometric(cls, ctx, dims: Sequence[int], block: Sequence[int] = (2, 2, 2)):
+        from ._ffi import call, i64p, vp
+        h = vp()
+        coarse = np.zeros(3, dtype=np.int64)
+        call("famg_partition_geometric_dev", ctx._h, int(dims[0]), int(dims[1]), int(dims[2]), int(block[0]), int(block[1]), int(block[2]),
+             C.byref(h), coarse.ctypes.data_as(i64p))
+        return cls(ctx, h), tuple(int(c) for c in coarse)
+
+    @classmethod
+    def from_host(cls, ctx, part: Partition) -> "DevicePartition":
+        from ._ffi import call, u64p, vp
+        h = vp()
+        ap = np.ascontiguousarray(part.agg_ptr, dtype=np.int64)
+        an = np.ascontiguousarray(part.agg_nodes, dtype=np.int64)
+        call("famg_partition_upload", ctx._h, part.nnodes(), part.naggs(), ap.ctypes.data_as(u64p), an.ctypes.data_as(u64p), C.byref(h))
+        out = cls(ctx, h)
+        out._host = part
+        return out
+
+    def naggs(self) -> int:
+        return self._naggs
+
+    def nnodes(self) -> int:
+        return self._nnodes
+
+    def to_host(self) -> Partition:
+        if self._host is None:
+            from ._ffi import call, u64p
+            ptr = np.empty(self._naggs + 1, dtype=np.uint64)
+            nodes = np.empty(max(self._nnodes, 1), dtype=np.uint64)
+            call("famg_partition_download", self._h, ptr.ctypes.data_as(u64p), nodes.ctypes.data_as(u64p))
+            self._host = Partition(ptr.view(np.int64), nodes.view(np.int64)[: self._nnodes], self._nnodes, validate=False)
+        return self._host
+
+    # the hot path only needs the lists; everything else goes through the host view
+    def __getattr__(self, name):
+        if name in ("agg_ptr", "agg_nodes", "aggregates", "node_to_agg", "validate"):
+            return getattr(self.to_host(), name)
+        raise AttributeError(name)
+
+    def __del__(self):
+        try:
+            from . import _ffi
+            _ffi.lib().famg_partition_destroy(self._h)
+        except Exception:
+            pass
+
+
 class GeometricPartitioner:
-    """Callable ``(level, op, near_null) -> Partition`` for :class:`HierarchyConfig`."""
+    """Callable ``(level, op, near_null) -> Partition`` for :class:`HierarchyConfig`.  ``device(level, ctx)`` yields the
+    same aggregates as a :class:`DevicePartition` generated on the device (used by the hierarchy build for scalar
+    problems with one near-null vector)."""
 
     def __init__(self, dims: Sequence[int], block: Sequence[int] = (2, 2, 2)):
         self.dims = [tuple(dims)]
         self.block = tuple(block)
 
+    def _coarse(self, d):
+        return tuple(max(d[i] // self.block[i], 1) for i in range(3))
+
     def __call__(self, level: int, op, near_null) -> Partition:
         part, coarse = geometric_partition(self.dims[level], self.block)
+        if len(self.dims) == level + 1:
+            self.dims.append(coarse)
+        return part
+
+    def device(self, level: int, ctx) -> DevicePartition:
+        part, coarse = DevicePartition.geometric(ctx, self.dims[level], self.block)
         if len(self.dims) == level + 1:
             self.dims.append(coarse)
         return part

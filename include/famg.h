@@ -52,6 +52,7 @@ typedef struct famg_smoother famg_smoother; /* Arc<dyn BiPrecond<f64>> of one le
 typedef struct famg_mg famg_mg;             /* Multigrid (multigrid.rs:171-179) */
 typedef struct famg_comm famg_comm;         /* one rank of a row-partitioned multi-GPU job */
 typedef struct famg_dist_mg famg_dist_mg;   /* row-partitioned Multigrid + PCG */
+typedef struct famg_partition famg_partition; /* device-resident aggregates (Partition, partitioners/mod.rs:23-27) */
 
 const char *famg_last_error(void);
 const char *famg_version(void);
@@ -212,6 +213,20 @@ famg_status famg_tentative_p(famg_ctx *ctx, int64_t n_fine, int64_t block_size, 
                              int64_t cand, const double *near_null, int64_t ld_nn, int64_t n_aggs,
                              const uint64_t *agg_ptr, const uint64_t *agg_nodes, famg_csr **p,
                              double *coarse_nn);
+/* The same two steps with the aggregates in device memory (the north-star moves aggregation work to the device where it
+ * is measured on the critical path: these two host passes were a quarter of a 256^3 hierarchy build, and grew with the
+ * number of ranks sharing the host cores).  famg_partition: aggregate lists on the device -- generated in place for box
+ * aggregates (same aggregates and order as famg_geometric_partition) or uploaded from any host partitioner. */
+famg_status famg_partition_geometric_dev(famg_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, int64_t bx, int64_t by, int64_t bz,
+                                         famg_partition **out, int64_t *coarse_dims /* 3, may be NULL */);
+famg_status famg_partition_upload(famg_ctx *ctx, int64_t n_nodes, int64_t n_aggs, const uint64_t *agg_ptr, const uint64_t *agg_nodes,
+                                  famg_partition **out);
+famg_status famg_partition_dims(const famg_partition *p, int64_t *n_nodes, int64_t *n_aggs);
+famg_status famg_partition_download(const famg_partition *p, uint64_t *agg_ptr, uint64_t *agg_nodes);
+famg_status famg_partition_destroy(famg_partition *p);
+/* tentative prolongator (interpolation/mod.rs:747-809) of a scalar problem with one near-null vector, on the device: one
+ * thread per aggregate in list order -- bit-identical to famg_tentative_p.  near_null: n_nodes x 1, coarse_nn: n_aggs x 1 */
+famg_status famg_tentative_p_dev(const famg_partition *part, const famg_vec *near_null, famg_csr **p, famg_vec *coarse_nn);
 /* coarse_nn.qr().compute_thin_Q() (hierarchy.rs:228); host, in place, R with positive diagonal */
 famg_status famg_thin_q(int64_t n, int64_t k, double *a, int64_t lda);
 /* the same on a device-resident block (k <= 64): CholeskyQR2 -- Gram matrix by a deterministic
@@ -356,6 +371,10 @@ famg_status famg_dmat_gather(const famg_dmat *m, famg_csr **out);
 famg_status famg_dist_coarsen(famg_dmat *a, const int64_t *n_aggs, const uint64_t *const *agg_ptr, const uint64_t *const *agg_nodes,
                               const double *const *near_null, int smoothing_steps, double omega, famg_dmat **p, famg_dmat **r,
                               famg_dmat **a_coarse, double *const *coarse_nn);
+/* the same with device aggregates and device near-null columns (one famg_partition / famg_vec per hosted rank) */
+famg_status famg_dist_coarsen_dev(famg_dmat *a, famg_partition *const *parts, const famg_vec *const *near_null, int smoothing_steps,
+                                  double omega, famg_dmat **p, famg_dmat **r, famg_dmat **a_coarse, famg_vec *const *coarse_nn);
+famg_status famg_dist_smooth_near_null_dev(famg_dmat *a, int iters, famg_vec *const *near_null);
 /* hierarchy.rs:217-228 on a finalized distributed level: `iters`-step L1 stationary iteration on the near-null
  * slices (in place, host), then the thin Q of the single column with the sum of squares chained through the ranks
  * in order -- bit-identical to the undistributed build */

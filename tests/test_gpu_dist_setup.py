@@ -67,7 +67,7 @@ def test_dist_hierarchy_bit_identical_to_single_gpu(ctx, nranks, dims, stencil, 
             _same(dh.P[l].local(r, True), h.get_interpolation(l), int(rsl[r]), int(rsl[r + 1]), f"P level {l} rank {r}")
             _same(dh.R[l].local(r, True), h.get_restriction(l), int(csl[r]), int(csl[r + 1]), f"R level {l} rank {r}")
         if l > 0:
-            got = np.concatenate(dh.near_nulls[l])
+            got = dh.near_null_host(l)
             assert np.array_equal(got, h.get_near_null(l).ravel()), f"near-null level {l}"
     # replicated tail == remaining levels of the undistributed hierarchy
     for t in range(dh.tail.levels()):
@@ -113,3 +113,60 @@ def test_tail_of_one_level(ctx):
     assert dh.levels() == h.levels() == 3 and dh.tail.levels() == 1
     w = h.get_mat_ref(2)
     _same(dh.tail.get_mat_ref(0), w, 0, w.nrows, "tail")
+
+
+@pytest.mark.parametrize("dims,block", [((7, 5, 9), (2, 2, 2)), ((16, 16, 16), (2, 2, 2)), ((9, 4, 6), (3, 2, 1)), ((1, 1, 5), (2, 2, 2))])
+def test_device_aggregates_and_tentative_p_bit_identical_to_host(ctx, dims, block):
+    """famg_partition_geometric_dev == famg_geometric_partition, famg_tentative_p_dev == famg_tentative_p (bit for bit),
+    upload / download round trip."""
+    import faer_amg_b200 as F
+    from faer_amg_b200.interpolation import tentative_prolongator, tentative_prolongator_dev
+    from faer_amg_b200.partitioners import DevicePartition, geometric_partition
+    hp, hc = geometric_partition(dims, block)
+    dp, dc = DevicePartition.geometric(ctx, dims, block)
+    assert hc == dc and dp.naggs() == hp.naggs() and dp.nnodes() == hp.nnodes()
+    got = dp.to_host()
+    assert np.array_equal(got.agg_ptr, hp.agg_ptr) and np.array_equal(got.agg_nodes, hp.agg_nodes)
+    up = DevicePartition.from_host(ctx, hp)
+    up._host = None
+    back = up.to_host()
+    assert np.array_equal(back.agg_ptr, hp.agg_ptr) and np.array_equal(back.agg_nodes, hp.agg_nodes)
+    n = hp.nnodes()
+    rng = np.random.default_rng(3)
+    nn = rng.standard_normal((n, 1))
+    p_h, cnn_h = tentative_prolongator(ctx, n, hp, nn, 1, 1)
+    p_d, cnn_d = tentative_prolongator_dev(dp, F.DeviceMat.from_host(ctx, nn))
+    a, b = p_h.to_host(), p_d.to_host()
+    assert p_h.shape == p_d.shape and all(np.array_equal(x, y) for x, y in zip(a, b))
+    assert np.array_equal(cnn_h.ravel(), cnn_d.to_host().ravel())
+
+
+def test_device_tentative_p_rejects_bad_partitions(ctx):
+    import faer_amg_b200 as F
+    from faer_amg_b200.interpolation import tentative_prolongator_dev
+    from faer_amg_b200.partitioners import DevicePartition, Partition
+    nn = F.DeviceMat.from_host(ctx, np.ones((4, 1)))
+    twice = Partition(np.array([0, 2, 4]), np.array([0, 1, 1, 3]), 4, validate=False)   # node 1 twice, node 2 never
+    with pytest.raises(F.FamgError):
+        tentative_prolongator_dev(DevicePartition.from_host(ctx, twice), nn)
+    empty = Partition(np.array([0, 0, 4]), np.array([0, 1, 2, 3]), 4, validate=False)   # interpolation/mod.rs:757-762
+    with pytest.raises(F.FamgError):
+        tentative_prolongator_dev(DevicePartition.from_host(ctx, empty), nn)
+
+
+def test_hierarchy_host_and_device_aggregate_paths_agree(ctx):
+    """Hierarchy::coarsen with the aggregates produced on the host (callable partitioner) and on the device."""
+    import faer_amg_b200 as F
+    dims = (12, 10, 8)
+    a = F.gallery.diffusion27(ctx, *dims)
+    nn = np.full((a.nrows, 1), 1.0 / np.sqrt(a.nrows))
+    gp = F.GeometricPartitioner(dims)
+    h_dev = F.HierarchyConfig(30, F.AggregationConfig(1, 1, gp)).build(F.SparseMatOp(a), nn)
+    gp2 = F.GeometricPartitioner(dims)
+    h_host = F.HierarchyConfig(30, F.AggregationConfig(1, 1, lambda level, op, v: gp2(level, op, v))).build(F.SparseMatOp(a), nn)
+    assert h_dev.levels() == h_host.levels() >= 3
+    for l in range(1, h_dev.levels()):
+        _same(h_dev.get_mat_ref(l), h_host.get_mat_ref(l), 0, h_host.get_mat_ref(l).nrows, f"A level {l}")
+        _same(h_dev.get_interpolation(l - 1), h_host.get_interpolation(l - 1), 0, h_host.get_interpolation(l - 1).nrows, f"P level {l - 1}")
+        assert np.array_equal(h_dev.get_near_null(l), h_host.get_near_null(l))
+        assert np.array_equal(np.asarray(h_dev.get_partition(l - 1).agg_nodes), np.asarray(h_host.get_partition(l - 1).agg_nodes))
