@@ -118,6 +118,31 @@ __global__ void oor_count_kernel(const int *__restrict__ col, int nnz, int c0, i
     for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(counter, local);
 }
+// count, smallest and largest out-of-range column id: stats[0] += count, stats[1] = min, stats[2] = max
+__global__ void oor_stats_kernel(const int *__restrict__ col, int nnz, int c0, int c1, int *__restrict__ stats) {
+    int local = 0, lo = 0x7fffffff, hi = -1;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nnz; q += gridDim.x * blockDim.x) {
+        const int c = col[q];
+        if (c < c0 || c >= c1) { ++local; lo = min(lo, c); hi = max(hi, c); }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        local += __shfl_xor_sync(0xffffffffu, local, o);
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0 && local) { atomicAdd(&stats[0], local); atomicMin(&stats[1], lo); atomicMax(&stats[2], hi); }
+}
+__global__ void oor_mark_kernel(const int *__restrict__ col, int nnz, int c0, int c1, int gmin, int *__restrict__ flags) {
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nnz; q += gridDim.x * blockDim.x) {
+        const int c = col[q];
+        if (c < c0 || c >= c1) flags[c - gmin] = 1;  // same value from every writer
+    }
+}
+__global__ void oor_compact_kernel(const int *__restrict__ flags, const int *__restrict__ pos, int n, int gmin, int *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flags[i]) out[pos[i]] = gmin + i;
+}
 __global__ void oor_fill_kernel(const int *__restrict__ col, int nnz, int c0, int c1, int *__restrict__ counter, int *__restrict__ list) {
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nnz; q += gridDim.x * blockDim.x) {
         const int c = col[q];
@@ -289,32 +314,62 @@ famg_status dmat_finalize(famg_dmat *m, bool replicated_cols) {
         const int c0 = (int)m->csplit[(size_t)r], c1 = (int)m->csplit[(size_t)r + 1];
         const int nnz = (int)op.local->nnz;
         h.nloc = c1 - c0;
-        int cnt = 0;
-        cudaMemsetAsync(counter, 0, sizeof(int), ctx->stream);
+        // ghost columns = distinct out-of-range column ids, ascending.  They lie in a band around the owned range (a few
+        // planes of a slab partition): flag them in an array over [smallest, largest], scan, compact -- on the device.
+        // (A host sort of the raw list -- millions of duplicates on the wide-stencil coarse levels -- cost 0.1-0.3 s per
+        // operator on 8 ranks; profiles/r2_setup_phases.md.)  Only a band wider than 2^27 falls back to the host sort.
+        int stats[3] = {0, 0x7fffffff, -1};
+        cudaMemcpyAsync(counter, stats, sizeof(stats), cudaMemcpyHostToDevice, ctx->stream);
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(nnz, 256), 16 * (int64_t)ctx->num_sms));
         if (nnz) {
-            const int grid = (int)std::min<int64_t>(ceil_div(nnz, 256), 16 * (int64_t)ctx->num_sms);
-            oor_count_kernel<<<grid, 256, 0, ctx->stream>>>(op.local->col, nnz, c0, c1, counter);
+            oor_stats_kernel<<<grid, 256, 0, ctx->stream>>>(op.local->col, nnz, c0, c1, counter);
             count_launch(ctx);
         }
-        cudaMemcpyAsync(&cnt, counter, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaMemcpyAsync(stats, counter, sizeof(stats), cudaMemcpyDeviceToHost, ctx->stream);
         famg_status st = sync_check(ctx, "halo plan (count)");
         if (st != FAMG_OK) return fail(st);
-        std::vector<int> list((size_t)cnt);
+        const int cnt = stats[0];
+        std::vector<int> list;
         if (cnt) {
-            int *d_list = nullptr;
-            st = pool_alloc(ctx, sizeof(int) * (size_t)cnt, (void **)&d_list);
-            if (st != FAMG_OK) return fail(st);
-            cudaMemsetAsync(counter, 0, sizeof(int), ctx->stream);
-            const int grid = (int)std::min<int64_t>(ceil_div(nnz, 256), 16 * (int64_t)ctx->num_sms);
-            oor_fill_kernel<<<grid, 256, 0, ctx->stream>>>(op.local->col, nnz, c0, c1, counter, d_list);
-            count_launch(ctx);
-            cudaMemcpyAsync(list.data(), d_list, sizeof(int) * (size_t)cnt, cudaMemcpyDeviceToHost, ctx->stream);
-            st = sync_check(ctx, "halo plan (ghost list)");
-            pool_free(ctx, d_list, sizeof(int) * (size_t)cnt);
-            if (st != FAMG_OK) return fail(st);
-            std::sort(list.begin(), list.end());
-            list.erase(std::unique(list.begin(), list.end()), list.end());
-            if (list.front() < 0 || list.back() >= m->ncols) return fail((set_error("column index out of range in a distributed operator"), FAMG_ERR_INVALID));
+            if (stats[1] < 0 || stats[2] >= m->ncols) return fail((set_error("column index out of range in a distributed operator"), FAMG_ERR_INVALID));
+            const int64_t band = (int64_t)stats[2] - stats[1] + 1;
+            if (band <= ((int64_t)1 << 27)) {
+                int *flags = nullptr, *pos = nullptr, *d_list = nullptr;
+                const size_t fb = sizeof(int) * (size_t)(band + 2);
+                st = pool_alloc(ctx, fb, (void **)&flags);
+                if (st == FAMG_OK) st = pool_alloc(ctx, fb, (void **)&pos);
+                if (st != FAMG_OK) { pool_free(ctx, flags, 0); return fail(st); }
+                cudaMemsetAsync(flags, 0, fb, ctx->stream);
+                oor_mark_kernel<<<grid, 256, 0, ctx->stream>>>(op.local->col, nnz, c0, c1, stats[1], flags);
+                count_launch(ctx);
+                st = exclusive_scan_i32(ctx, flags, pos, band);
+                int ng = 0;
+                if (st == FAMG_OK) { cudaMemcpyAsync(&ng, pos + band, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream); st = sync_check(ctx, "halo plan (scan)"); }
+                if (st == FAMG_OK) st = pool_alloc(ctx, sizeof(int) * (size_t)std::max(ng, 1), (void **)&d_list);
+                if (st == FAMG_OK) {
+                    oor_compact_kernel<<<(unsigned)ceil_div(band, 256), 256, 0, ctx->stream>>>(flags, pos, (int)band, stats[1], d_list);
+                    count_launch(ctx);
+                    list.resize((size_t)ng);
+                    if (ng) cudaMemcpyAsync(list.data(), d_list, sizeof(int) * (size_t)ng, cudaMemcpyDeviceToHost, ctx->stream);
+                    st = sync_check(ctx, "halo plan (ghost list)");
+                }
+                pool_free(ctx, flags, 0); pool_free(ctx, pos, 0); pool_free(ctx, d_list, 0);
+                if (st != FAMG_OK) return fail(st);
+            } else {
+                list.resize((size_t)cnt);
+                int *d_list = nullptr;
+                st = pool_alloc(ctx, sizeof(int) * (size_t)cnt, (void **)&d_list);
+                if (st != FAMG_OK) return fail(st);
+                cudaMemsetAsync(counter, 0, sizeof(int), ctx->stream);
+                oor_fill_kernel<<<grid, 256, 0, ctx->stream>>>(op.local->col, nnz, c0, c1, counter, d_list);
+                count_launch(ctx);
+                cudaMemcpyAsync(list.data(), d_list, sizeof(int) * (size_t)cnt, cudaMemcpyDeviceToHost, ctx->stream);
+                st = sync_check(ctx, "halo plan (ghost list)");
+                pool_free(ctx, d_list, sizeof(int) * (size_t)cnt);
+                if (st != FAMG_OK) return fail(st);
+                std::sort(list.begin(), list.end());
+                list.erase(std::unique(list.begin(), list.end()), list.end());
+            }
         }
         op.ghost_gid.swap(list);
         h.nghost = (int)op.ghost_gid.size();
