@@ -7,8 +7,8 @@ pub mod ffi;
 
 use faer::dyn_stack::{MemStack, StackReq};
 use faer::matrix_free::{BiLinOp, BiPrecond, LinOp, Precond};
-use faer::sparse::SparseRowMatRef;
-use faer::{MatMut, MatRef, Par};
+use faer::sparse::{SparseRowMat, SparseRowMatRef, SymbolicSparseRowMat};
+use faer::{Mat, MatMut, MatRef, Par};
 use std::ffi::CStr;
 use std::sync::Arc;
 
@@ -191,6 +191,181 @@ impl GpuComposite {
     pub(crate) fn raw(&self) -> *mut ffi::famg_composite { self.h }
 }
 impl Drop for GpuComposite { fn drop(&mut self) { unsafe { ffi::famg_composite_destroy(self.h); } } }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Plug point P3: the three sparse expressions of `smoothed_aggregation` (interpolation/mod.rs:747-828)
+// ---------------------------------------------------------------------------------------------------------------
+/// Owned device CSR handle -> faer `SparseRowMat` (the buffers Rust wraps are Rust's own: two-phase download).
+pub fn download_csr(h: *mut ffi::famg_csr) -> SparseRowMat<usize, f64> {
+    let (mut nr, mut nc, mut nnz) = (0i64, 0i64, 0i64);
+    check(unsafe { ffi::famg_csr_dims(h, &mut nr, &mut nc, &mut nnz) });
+    let mut row_ptr = vec![0usize; nr as usize + 1];
+    let mut col_idx = vec![0usize; nnz as usize];
+    let mut val = vec![0f64; nnz as usize];
+    check(unsafe { ffi::famg_csr_download(h, row_ptr.as_mut_ptr(), col_idx.as_mut_ptr(), val.as_mut_ptr()) });
+    unsafe { ffi::famg_csr_destroy(h) };
+    let sym = SymbolicSparseRowMat::new_checked(nr as usize, nc as usize, row_ptr, None, col_idx);
+    SparseRowMat::new(sym, val)
+}
+
+/// `smoothed_aggregation` (interpolation/mod.rs:730-836) with the tentative prolongator, its smoothing, the transpose
+/// and `R * (A * P)` on the GPU.  Same inputs, same outputs `(coarse_near_null, R, P, A_c)`: a drop-in for the body of
+/// the reference function (the `PartitionType` is the caller's own `partition`).
+pub fn smoothed_aggregation_gpu(
+    ctx: &Arc<GpuContext>,
+    fine_mat: SparseRowMatRef<usize, f64>,
+    aggregates: &[std::collections::BTreeSet<usize>],   // Partition::aggregates()
+    block_size: usize,
+    near_null: MatRef<f64>,
+    candidate_dimension: usize,
+    smoothing_steps: usize,
+) -> (Mat<f64>, SparseRowMat<usize, f64>, SparseRowMat<usize, f64>, SparseRowMat<usize, f64>) {
+    let n_fine = fine_mat.nrows();
+    assert_eq!(n_fine % block_size, 0);                                   // :743
+    let mut agg_ptr = Vec::with_capacity(aggregates.len() + 1);
+    let mut agg_nodes = Vec::with_capacity(n_fine / block_size);
+    agg_ptr.push(0usize);
+    for agg in aggregates { agg_nodes.extend(agg.iter().copied()); agg_ptr.push(agg_nodes.len()); }   // BTreeSet: ascending
+    assert_eq!(near_null.row_stride(), 1);
+    let k = near_null.ncols();
+    let n_coarse = aggregates.len() * candidate_dimension;
+    let mut coarse_nn = Mat::<f64>::zeros(n_coarse, k);
+    let a = GpuSpmmOp::new(ctx.clone(), fine_mat);
+    let mut p0 = std::ptr::null_mut();
+    check(unsafe {
+        ffi::famg_tentative_p(ctx.0, n_fine as i64, block_size as i64, k as i64, candidate_dimension as i64, near_null.as_ptr(),
+                              near_null.col_stride() as i64, aggregates.len() as i64, agg_ptr.as_ptr(), agg_nodes.as_ptr(), &mut p0,
+                              coarse_nn.as_ptr_mut())
+    });
+    let (mut p, mut r, mut ac) = (std::ptr::null_mut(), std::ptr::null_mut(), std::ptr::null_mut());
+    check(unsafe { ffi::famg_galerkin_block(a.raw(), p0, block_size as i64, smoothing_steps as i32, 0.66, &mut p, &mut r, &mut ac) });
+    unsafe { ffi::famg_csr_destroy(p0) };
+    (coarse_nn, download_csr(r), download_csr(p), download_csr(ac))
+}
+
+/// `&a * &b` on `SparseRowMat` (interpolation/mod.rs:720,828,938) -- structural, sorted, unpruned; ascending inner index.
+pub fn spgemm_gpu(a: &GpuSpmmOp, b: &GpuSpmmOp) -> SparseRowMat<usize, f64> {
+    let mut out = std::ptr::null_mut();
+    check(unsafe { ffi::famg_spgemm(a.raw(), b.raw(), &mut out) });
+    download_csr(out)
+}
+/// `p.transpose().to_row_major()` (interpolation/mod.rs:824-827)
+pub fn transpose_gpu(a: &GpuSpmmOp) -> SparseRowMat<usize, f64> {
+    let mut out = std::ptr::null_mut();
+    check(unsafe { ffi::famg_transpose(a.raw(), &mut out) });
+    download_csr(out)
+}
+
+/// `BiLinOp` for the operator itself: the transposed operator is built on the device at construction
+/// (`GpuSpmmOp::with_transpose`) -- `StationaryIteration::transpose_apply` (smoothers.rs:179-197) needs it.
+#[derive(Debug)]
+pub struct GpuBiSpmmOp { pub op: GpuSpmmOp, t: *mut ffi::famg_csr }
+unsafe impl Send for GpuBiSpmmOp {}
+unsafe impl Sync for GpuBiSpmmOp {}
+impl GpuBiSpmmOp {
+    pub fn new(op: GpuSpmmOp) -> Self {
+        let mut t = std::ptr::null_mut();
+        check(unsafe { ffi::famg_transpose(op.raw(), &mut t) });
+        Self { op, t }
+    }
+}
+impl Drop for GpuBiSpmmOp { fn drop(&mut self) { unsafe { ffi::famg_csr_destroy(self.t); } } }
+impl LinOp<f64> for GpuBiSpmmOp {
+    fn apply_scratch(&self, n: usize, par: Par) -> StackReq { self.op.apply_scratch(n, par) }
+    fn nrows(&self) -> usize { self.op.nrows() }
+    fn ncols(&self) -> usize { self.op.ncols() }
+    fn apply(&self, out: MatMut<f64>, rhs: MatRef<f64>, par: Par, stack: &mut MemStack) { self.op.apply(out, rhs, par, stack) }
+    fn conj_apply(&self, out: MatMut<f64>, rhs: MatRef<f64>, par: Par, stack: &mut MemStack) { self.op.apply(out, rhs, par, stack) }
+}
+impl BiLinOp<f64> for GpuBiSpmmOp {
+    fn transpose_apply_scratch(&self, _n: usize, _par: Par) -> StackReq { StackReq::empty() }
+    fn transpose_apply(&self, mut out: MatMut<f64>, rhs: MatRef<f64>, _par: Par, _stack: &mut MemStack) {
+        assert!(out.row_stride() == 1 && rhs.row_stride() == 1);
+        check(unsafe { ffi::famg_spmm(self.t, out.as_ptr_mut(), out.col_stride() as i64, rhs.as_ptr(), rhs.col_stride() as i64, rhs.ncols() as i64) });
+    }
+    fn adjoint_apply(&self, out: MatMut<f64>, rhs: MatRef<f64>, par: Par, stack: &mut MemStack) { self.transpose_apply(out, rhs, par, stack) }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Multi-GPU: one rank (process or thread) per GPU, row slabs.  `Hierarchy::coarsen` (hierarchy.rs:190-248)
+// on slabs: every rank owns the rows [row_split[rank], row_split[rank + 1]) of every level.
+// ---------------------------------------------------------------------------------------------------------------
+pub struct GpuComm { h: *mut ffi::famg_comm, pub nranks: usize, pub rank: usize, ctx: Arc<GpuContext> }
+impl GpuComm {
+    /// `id`: 128 bytes from `GpuComm::unique_id()` on rank 0, broadcast by the caller's launcher (MPI, sci-bevy-comm, files ...)
+    pub fn new(ctx: Arc<GpuContext>, nranks: usize, rank: usize, id: &[u8; ffi::FAMG_UNIQUE_ID_BYTES]) -> Self {
+        let mut h = std::ptr::null_mut();
+        check(unsafe { ffi::famg_comm_create(ctx.0, nranks as i32, rank as i32, id.as_ptr() as *const _, &mut h) });
+        Self { h, nranks, rank, ctx }
+    }
+    pub fn unique_id() -> [u8; ffi::FAMG_UNIQUE_ID_BYTES] {
+        let mut id = [0u8; ffi::FAMG_UNIQUE_ID_BYTES];
+        check(unsafe { ffi::famg_comm_unique_id(id.as_mut_ptr() as *mut _) });
+        id
+    }
+}
+impl Drop for GpuComm { fn drop(&mut self) { unsafe { ffi::famg_comm_destroy(self.h); } } }
+
+/// Row-partitioned operator: this rank's slab carries GLOBAL column indices (exactly the rows a rank would cut out of the
+/// crate's `SparseRowMat`); `finalize` builds the halo plan.
+pub struct GpuDistMat { h: *mut ffi::famg_dmat }
+impl GpuDistMat {
+    pub fn from_slab(comm: &GpuComm, slab: SparseRowMatRef<usize, f64>, ncols_global: usize) -> Self {
+        let op = GpuSpmmOp::new(comm.ctx.clone(), slab);
+        let slabs = [op.raw() as *mut ffi::famg_csr];
+        let mut h = std::ptr::null_mut();
+        check(unsafe { ffi::famg_dmat_create(comm.h, slabs.as_ptr(), ncols_global as i64, std::ptr::null(), &mut h) });
+        Self { h }   // the distributed matrix holds its own reference on the slab
+    }
+    pub fn finalize(self, replicated_cols: bool) -> Self { check(unsafe { ffi::famg_dmat_finalize(self.h, replicated_cols as i32) }); self }
+    pub fn nrows_global(&self) -> usize { let mut n = 0i64; check(unsafe { ffi::famg_dmat_info(self.h, &mut n, std::ptr::null_mut(), std::ptr::null_mut(), std::ptr::null_mut()) }); n as usize }
+    /// the whole operator on every rank (transition to the replicated coarse tail)
+    pub fn gather(&self) -> SparseRowMat<usize, f64> {
+        let mut out = [std::ptr::null_mut::<ffi::famg_csr>()];
+        check(unsafe { ffi::famg_dmat_gather(self.h, out.as_mut_ptr()) });
+        download_csr(out[0])
+    }
+}
+impl Drop for GpuDistMat { fn drop(&mut self) { unsafe { ffi::famg_dmat_destroy(self.h); } } }
+
+/// One level of `Hierarchy::coarsen` on slabs: this rank's own aggregates over LOCAL row ids and its slice of the
+/// near-null vector in, `(P, R, A_c, coarse near-null slice)` out; `P` / `A_c` still need `finalize`.
+pub fn dist_coarsen(a: &GpuDistMat, aggregates: &[std::collections::BTreeSet<usize>], near_null_local: &[f64], smoothing_steps: usize)
+    -> (GpuDistMat, GpuDistMat, GpuDistMat, Vec<f64>) {
+    let mut agg_ptr = vec![0usize];
+    let mut agg_nodes = Vec::new();
+    for agg in aggregates { agg_nodes.extend(agg.iter().copied()); agg_ptr.push(agg_nodes.len()); }
+    let n_aggs = [aggregates.len() as i64];
+    let mut coarse_nn = vec![0f64; aggregates.len()];
+    let (mut p, mut r, mut ac) = (std::ptr::null_mut(), std::ptr::null_mut(), std::ptr::null_mut());
+    check(unsafe {
+        ffi::famg_dist_coarsen(a.h, n_aggs.as_ptr(), [agg_ptr.as_ptr()].as_ptr(), [agg_nodes.as_ptr()].as_ptr(), [near_null_local.as_ptr()].as_ptr(),
+                               smoothing_steps as i32, 0.66, &mut p, &mut r, &mut ac, [coarse_nn.as_mut_ptr()].as_ptr())
+    });
+    (GpuDistMat { h: p }, GpuDistMat { h: r }, GpuDistMat { h: ac }, coarse_nn)
+}
+/// hierarchy.rs:217-228 on a distributed level (3-step L1 stationary iteration, thin Q of the single column)
+pub fn dist_smooth_near_null(a: &GpuDistMat, nn_local: &mut [f64]) {
+    check(unsafe { ffi::famg_dist_smooth_near_null(a.h, 3, [nn_local.as_mut_ptr()].as_ptr()) });
+}
+
+/// Row-partitioned `Multigrid` + PCG: distributed levels from `dist_coarsen`, the replicated tail as a `GpuMultigrid`.
+pub struct GpuDistMultigrid { h: *mut ffi::famg_dist_mg, _tail: GpuMultigrid }
+impl GpuDistMultigrid {
+    pub fn new(comm: &GpuComm, a: &[&GpuDistMat], r: &[&GpuDistMat], p: &[&GpuDistMat], tail: GpuMultigrid) -> Self {
+        let (ah, rh, ph): (Vec<_>, Vec<_>, Vec<_>) = (a.iter().map(|m| m.h).collect(), r.iter().map(|m| m.h).collect(), p.iter().map(|m| m.h).collect());
+        let mut h = std::ptr::null_mut();
+        check(unsafe { ffi::famg_dist_mg_create_levels(comm.h, a.len() as i32, ah.as_ptr(), rh.as_ptr(), ph.as_ptr(), 0 /* L1 */, 0.66, tail.raw(), &mut h) });
+        Self { h, _tail: tail }
+    }
+    /// `conjugate_gradient` on the partitioned system: `x_local` / `b_local` are this rank's rows
+    pub fn solve(&self, x_local: &mut [f64], b_local: &[f64], rel_tol: f64, max_iters: usize) -> Result<ffi::famg_cg_info, ffi::famg_cg_info> {
+        let mut info = ffi::famg_cg_info::default();
+        let st = unsafe { ffi::famg_dist_pcg_solve(self.h, x_local.as_mut_ptr(), b_local.as_ptr(), rel_tol, 0.0, max_iters as i64, 1, &mut info) };
+        match st { ffi::FAMG_OK => Ok(info), ffi::FAMG_ERR_NO_CONVERGENCE | ffi::FAMG_ERR_NOT_SPD => Err(info), other => { check(other); unreachable!() } }
+    }
+}
+impl Drop for GpuDistMultigrid { fn drop(&mut self) { unsafe { ffi::famg_dist_mg_destroy(self.h); } } }
 
 /// Prolongator smoothing for `block_size > 1` (interpolation/mod.rs:963-1028): returns the device CSR of
 /// `P - 0.66 D_b^-1 A P`; download with `famg_csr_download` into `SparseRowMat::new(..)`.
