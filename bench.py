@@ -472,8 +472,8 @@ def run_ours(args):
         traffic, traffic_src = None, None
         try:  # DRAM bytes per launch from the committed ncu --set full capture of this exact operator
             if dims == (256, 256, 256) and args.stencil == 7 and world == 1:
-                traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["smooth"]["traffic_bytes_per_launch"]
-                traffic_src = "profiles/r1_traffic.json (ncu --set full capture of this kernel on this operator; not measured in this run)"
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))["smooth"]["traffic_bytes_per_launch"]
+                traffic_src = "profiles/r2_traffic.json (ncu --set full capture of this kernel on this operator; not measured in this run)"
         except Exception:
             pass
         tpr = ar.plan()["threads_per_row"]
