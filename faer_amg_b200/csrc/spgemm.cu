@@ -109,9 +109,31 @@ struct SgStage {
 
 // DENSE: `vals` is indexed by the column itself (ncols(B) accumulators), `touched` records the
 // structural pattern; no search pass.
+// column -> output slot.  slot16 mirrors the key table of the insertion pass: position h holds the rank of the key that
+// landed there among the sorted distinct columns, so a lookup re-walks the key's own probe sequence (1-2 steps at load
+// <= 0.5) and recognises it by list[slot] == j -- two shared-memory reads per step instead of the 7-9 dependent reads of a
+// bisection (45 % of the instructions of the fill kernels in round 1's source-level profile).  Without a slot table
+// (global-memory class) the bisection stays.
+__device__ __forceinline__ int sg_find_slot(int j, const int *__restrict__ list, int n, const unsigned short *__restrict__ slot16, int hmask) {
+    if (slot16 != nullptr) {
+        unsigned h = sg_hash(j, hmask);
+        while (true) {
+            const int sl = slot16[h];
+            if (list[sl] == j) return sl;
+            h = (h + 1) & (unsigned)hmask;
+        }
+    }
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (list[mid] < j) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
 template <bool DENSE>
 __device__ void sg_accumulate_staged(int tid, const SgMat &a, const SgMat &b, int a0, int a1, const int *list, int n, double *vals,
-                                     SgStage &st, unsigned char *touched = nullptr) {
+                                     SgStage &st, unsigned char *touched = nullptr, const unsigned short *slot16 = nullptr, int hmask = 0) {
     const int warp = tid >> 5, lane = tid & 31;
     int q = a0, poff = 0;  // next k of the row; entries of that k already consumed (a B_k longer than one batch)
     while (q < a1) {
@@ -147,15 +169,7 @@ __device__ void sg_accumulate_staged(int tid, const SgMat &a, const SgMat &b, in
         }
         __syncthreads();
         if (!DENSE) {
-            for (int t = tid; t < total; t += 256) {  // column -> output slot
-                const int j = st.slot[t];
-                int lo = 0, hi = n;
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (list[mid] < j) lo = mid + 1; else hi = mid;
-                }
-                st.slot[t] = lo;
-            }
+            for (int t = tid; t < total; t += 256) st.slot[t] = sg_find_slot(st.slot[t], list, n, slot16, hmask);  // column -> output slot
             __syncthreads();
         }
         if (total > 64 * nk) {  // long segments: the whole CTA takes one k at a time
@@ -185,7 +199,8 @@ __device__ void sg_accumulate_staged(int tid, const SgMat &a, const SgMat &b, in
 // once the keys have been compacted), list: H/2 ints.  The row has n <= H/2 distinct columns.
 template <int GROUP>
 __device__ void sg_row_fill(int i, int lane, const SgMat &a, const SgMat &b, int *table, int *list, int hmask, int *cnt,
-                            const int *c_rp, int *c_col, double *c_val, const SgEpilogue &ep, SgStage *stage = nullptr) {
+                            const int *c_rp, int *c_col, double *c_val, const SgEpilogue &ep, SgStage *stage = nullptr,
+                            unsigned short *slot16 = nullptr) {
     const int n = sg_row_insert<GROUP>(i, lane, a, b, table, hmask, cnt);
     const int half = (hmask + 1) >> 1;
     // compact the distinct columns, pad with INT_MAX up to the sort width (power of two >= n)
@@ -212,13 +227,23 @@ __device__ void sg_row_fill(int i, int lane, const SgMat &a, const SgMat &b, int
             group_sync<GROUP>();
         }
     }
-    double *vals = reinterpret_cast<double *>(table);  // keys are in `list` now
+    if (slot16 != nullptr) {
+        // rank of every key at the position it occupies in the key table (unique per key: no conflicts)
+        for (int t = lane; t < n; t += GROUP) {
+            const int key = list[t];
+            unsigned h = sg_hash(key, hmask);
+            while (table[h] != key) h = (h + 1) & (unsigned)hmask;
+            slot16[h] = (unsigned short)t;
+        }
+        group_sync<GROUP>();
+    }
+    double *vals = reinterpret_cast<double *>(table);  // the keys are in `list` (and their ranks in slot16) now
     (void)half;
     for (int t = lane; t < n; t += GROUP) vals[t] = 0.0;
     group_sync<GROUP>();
     const int a0 = a.rp[i], a1 = a.rp[i + 1];
     if (GROUP == 256 && stage != nullptr) {
-        sg_accumulate_staged<false>(lane, a, b, a0, a1, list, n, vals, *stage);
+        sg_accumulate_staged<false>(lane, a, b, a0, a1, list, n, vals, *stage, nullptr, slot16, hmask);
     } else {
     // numeric: ascending k, lanes over the entries of B_k (each j unique within one k => no races)
     // The loop is latency-bound (a.col[q] -> b.rp[k] -> b.col[p] are dependent loads and every k ends
@@ -241,11 +266,7 @@ __device__ void sg_row_fill(int i, int lane, const SgMat &a, const SgMat &b, int
         }
         for (int p = b0 + lane; p < b1; p += GROUP) {
             if (p != b0 + lane) { j = b.col[p]; bv = b.val[p]; }
-            int lo = 0, hi = n;
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (list[mid] < j) lo = mid + 1; else hi = mid;
-            }
+            const int lo = sg_find_slot(j, list, n, slot16, hmask);
             vals[lo] = vals[lo] + av * bv;
         }
         group_sync<GROUP>();
@@ -411,6 +432,7 @@ struct SgArgs {
     const int *c_rp; int *c_col; double *c_val;  // pass 2 output
     SgEpilogue ep;
     int *g_table; int *g_list;    // global-table class scratch (per CTA slices)
+    int slots;                    // CTA class: a slot table fits next to the key table (2h ints + stage <= shared memory)
 };
 
 // ---- tiny rows (ub <= SG_TINY): one THREAD per row.  A warp-per-row walk of a 7-product row is a
@@ -472,12 +494,13 @@ __global__ void __launch_bounds__(SG_WARPS * 32) sg_warp_kernel(SgArgs s) {
     __shared__ int s_cnt[SG_WARPS];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int h = s.hmask + 1;
-    const int per_warp = FILL ? h + (h >> 1) : h;
+    const int per_warp = FILL ? 2 * h : h;  // fill: key table / accumulators (h) + sorted list (h/2) + slot table (h x u16)
     int *table = sg_smem + w * per_warp;
     const int idx = blockIdx.x * SG_WARPS + w;
     if (idx >= s.count) return;
     const int i = s.perm[idx];
-    if (FILL) sg_row_fill<32>(i, lane, s.a, s.b, table, table + h, s.hmask, &s_cnt[w], s.c_rp, s.c_col, s.c_val, s.ep);
+    if (FILL) sg_row_fill<32>(i, lane, s.a, s.b, table, table + h, s.hmask, &s_cnt[w], s.c_rp, s.c_col, s.c_val, s.ep, nullptr,
+                              reinterpret_cast<unsigned short *>(table + h + (h >> 1)));
     else sg_row_count<32>(i, lane, s.a, s.b, table, s.hmask, &s_cnt[w], s.row_nnz);
 }
 
@@ -488,8 +511,9 @@ __global__ void __launch_bounds__(256) sg_cta_kernel(SgArgs s) {
     const int h = s.hmask + 1;
     const int i = s.perm[blockIdx.x];
     if (FILL) {
-        SgStage *stage = reinterpret_cast<SgStage *>(sg_smem + h + (h >> 1));  // 8-byte aligned: h is a multiple of 4
-        sg_row_fill<256>(i, threadIdx.x, s.a, s.b, sg_smem, sg_smem + h, s.hmask, &s_cnt, s.c_rp, s.c_col, s.c_val, s.ep, stage);
+        SgStage *stage = reinterpret_cast<SgStage *>(sg_smem + (s.slots ? 2 * h : h + (h >> 1)));  // 8-byte aligned: h is a multiple of 4
+        sg_row_fill<256>(i, threadIdx.x, s.a, s.b, sg_smem, sg_smem + h, s.hmask, &s_cnt, s.c_rp, s.c_col, s.c_val, s.ep, stage,
+                         s.slots ? reinterpret_cast<unsigned short *>(sg_smem + h + (h >> 1)) : nullptr);
     } else sg_row_count<256>(i, threadIdx.x, s.a, s.b, sg_smem, s.hmask, &s_cnt, s.row_nnz);
 }
 
@@ -679,7 +703,9 @@ static famg_status sg_run_pass(famg_ctx *ctx, SgArgs base, const int *d_size, in
             continue;
         }
         s.hmask = plan[c].h - 1;
-        const size_t per_row = (size_t)(FILL ? plan[c].h + plan[c].h / 2 : plan[c].h) * sizeof(int);
+        // fill: key table / accumulators (h ints) + sorted list (h/2) + slot table (h x u16) when it fits (the 32768-slot class does not)
+        s.slots = FILL && (plan[c].kind == 0 || (size_t)2 * plan[c].h * sizeof(int) + sizeof(SgStage) <= 200 * 1024);
+        const size_t per_row = (size_t)(FILL ? (s.slots ? 2 * plan[c].h : plan[c].h + plan[c].h / 2) : plan[c].h) * sizeof(int);
         if (plan[c].kind == 0) {
             const size_t smem = per_row * SG_WARPS;
             if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(sg_warp_kernel<FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
