@@ -77,7 +77,9 @@ struct SpmvKernelParams {
 __device__ __noinline__ void chunk_signal(const P2PPlanDev *pl, const int *push_map, int push_lo, int push_hi, unsigned *sig,
                                           unsigned sig_target, const double *y, int row, bool owner) {
     if (pl != nullptr) {
-        if (owner) {
+        // a signalled chunk may reach past the boundary rows (chunks hold 256 / tpr rows): only rows outside [push_lo, push_hi)
+        // have an entry in the push map
+        if (owner && (row < push_lo || row >= push_hi)) {
             const int mi = row < push_lo ? row : row - push_hi + push_lo;
             const int m = __ldg(push_map + mi);
             if (m >= 0) {
