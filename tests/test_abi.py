@@ -101,3 +101,35 @@ def test_argument_validation_without_a_device():
     empty = StrengthGraph.from_csr([0], [], [])
     naggs = C.c_int64(-1)
     assert L.famg_partition_modularity(empty._h, 8.0, 1.0, 10, (C.c_uint64 * 1)(), C.byref(naggs)) == _ffi.OK and naggs.value == 0
+
+
+def test_distributed_setup_entry_points_validate_without_a_device():
+    """The round-2 entry points (distributed hierarchy construction, device aggregates, instrumentation) reject bad
+    arguments before touching CUDA; the host-thread knob works without a device."""
+    import ctypes as C
+    from faer_amg_b200 import _ffi
+    L = _ffi.lib()
+    out = C.c_void_p()
+    assert L.famg_comm_create_sim(None, 2, C.byref(out)) == _ffi.ERR_INVALID
+    assert L.famg_comm_dims(None, None, None, None) == _ffi.ERR_INVALID
+    assert L.famg_dmat_create(None, None, 4, None, C.byref(out)) == _ffi.ERR_INVALID
+    assert L.famg_dmat_finalize(None, 0) == _ffi.ERR_INVALID
+    assert L.famg_dmat_info(None, None, None, None, None) == _ffi.ERR_INVALID
+    assert L.famg_dmat_local(None, 0, 1, C.byref(out)) == _ffi.ERR_INVALID
+    assert L.famg_dmat_gather(None, C.byref(out)) == _ffi.ERR_INVALID
+    assert L.famg_dmat_destroy(None) == _ffi.OK
+    assert L.famg_dist_coarsen(None, None, None, None, None, 1, 0.66, C.byref(out), C.byref(out), C.byref(out), None) == _ffi.ERR_INVALID
+    assert L.famg_dist_coarsen_dev(None, None, None, 1, 0.66, C.byref(out), C.byref(out), C.byref(out), None) == _ffi.ERR_INVALID
+    assert L.famg_dist_smooth_near_null(None, 3, None) == _ffi.ERR_INVALID
+    assert L.famg_dist_smooth_near_null_dev(None, 3, None) == _ffi.ERR_INVALID
+    assert L.famg_dist_mg_create_levels(None, 0, None, None, None, 0, 0.66, None, C.byref(out)) == _ffi.ERR_INVALID
+    assert L.famg_partition_geometric_dev(None, 4, 4, 4, 2, 2, 2, C.byref(out), None) == _ffi.ERR_INVALID
+    assert L.famg_partition_upload(None, 4, 2, None, None, C.byref(out)) == _ffi.ERR_INVALID
+    assert L.famg_partition_dims(None, None, None) == _ffi.ERR_INVALID
+    assert L.famg_partition_destroy(None) == _ffi.OK
+    assert L.famg_tentative_p_dev(None, None, C.byref(out), None) == _ffi.ERR_INVALID
+    assert L.famg_ctx_reserve(None, 1 << 20) == _ffi.ERR_INVALID
+    assert L.famg_ctx_trace_dump(None, b"/tmp/x") == _ffi.ERR_INVALID
+    assert L.famg_gallery_g7_slab(None, 4, 4, 4, 0, 2, C.byref(out)) == _ffi.ERR_INVALID
+    assert L.famg_set_num_threads(0) == _ffi.ERR_INVALID
+    assert L.famg_set_num_threads(2) == _ffi.OK
