@@ -386,6 +386,93 @@ struct MultigridConfig {
     }
 };
 
+// ---------------------------------------------------------------------------------------------------------------
+// Hierarchy::coarsen on row slabs (one rank per GPU; the reference is shared-memory only).  A Comm hosts one rank of a
+// multi-process job (id from famg_comm_unique_id on rank 0) or -- for tests on a single GPU -- all `nranks` virtual
+// ranks of the CONSTRUCTION (Comm::virtual_ranks); per-rank arguments are vectors with one entry per hosted rank.
+// ---------------------------------------------------------------------------------------------------------------
+class Comm {
+public:
+    Comm(const Context &ctx, int nranks, int rank, const void *unique_id) { check(famg_comm_create(ctx.raw(), nranks, rank, unique_id, &h_)); }
+    static std::unique_ptr<Comm> virtual_ranks(const Context &ctx, int nranks) {
+        famg_comm *h = nullptr;
+        check(famg_comm_create_sim(ctx.raw(), nranks, &h));
+        return std::unique_ptr<Comm>(new Comm(h));
+    }
+    ~Comm() { famg_comm_destroy(h_); }
+    Comm(const Comm &) = delete;
+    famg_comm *raw() const { return h_; }
+    int nranks() const { int n; check(famg_comm_dims(h_, &n, nullptr, nullptr)); return n; }
+    int rank() const { int r; check(famg_comm_dims(h_, nullptr, &r, nullptr)); return r; }
+    int nlocal() const { int n; check(famg_comm_dims(h_, nullptr, nullptr, &n)); return n; }
+private:
+    explicit Comm(famg_comm *h) : h_(h) {}
+    famg_comm *h_ = nullptr;
+};
+
+// row-partitioned SparseRowMat: the slabs carry global column ids and are taken over (finalize renumbers them in place)
+class DistMat {
+public:
+    DistMat(const Comm &comm, const std::vector<std::shared_ptr<SparseRowMat>> &slabs, int64_t ncols_global) : nlocal_(comm.nlocal()), nranks_(comm.nranks()) {
+        std::vector<famg_csr *> raw;
+        for (auto &m : slabs) raw.push_back(m->raw());
+        check(famg_dmat_create(comm.raw(), raw.data(), ncols_global, nullptr, &h_));
+    }
+    explicit DistMat(famg_dmat *adopt, int nlocal, int nranks) : h_(adopt), nlocal_(nlocal), nranks_(nranks) {}
+    ~DistMat() { famg_dmat_destroy(h_); }
+    DistMat(const DistMat &) = delete;
+    famg_dmat *raw() const { return h_; }
+    DistMat &finalize(bool replicated_cols = false) { check(famg_dmat_finalize(h_, replicated_cols ? 1 : 0)); return *this; }
+    int64_t nrows() const { int64_t n; check(famg_dmat_info(h_, &n, nullptr, nullptr, nullptr)); return n; }
+    std::vector<int64_t> row_split() const { std::vector<int64_t> rs((size_t)nranks_ + 1); check(famg_dmat_info(h_, nullptr, nullptr, rs.data(), nullptr)); return rs; }
+    std::shared_ptr<SparseRowMat> local(int li, bool global_cols) const { famg_csr *m; check(famg_dmat_local(h_, li, global_cols ? 1 : 0, &m)); return std::make_shared<SparseRowMat>(m); }
+    std::shared_ptr<SparseRowMat> gather() const {  // the whole operator, replicated (collective); one copy is kept
+        std::vector<famg_csr *> out((size_t)nlocal_, nullptr);
+        check(famg_dmat_gather(h_, out.data()));
+        for (size_t i = 1; i < out.size(); ++i) famg_csr_destroy(out[i]);
+        return std::make_shared<SparseRowMat>(out[0]);
+    }
+private:
+    famg_dmat *h_ = nullptr;
+    int nlocal_ = 1, nranks_ = 1;
+};
+
+// One level: every hosted rank's aggregates over LOCAL row ids and its near-null slice in; P, R, A_c and the coarse near-null
+// slices out (hierarchy.rs:203-216 / interpolation/mod.rs:730-836 on slabs).
+struct DistGalerkinCoarse {
+    std::unique_ptr<DistMat> interpolation, restriction, coarse_mat;
+    std::vector<std::vector<double>> coarse_nn;
+};
+inline DistGalerkinCoarse dist_smoothed_aggregation(const Comm &comm, DistMat &fine, const std::vector<Partition> &parts,
+                                                    const std::vector<std::vector<double>> &near_null, int smoothing_steps) {
+    const int nl = comm.nlocal();
+    std::vector<int64_t> na;
+    std::vector<const uint64_t *> ap, an;
+    std::vector<const double *> nn;
+    DistGalerkinCoarse g;
+    std::vector<double *> cnn;
+    for (int li = 0; li < nl; ++li) {
+        na.push_back(parts[(size_t)li].naggs());
+        ap.push_back(parts[(size_t)li].agg_ptr.data()); an.push_back(parts[(size_t)li].agg_nodes.data());
+        nn.push_back(near_null[(size_t)li].data());
+        g.coarse_nn.emplace_back((size_t)std::max<int64_t>(na.back(), 1), 0.0);
+    }
+    for (auto &v : g.coarse_nn) cnn.push_back(v.data());
+    famg_dmat *p = nullptr, *r = nullptr, *ac = nullptr;
+    check(famg_dist_coarsen(fine.raw(), na.data(), ap.data(), an.data(), nn.data(), smoothing_steps, 0.66, &p, &r, &ac, cnn.data()));
+    for (int li = 0; li < nl; ++li) g.coarse_nn[(size_t)li].resize((size_t)na[(size_t)li]);
+    g.interpolation.reset(new DistMat(p, nl, comm.nranks()));
+    g.restriction.reset(new DistMat(r, nl, comm.nranks()));
+    g.coarse_mat.reset(new DistMat(ac, nl, comm.nranks()));
+    return g;
+}
+// hierarchy.rs:217-228 on a finalized distributed level
+inline void dist_smooth_near_null(DistMat &a, std::vector<std::vector<double>> &nn) {
+    std::vector<double *> ptrs;
+    for (auto &v : nn) ptrs.push_back(v.data());
+    check(famg_dist_smooth_near_null(a.raw(), 3, ptrs.data()));
+}
+
 struct CgParams { double abs_tolerance = 0.0, rel_tolerance = 1e-12; int64_t max_iters = 1000; bool zero_guess = true; };
 // faer conjugate_gradient as driven by utils.rs:574-609; throws on NoConvergence like Err(CgError).
 inline famg_cg_info conjugate_gradient(double *x, const Multigrid &pc, const SparseRowMat &a, const double *b, const CgParams &p) {

@@ -80,6 +80,46 @@ int main() {
             if (!(ic.iter_count <= i3.iter_count) || !(std::sqrt(diff) <= 1e-4 * std::sqrt(nrm))) return 1;  // E^3 instead of E per iteration
             std::printf("composite ok: %lld PCG iterations (single multigrid: %lld)\n", (long long)ic.iter_count, (long long)i3.iter_count);
         }
+        {   // the first level of the same hierarchy built on 4 row slabs (virtual ranks hosted by this process): every rank's
+            // rows of A_c must be the rows of the undistributed coarse operator, bit for bit
+            const int nr = 4;
+            auto comm = famg::Comm::virtual_ranks(ctx, nr);
+            std::vector<std::shared_ptr<famg::SparseRowMat>> slabs;
+            std::vector<famg::Partition> parts;
+            std::vector<std::vector<double>> nns;
+            for (int r = 0; r < nr; ++r) {
+                famg_csr *sl = nullptr;
+                famg::check(famg_gallery_g7_slab(ctx.raw(), N, N, N, r * (N / nr), (r + 1) * (N / nr), &sl));
+                slabs.push_back(std::make_shared<famg::SparseRowMat>(sl));
+                const int64_t d[3] = {N, N, N / nr};
+                int64_t c[3];
+                parts.push_back(famg::geometric_partition(d, block, c));
+                nns.emplace_back((size_t)(rows / nr), 1.0 / std::sqrt((double)rows));
+            }
+            famg::DistMat a_dist(*comm, slabs, rows);
+            a_dist.finalize();
+            famg::DistGalerkinCoarse g = famg::dist_smoothed_aggregation(*comm, a_dist, parts, nns, 1);
+            const std::vector<int64_t> cs = g.coarse_mat->row_split();
+            const famg::SparseRowMat &want = *h.operators[1];
+            std::vector<uint64_t> wrp((size_t)want.nrows() + 1), wci((size_t)want.compute_nnz());
+            std::vector<double> wv((size_t)want.compute_nnz());
+            famg::check(famg_csr_download(want.raw(), wrp.data(), wci.data(), wv.data()));
+            for (int r = 0; r < nr; ++r) {
+                auto got = g.coarse_mat->local(r, true);
+                std::vector<uint64_t> rp((size_t)got->nrows() + 1), ci((size_t)got->compute_nnz());
+                std::vector<double> v((size_t)got->compute_nnz());
+                famg::check(famg_csr_download(got->raw(), rp.data(), ci.data(), v.data()));
+                const uint64_t base = wrp[(size_t)cs[(size_t)r]];
+                bool same = got->nrows() == cs[(size_t)r + 1] - cs[(size_t)r] && rp.back() == wrp[(size_t)cs[(size_t)r + 1]] - base;
+                for (size_t q = 0; same && q < ci.size(); ++q) same = ci[q] == wci[base + q] && v[q] == wv[base + q];
+                if (!same) { std::printf("distributed coarse operator differs on virtual rank %d\n", r); return 1; }
+            }
+            g.coarse_mat->finalize();
+            famg::dist_smooth_near_null(*g.coarse_mat, g.coarse_nn);
+            size_t off = 0;
+            for (auto &v : g.coarse_nn) { for (size_t i = 0; i < v.size(); ++i) if (v[i] != h.near_nulls[1][off + i]) { std::printf("distributed near-null differs\n"); return 1; } off += v.size(); }
+            std::printf("distributed ok: level-1 operator and near-null of %d row slabs bit-identical to the undistributed build\n", nr);
+        }
         std::printf("mirror ok: 32^3 hierarchy %zu levels, op complexity %.3f, %lld PCG iterations, rel residual %.2e\n", h.levels(),
                     h.op_complexity(), (long long)i3.iter_count, i3.rel_residual);
         // the oracle's count for this case is 15 (tests/golden/oracle_golden.json g7_32_l1)

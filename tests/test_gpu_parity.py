@@ -454,4 +454,4 @@ def test_cpp_mirror_on_gpu():
     if not os.path.exists(exe):
         pytest.skip("run __graft_entry__.build() first")
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
-    assert out.returncode == 0 and "mirror ok" in out.stdout, out.stdout + out.stderr
+    assert out.returncode == 0 and "mirror ok" in out.stdout and "distributed ok" in out.stdout, out.stdout + out.stderr
