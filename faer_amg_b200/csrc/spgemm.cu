@@ -21,6 +21,8 @@
 //   classes one warp per row (tables of 64..4096 slots in shared memory), one CTA per row (up to
 //           192 KB of shared memory), and per-CTA tables in global memory for anything larger.
 // The prolongator-smoothing epilogue  S_i <- -(w/a_ii) S_i + P_i  is fused into pass 2.
+#include <cuda_pipeline.h>
+
 #include "common.cuh"
 
 namespace famg {
@@ -320,28 +322,84 @@ constexpr int SG_NCLS = 8;   // size classes per pass (see sg_plan)
 constexpr int SG_TINY = 32;  // rows with at most this many products: one thread per row
 constexpr int SG_WARPS = 4;  // rows per CTA in the warp-per-row classes
 
+// ---- window class: rows whose candidate columns all lie in a short range [lo, lo + span) -----------------
+// The products of a Galerkin triple product on the coarse levels have hundreds to thousands of B-rows per output row, and
+// those rows overlap heavily: with a locality-preserving numbering all of them fall into a window of a few thousand
+// columns.  Such rows get one f64 accumulator per column of the window in shared memory (no table, no sort, no search) and
+// are computed ONCE: the count pass already does the arithmetic and parks the finished row in a scratch buffer, the fill
+// pass only copies it (see sg_window_kernel).
+constexpr int WR_SE = 512;          // entries of B staged per chunk (two chunks per warp: one in flight, one being accumulated)
+constexpr int WN_SPAN_MAX = 11264;  // widest window: 9 * span + 12 KB of shared memory per row, two rows per SM
+constexpr int WN_CLASS = 7, SG_SKIP_CLASS = 5, SG_GLOBAL_CLASS = 6;
+
+struct SgWinPlan {               // inputs / outputs of the classification of window rows (device pointers; bfirst == nullptr: off)
+    const int *bfirst, *blast;   // first / last column of every row of B
+    const int *unsorted;         // != 0: some row of B is not strictly ascending -> no window rows
+    int *lo, *span;              // per row of A
+    unsigned long long *bound;   // sum over the window rows of min(ub, span): what the scratch buffer has to hold at most
+    int *max_span;
+    int min_ub, min_seg;         // rows with more than min_ub products in segments (rows of B) of at least min_seg entries on average
+};
+
+// first / last column of every row of B (8 lanes per row) and whether every row is strictly ascending
+__global__ void __launch_bounds__(256) sg_bspan_kernel(SgMat b, int nrows, int *__restrict__ bfirst, int *__restrict__ blast,
+                                                       int *__restrict__ unsorted) {
+    const int r = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 3), l = threadIdx.x & 7;
+    if (r >= nrows) return;
+    const int b0 = b.rp[r], b1 = b.rp[r + 1];
+    bool bad = false;
+    for (int p = b0 + l; p + 1 < b1; p += 8) bad |= b.col[p] >= b.col[p + 1];
+    if (bad) atomicOr(unsorted, 1);
+    if (l == 0) { bfirst[r] = b0 < b1 ? b.col[b0] : 0x7fffffff; blast[r] = b0 < b1 ? b.col[b1 - 1] : -1; }
+}
+
 // ub_i = number of products of row i (work); size_i = min(ub_i, ncols(B)) bounds the distinct columns
-__global__ void sg_ub_kernel(SgMat a, SgMat b, int m, int ncols_b, int *__restrict__ ub, int *__restrict__ size) {
+__global__ void __launch_bounds__(256) sg_ub_kernel(SgMat a, SgMat b, int m, int ncols_b, int *__restrict__ ub, int *__restrict__ size,
+                                                    SgWinPlan wp) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m) return;
     long long s = 0;
-    for (int q = a.rp[i]; q < a.rp[i + 1]; ++q) { const int k = a.col[q]; s += b.rp[k + 1] - b.rp[k]; }
+    int jmin = 0x7fffffff, jmax = -1;
+    if (i < m) {
+        for (int q = a.rp[i]; q < a.rp[i + 1]; ++q) {
+            const int k = a.col[q];
+            s += b.rp[k + 1] - b.rp[k];
+            if (wp.bfirst) { jmin = min(jmin, wp.bfirst[k]); jmax = max(jmax, wp.blast[k]); }
+        }
+    }
     const int u = s > 0x3fffffff ? 0x3fffffff : (int)s;
-    ub[i] = u;
-    // rows with a lot of products get a whole CTA in the count pass even when B is narrow
-    size[i] = u > 3072 ? max(min(u, ncols_b), 3073) : min(u, ncols_b);
+    unsigned wbound = 0, wspan = 0;
+    if (i < m) {
+        ub[i] = u;
+        // rows with a lot of products get a whole CTA in the count pass even when B is narrow
+        int sz = u > 3072 ? max(min(u, ncols_b), 3073) : min(u, ncols_b);
+        if (wp.bfirst && u > wp.min_ub && (long long)u >= (long long)wp.min_seg * (a.rp[i + 1] - a.rp[i]) && jmax >= jmin &&
+            jmax - jmin < WN_SPAN_MAX && *wp.unsorted == 0) {
+            const int span = jmax - jmin + 1;
+            wp.lo[i] = jmin; wp.span[i] = span;
+            wbound = (unsigned)min(u, span); wspan = (unsigned)span;
+            sz = -WN_CLASS;
+        }
+        size[i] = sz;
+    }
+    if (wp.bfirst) {  // one atomic per warp
+        const unsigned tb = __reduce_add_sync(0xffffffffu, wbound), ts = __reduce_max_sync(0xffffffffu, wspan);
+        if ((threadIdx.x & 31) == 0 && tb) { atomicAdd(wp.bound, (unsigned long long)tb); atomicMax(wp.max_span, (int)ts); }
+    }
 }
 
 // pass-2 size: the exact row length, raised for rows with a lot of work per output entry so that
 // they get a whole CTA (the k loop is sequential per row; see sg_row_fill)
-__global__ void sg_size2_kernel(const int *__restrict__ row_nnz, const int *__restrict__ ub, int m, int *__restrict__ size) {
+__global__ void sg_size2_kernel(const int *__restrict__ row_nnz, const int *__restrict__ ub, int m, int *__restrict__ size,
+                                const int *__restrict__ saved) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
+    // window rows: already computed by the count pass (skip), or deferred to the fill pass because the scratch buffer was full
+    if (saved && saved[i] != -1) { size[i] = saved[i] >= 0 ? -SG_SKIP_CLASS : -WN_CLASS; return; }
     // ub <= SG_TINY: scalar class (size 0); otherwise at least 1 so that the row lands in a table class
     size[i] = ub[i] <= SG_TINY ? 0 : max(max(row_nnz[i], 1), min(ub[i] >> 4, 2048));
 }
 
-struct SgBounds { int limit[SG_NCLS]; };  // class c holds rows with size <= limit[c] (ascending; last = INT_MAX)
+struct SgBounds { int limit[SG_NCLS]; };  // class c holds rows with size <= limit[c] (ascending); a negative size names its class
 
 // Rows -> size classes -> `perm` (rows of each class contiguous, ascending inside a class: the
 // permutation is deterministic).  Every CTA owns one contiguous chunk of rows; class counts are
@@ -362,11 +420,12 @@ __global__ void __launch_bounds__(SG_BIN_THREADS) sg_classify_kernel(const int *
     for (int i = r0 + threadIdx.x; i < r1; i += SG_BIN_THREADS) {
         const int u = size[i];
         int c = 0;
-        while (c < SG_NCLS - 1 && u > bnd.limit[c]) ++c;
+        if (u < 0) c = -u;  // explicit class (window / skip)
+        else while (c < SG_NCLS - 1 && u > bnd.limit[c]) ++c;
         cls[i] = c;
         const unsigned peers = __match_any_sync(__activemask(), c);
         if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&s_count[c], __popc(peers));
-        if (c == SG_NCLS - 1) atomicMax(&s_max, u);
+        if (c == SG_GLOBAL_CLASS) atomicMax(&s_max, u);
     }
     __syncthreads();
     if (threadIdx.x < SG_NCLS) {
@@ -424,6 +483,13 @@ __global__ void __launch_bounds__(SG_BIN_THREADS) sg_bin_kernel(const int *__res
     }
 }
 
+struct SgWin {
+    const int *lo, *span;         // per row of A: all candidate columns lie in [lo, lo + span)
+    int *saved;                   // per row: -1 not a window row | >= 0 offset of the finished row in tcol / tval | -2 deferred
+    int *tcol; double *tval;      // scratch rows of the count pass
+    unsigned long long *cursor; unsigned long long cap;
+};
+
 struct SgArgs {
     SgMat a, b;
     const int *perm; int count;   // rows of this class
@@ -433,6 +499,7 @@ struct SgArgs {
     SgEpilogue ep;
     int *g_table; int *g_list;    // global-table class scratch (per CTA slices)
     int slots;                    // CTA class: a slot table fits next to the key table (2h ints + stage <= shared memory)
+    SgWin win;                    // window class
 };
 
 // ---- tiny rows (ub <= SG_TINY): one THREAD per row.  A warp-per-row walk of a 7-product row is a
@@ -582,6 +649,205 @@ __global__ void __launch_bounds__(256) sg_dense_kernel(SgArgs s, int ncols_b) {
     if (tid == 0 && s_matched != p1 - p0) atomicMax(s.ep.error_flag, 2);
 }
 
+// ---- window rows: one WARP per row, one accumulator per column of the row's window ---------------------------
+// These products are bound by instruction issue, not by memory (ncu, r2: a CTA-per-row version of this kernel that gave every
+// warp a range of the window's columns and walked the k's of a staged batch over 8 short pieces executed 7.8 warp
+// instructions per product, 62 % issue-slot utilisation, 25 ms for the 2.3 G products of level 3's A*P).  So the walk is
+// organised for few instructions per product instead:
+//   * a warp owns the whole row: the entries of one B_k are taken 128 at a time (four independent read-modify-writes per lane,
+//     all of one k: distinct columns, no conflicts), k after k in ascending order with nothing but __syncwarp in between -- no
+//     CTA barriers, no per-piece bookkeeping, no search;
+//   * the descriptors (start, length, a_ik) of 32 k's at a time live in registers (one per lane; the next 32 are fetched while
+//     the current ones are processed), a warp scan of the lengths cuts them into chunks of <= WR_SE entries (a longer B_k is cut
+//     into pieces that run one after the other: the order per output entry stays ascending k);
+//   * the next chunk is brought into the warp's staging buffer with cp.async while the current one is accumulated.
+// SAVE (count pass): the finished row goes to a bump-allocated scratch buffer and its length to row_nnz; the fill pass copies
+// it to its place once row_ptr is known (sg_copy_saved_kernel).  Rows that did not fit are recomputed by the fill pass
+// (!SAVE writes straight into C).
+constexpr unsigned WR_FULL = 0xffffffffu;
+constexpr size_t wn_smem_bytes(int span_max) { return (size_t)9 * span_max + (size_t)24 * WR_SE; }
+
+struct WrDesc { int b0, len, end; double av; };  // lane l: B-row of the l-th k of the group; end = inclusive scan of len
+
+__device__ __forceinline__ WrDesc wr_load_group(const SgMat &a, const SgMat &b, int q, int a1, int lane) {
+    WrDesc d{0, 0, 0, 0.0};
+    if (q + lane < a1) {
+        const int k = a.col[q + lane];
+        d.av = a.val[q + lane];
+        d.b0 = b.rp[k];
+        d.len = b.rp[k + 1] - d.b0;
+    }
+    return d;
+}
+__device__ __forceinline__ void wr_scan(WrDesc &d, int lane) {
+    int incl = d.len;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(WR_FULL, incl, o); if (lane >= o) incl += v; }
+    d.end = incl;
+}
+
+// segments ks .. ke-1 of a group; the first contributes first_cnt entries starting at poff, the others are whole;
+// base = position of the chunk's first entry in the group's scan space
+struct WrChunk { int ks, ke, poff, first_cnt, base; };
+
+// next chunk of the group starting at (ks, poff); advances (ks, poff) past it
+__device__ __forceinline__ WrChunk wr_next_chunk(const WrDesc &d, int lane, int &ks, int &poff) {
+    const int len_ks = __shfl_sync(WR_FULL, d.len, ks), end_ks = __shfl_sync(WR_FULL, d.end, ks);
+    const int rem = len_ks - poff;
+    WrChunk c;
+    c.ks = ks; c.poff = poff; c.base = end_ks - rem;
+    if (rem > WR_SE) {  // a piece of one long B_k
+        c.ke = ks + 1; c.first_cnt = WR_SE; poff += WR_SE;
+    } else {            // as many whole segments as fit (the scan is monotone: the lanes that fit are a prefix of ks..31)
+        const unsigned fits = __ballot_sync(WR_FULL, lane >= ks && d.end - c.base <= WR_SE);
+        c.ke = ks + __popc(fits); c.first_cnt = rem; ks = c.ke; poff = 0;
+    }
+    return c;
+}
+
+__device__ __forceinline__ void wr_issue(const SgMat &b, const WrDesc &d, const WrChunk &c, int lane, int *dc, double *dv) {
+    for (int l = c.ks; l < c.ke; ++l) {
+        const int b0 = __shfl_sync(WR_FULL, d.b0, l), len = __shfl_sync(WR_FULL, d.len, l), end = __shfl_sync(WR_FULL, d.end, l);
+        const bool first = l == c.ks;
+        const int src = b0 + (first ? c.poff : 0), cnt = first ? c.first_cnt : len, pos = first ? 0 : end - len - c.base;
+        for (int e = lane; e < cnt; e += 32) {
+            __pipeline_memcpy_async(dc + pos + e, b.col + src + e, 4);
+            __pipeline_memcpy_async(dv + pos + e, b.val + src + e, 8);
+        }
+    }
+}
+
+__device__ __forceinline__ void wr_consume(const WrDesc &d, const WrChunk &c, int lane, const int *dc, const double *dv, double *acc,
+                                           unsigned char *touched, int jmin) {
+    for (int l = c.ks; l < c.ke; ++l) {
+        const double av = __shfl_sync(WR_FULL, d.av, l);
+        const int len = __shfl_sync(WR_FULL, d.len, l), end = __shfl_sync(WR_FULL, d.end, l);
+        const bool first = l == c.ks;
+        const int cnt = first ? c.first_cnt : len, pos = first ? 0 : end - len - c.base;
+        const int *pc = dc + pos;
+        const double *pv = dv + pos;
+        for (int e = lane; e < cnt; e += 128) {
+            int cc[4];
+            double vv[4], aa[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool ok = e + 32 * u < cnt;
+                cc[u] = ok ? pc[e + 32 * u] - jmin : -1;
+                vv[u] = ok ? pv[e + 32 * u] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) aa[u] = cc[u] >= 0 ? acc[cc[u]] : 0.0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (cc[u] >= 0) { acc[cc[u]] = aa[u] + av * vv[u]; touched[cc[u]] = 1; }
+        }
+        __syncwarp();  // the next k may reach the same column from another lane
+    }
+}
+
+template <bool SAVE>
+__global__ void __launch_bounds__(32) sg_window_kernel(SgArgs s, int span_max) {
+    extern __shared__ __align__(16) unsigned char wn_smem[];
+    double *acc = reinterpret_cast<double *>(wn_smem);                    // span_max
+    double *sval = acc + span_max;                                        // 2 x WR_SE
+    int *scol = reinterpret_cast<int *>(sval + 2 * WR_SE);                // 2 x WR_SE
+    unsigned *touched_w = reinterpret_cast<unsigned *>(scol + 2 * WR_SE);  // span_max bytes
+    unsigned char *touched = reinterpret_cast<unsigned char *>(touched_w);
+    const int lane = threadIdx.x;
+    const int i = s.perm[blockIdx.x];
+    const int jmin = s.win.lo[i], span = s.win.span[i];
+    const int span4 = (span + 3) >> 2;
+    for (int t = lane; t < span; t += 32) acc[t] = 0.0;
+    for (int t = lane; t < span4; t += 32) touched_w[t] = 0u;
+    __syncwarp();
+    const int a0 = s.a.rp[i], a1 = s.a.rp[i + 1];
+    if (a0 < a1) {
+        int qn = a0;  // first k of the group held in dn
+        WrDesc dn = wr_load_group(s.a, s.b, qn, a1, lane), dcur = dn;
+        wr_scan(dn, lane);
+        int ks = 0, poff = 0, buf = 0;
+        WrChunk cur = wr_next_chunk(dn, lane, ks, poff);
+        wr_issue(s.b, dn, cur, lane, scol, sval);
+        __pipeline_commit();
+        bool cur_in_next = true, n_scanned = true;
+        while (true) {
+            if (cur_in_next) {  // the group `cur` was cut from is the one consumed now; fetch the descriptors of the one after it
+                dcur = dn; qn += 32;
+                if (qn < a1) { dn = wr_load_group(s.a, s.b, qn, a1, lane); n_scanned = false; }
+                cur_in_next = false;
+            }
+            WrChunk nxt = cur;
+            bool have = false, nxt_in_next = false;
+            if (ks < 32) {
+                nxt = wr_next_chunk(dcur, lane, ks, poff); have = true;
+            } else if (qn < a1) {
+                if (!n_scanned) { wr_scan(dn, lane); n_scanned = true; }
+                ks = 0; poff = 0;
+                nxt = wr_next_chunk(dn, lane, ks, poff); have = true; nxt_in_next = true;
+            }
+            if (have) {
+                if (nxt_in_next) wr_issue(s.b, dn, nxt, lane, scol + (buf ^ 1) * WR_SE, sval + (buf ^ 1) * WR_SE);
+                else wr_issue(s.b, dcur, nxt, lane, scol + (buf ^ 1) * WR_SE, sval + (buf ^ 1) * WR_SE);
+            }
+            __pipeline_commit();
+            __pipeline_wait_prior(1);  // everything but the chunk just issued has landed
+            __syncwarp();
+            wr_consume(dcur, cur, lane, scol + buf * WR_SE, sval + buf * WR_SE, acc, touched, jmin);
+            if (!have) break;
+            cur = nxt; buf ^= 1; cur_in_next = nxt_in_next;
+        }
+    }
+    __syncwarp();
+    // length of the row, then its entries in column order
+    int n = 0;
+    for (int t = lane; t < span4; t += 32) n += __popc(touched_w[t] & 0x01010101u);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(WR_FULL, n, o);
+    int *o_col; double *o_val;
+    if (SAVE) {
+        long long base = 0;
+        if (lane == 0) {
+            s.row_nnz[i] = n;
+            const unsigned long long off = atomicAdd(s.win.cursor, (unsigned long long)n);
+            const bool fits = off + (unsigned long long)n <= s.win.cap;
+            s.win.saved[i] = fits ? (int)off : -2;
+            base = fits ? (long long)off : -1;
+        }
+        base = __shfl_sync(WR_FULL, base, 0);
+        if (base < 0) return;
+        o_col = s.win.tcol + base; o_val = s.win.tval + base;
+    } else {
+        o_col = s.c_col + s.c_rp[i]; o_val = s.c_val + s.c_rp[i];
+    }
+    // 128 columns per step: lane l holds the four flags of columns 4 (w0 + l) .. + 3 (one word of `touched`)
+    int run = 0;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int w0 = 0; w0 < span4; w0 += 32) {
+        const int wi = w0 + lane;
+        const unsigned w = wi < span4 ? touched_w[wi] : 0u;
+        const unsigned m0 = __ballot_sync(WR_FULL, w & 0x1u), m1 = __ballot_sync(WR_FULL, w & 0x100u),
+                       m2 = __ballot_sync(WR_FULL, w & 0x10000u), m3 = __ballot_sync(WR_FULL, w & 0x1000000u);
+        int pos = run + __popc(m0 & lt) + __popc(m1 & lt) + __popc(m2 & lt) + __popc(m3 & lt);
+        const int j = 4 * wi;
+        if (w & 0x1u) { o_col[pos] = jmin + j; o_val[pos] = acc[j]; ++pos; }
+        if (w & 0x100u) { o_col[pos] = jmin + j + 1; o_val[pos] = acc[j + 1]; ++pos; }
+        if (w & 0x10000u) { o_col[pos] = jmin + j + 2; o_val[pos] = acc[j + 2]; ++pos; }
+        if (w & 0x1000000u) { o_col[pos] = jmin + j + 3; o_val[pos] = acc[j + 3]; }
+        run += __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
+    }
+}
+
+// fill pass of the window rows the count pass finished: scratch row -> its place in C
+__global__ void __launch_bounds__(128) sg_copy_saved_kernel(const int *__restrict__ rows, const int *__restrict__ saved,
+                                                            const int *__restrict__ tcol, const double *__restrict__ tval,
+                                                            const int *__restrict__ c_rp, int *__restrict__ c_col, double *__restrict__ c_val) {
+    const int i = rows[blockIdx.x];
+    const int off = saved[i];
+    if (off < 0) return;
+    const int base = c_rp[i], n = c_rp[i + 1] - base;
+    for (int t = threadIdx.x; t < n; t += 128) { c_col[base + t] = tcol[off + t]; c_val[base + t] = tval[off + t]; }
+}
+
 // Pass 1 for rows with many candidates when B is not too wide: distinct columns counted with a
 // bitmap of ncols(B) bits in shared memory (clearing ncols/8 bytes beats clearing a hash table of
 // 4 * 1.33 * ub bytes for the dense rows of coarse-level products).
@@ -632,18 +898,36 @@ __global__ void __launch_bounds__(256) sg_global_kernel(SgArgs s) {
 struct SgClass { int limit, h, kind; };
 // Only the last class is open-ended (it alone tracks the maximum row size for its table); unused
 // slots repeat the previous limit so that nothing falls into them.
-static const SgClass SG_PASS1[SG_NCLS] = {{SG_TINY, 0, 3},  {192, 256, 0},     {768, 1024, 0},    {3072, 4096, 0},
-                                          {12288, 16384, 1}, {12288, 16384, 1}, {12288, 16384, 1}, {0x7fffffff, 0, 2}};
-static const SgClass SG_PASS2[SG_NCLS] = {{0, 0, 3},        {128, 256, 0},     {512, 1024, 0},    {2048, 4096, 1},
-                                          {16384, 32768, 1}, {16384, 32768, 1}, {16384, 32768, 1}, {0x7fffffff, 0, 2}};
+//   kind 3: thread per row, 4: window rows (sg_window_kernel), 5: nothing to do (fill pass: rows the count pass finished)
+// Classes SG_SKIP_CLASS and WN_CLASS are only entered explicitly (negative sizes); SG_GLOBAL_CLASS is the open-ended one and
+// alone tracks the maximum row size for its table.
+static const SgClass SG_PASS1[SG_NCLS] = {{SG_TINY, 0, 3},   {192, 256, 0}, {768, 1024, 0},     {3072, 4096, 0},
+                                          {12288, 16384, 1}, {12288, 0, 5}, {0x7fffffff, 0, 2}, {0x7fffffff, 0, 4}};
+static const SgClass SG_PASS2[SG_NCLS] = {{0, 0, 3},         {128, 256, 0}, {512, 1024, 0},     {2048, 4096, 1},
+                                          {16384, 32768, 1}, {16384, 0, 5}, {0x7fffffff, 0, 2}, {0x7fffffff, 0, 4}};
+
+// host side of the window class for one product
+struct SgWinHost {
+    bool on = false;
+    int *blk = nullptr;          // lo | span | saved (m + 2 each) | bfirst | blast (nrows(B) + 2 each)
+    int *lo = nullptr, *span = nullptr, *saved = nullptr;
+    unsigned long long *bound = nullptr, *cursor = nullptr;  // in the counters block
+    int span_max = 0;
+    int *tcol = nullptr; double *tval = nullptr; unsigned long long cap = 0;
+    int rows_off = 0, rows = 0;  // slice of `perm` holding the window rows of the count pass
+};
+static unsigned long long sg_win_cap() {  // entries of the scratch buffer at most (12 bytes each)
+    static const unsigned long long cap = [] { const char *e = getenv("FAMG_SG_WIN_CAP"); return e ? strtoull(e, nullptr, 10) : (32ull << 20); }();
+    return cap;
+}
 
 template <bool FILL>
 static famg_status sg_run_pass(famg_ctx *ctx, SgArgs base, const int *d_size, int m, int ncols_b, int *d_cls, int *d_perm,
-                               int *d_counters, int **scratch) {
+                               int *d_counters, int **scratch, SgWinHost *wh) {
     const SgClass *plan = FILL ? SG_PASS2 : SG_PASS1;
     SgBounds bnd;
     for (int c = 0; c < SG_NCLS; ++c) bnd.limit[c] = plan[c].limit;
-    int h_counters[16] = {0};
+    int h_counters[32] = {0};  // [0..7] class counts, [8] largest size of the global class, [12] error flag, [16..] window class
     cudaMemsetAsync(d_counters, 0, sizeof(int) * 16, ctx->stream);
     // contiguous chunks of rows per CTA (multiples of the CTA width so warps stay full)
     const int nblocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(m, SG_BIN_THREADS * 4), 8 * (int64_t)ctx->num_sms));
@@ -653,7 +937,7 @@ static famg_status sg_run_pass(famg_ctx *ctx, SgArgs base, const int *d_size, in
     FAMG_TRY(pool_alloc(ctx, block_bytes, (void **)&d_block));
     sg_classify_kernel<<<nblocks, SG_BIN_THREADS, 0, ctx->stream>>>(d_size, m, chunk, bnd, d_cls, d_block, d_counters, d_counters + 8);
     count_launch(ctx);
-    cudaError_t ce = cudaMemcpyAsync(h_counters, d_counters, sizeof(int) * 16, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t ce = cudaMemcpyAsync(h_counters, d_counters, sizeof(int) * 32, cudaMemcpyDeviceToHost, ctx->stream);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
     int h_cursor[SG_NCLS], acc = 0;
     for (int c = 0; c < SG_NCLS; ++c) { h_cursor[c] = acc; acc += h_counters[c]; }
@@ -676,7 +960,26 @@ static famg_status sg_run_pass(famg_ctx *ctx, SgArgs base, const int *d_size, in
         s.perm = d_perm + off; s.count = cnt;
         const int my_off = off;
         off += cnt;
-        if (cnt == 0) continue;
+        if (cnt == 0 || plan[c].kind == 5) continue;
+        if (plan[c].kind == 4) {
+            if (!wh || !wh->on) FAMG_FAIL(FAMG_ERR_CUDA, "spgemm: window rows without a window plan");
+            if (!FILL) {
+                unsigned long long bound = 0;
+                memcpy(&bound, h_counters + 16, sizeof(bound));
+                wh->span_max = (h_counters[18] + 15) & ~15;
+                wh->cap = std::max<unsigned long long>(std::min(bound, sg_win_cap()), 1);
+                FAMG_TRY(pool_alloc(ctx, sizeof(int) * (size_t)wh->cap, (void **)&wh->tcol));
+                FAMG_TRY(pool_alloc(ctx, sizeof(double) * (size_t)wh->cap, (void **)&wh->tval));
+                wh->rows_off = my_off; wh->rows = cnt;
+            }
+            s.win = SgWin{wh->lo, wh->span, wh->saved, wh->tcol, wh->tval, wh->cursor, wh->cap};
+            const size_t smem = wn_smem_bytes(wh->span_max);
+            CUDA_TRY(cudaFuncSetAttribute(sg_window_kernel<!FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            sg_window_kernel<!FILL><<<(unsigned)cnt, 32, smem, ctx->stream>>>(s, wh->span_max);
+            count_launch(ctx);
+            KERNEL_CHECK();
+            continue;
+        }
         const int bm_words = (ncols_b + 31) / 32;
         if (!FILL && plan[c].kind >= 1 && (size_t)bm_words * 4 <= 160 * 1024) {
             // big rows of the count pass: bitmap over the columns of B
@@ -745,7 +1048,7 @@ famg_status spgemm_impl(const famg_csr *a, const famg_csr *b, const famg_csr *p_
         return csr_finalize_plan(*out);
     }
     SgMat A{a->row_ptr, a->col, a->val}, B{b->row_ptr, b->col, b->val};
-    // one pooled scratch block: ub | size | cls | perm | row_nnz(+1) | rp(+1) | counters(16)
+    // one pooled scratch block: ub | size | cls | perm | row_nnz(+1) | rp(+1) | counters(32)
     const size_t words = (size_t)6 * (m + 2) + 32;
     int *blk = nullptr, *scratch = nullptr;
     famg_csr *c = nullptr;
@@ -754,20 +1057,44 @@ famg_status spgemm_impl(const famg_csr *a, const famg_csr *b, const famg_csr *p_
     if (st != FAMG_OK) return st;
     int *ub = blk, *size = ub + (m + 2), *cls = size + (m + 2), *perm = cls + (m + 2), *row_nnz = perm + (m + 2),
         *rp = row_nnz + (m + 2), *counters = rp + (m + 2);
+    SgWinHost wh;
     auto cleanup = [&]() {
         pool_free(ctx, blk, words * sizeof(int));
         if (scratch) pool_free(ctx, scratch, 0);
+        if (wh.blk) pool_free(ctx, wh.blk, 0);
+        if (wh.tcol) pool_free(ctx, wh.tcol, 0);
+        if (wh.tval) pool_free(ctx, wh.tval, 0);
     };
 #define SG_TRY(expr) do { st = (expr); if (st != FAMG_OK) { cleanup(); if (c) csr_release(c); return st; } } while (0)
     SgArgs base{};
     base.a = A; base.b = B; base.row_nnz = row_nnz;
     base.ep.enabled = 0;
     int total = 0;
+    // window class (sg_window_kernel): worth its set-up only when rows with thousands of products are to be expected
+    static const int win_min_ub = [] { const char *e = getenv("FAMG_SG_WIN_MIN_UB"); return e ? atoi(e) : 3072; }();
+    static const bool win_enabled = [] { const char *e = getenv("FAMG_SG_WINDOW"); return !e || atoi(e) != 0; }();
+    static const int win_min_seg = [] { const char *e = getenv("FAMG_SG_WIN_MIN_SEG"); return e ? atoi(e) : 64; }();
+    const double est_ub = (double)a->nnz / (double)m * ((double)b->nnz / (double)std::max<int64_t>(b->nrows, 1));
+    SgWinPlan wp{};
+    if (win_enabled && !p_for_smoothing && est_ub * 4 >= win_min_ub && b->nrows > 0) {
+        const int nb = (int)b->nrows;
+        SG_TRY(pool_alloc(ctx, sizeof(int) * ((size_t)3 * (m + 2) + (size_t)2 * (nb + 2)), (void **)&wh.blk));
+        wh.on = true;
+        wh.lo = wh.blk; wh.span = wh.lo + (m + 2); wh.saved = wh.span + (m + 2);
+        int *bfirst = wh.saved + (m + 2), *blast = bfirst + (nb + 2);
+        wh.bound = reinterpret_cast<unsigned long long *>(counters + 16);
+        wh.cursor = reinterpret_cast<unsigned long long *>(counters + 20);
+        cudaMemsetAsync(counters + 16, 0, sizeof(int) * 16, ctx->stream);
+        cudaMemsetAsync(wh.saved, 0xff, sizeof(int) * (size_t)(m + 2), ctx->stream);
+        sg_bspan_kernel<<<(unsigned)ceil_div((int64_t)nb * 8, 256), 256, 0, ctx->stream>>>(B, nb, bfirst, blast, counters + 19);
+        count_launch(ctx);
+        wp = SgWinPlan{bfirst, blast, counters + 19, wh.lo, wh.span, wh.bound, counters + 18, win_min_ub, win_min_seg};
+    }
     if (m > 0) {
         PhaseTimer pt(ctx, "    spgemm: bounds + count pass");
-        sg_ub_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, ctx->stream>>>(A, B, m, (int)b->ncols, ub, size);
+        sg_ub_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, ctx->stream>>>(A, B, m, (int)b->ncols, ub, size, wp);
         count_launch(ctx);
-        SG_TRY((sg_run_pass<false>(ctx, base, size, m, (int)b->ncols, cls, perm, counters, &scratch)));
+        SG_TRY((sg_run_pass<false>(ctx, base, size, m, (int)b->ncols, cls, perm, counters, &scratch, &wh)));
     }
     PhaseTimer pt_alloc(ctx, "    spgemm: scan + allocate C");
     SG_TRY(exclusive_scan_i32(ctx, row_nnz, rp, m));
@@ -788,9 +1115,13 @@ famg_status spgemm_impl(const famg_csr *a, const famg_csr *b, const famg_csr *p_
     pt_alloc.~PhaseTimer(); pt_alloc.on = false;
     if (m > 0) {
         PhaseTimer pt(ctx, "    spgemm: fill pass");
-        sg_size2_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, ctx->stream>>>(row_nnz, ub, m, size);
+        if (wh.rows > 0) {  // rows the count pass finished (`perm` still holds the count pass's order)
+            sg_copy_saved_kernel<<<(unsigned)wh.rows, 128, 0, ctx->stream>>>(perm + wh.rows_off, wh.saved, wh.tcol, wh.tval, c->row_ptr, c->col, c->val);
+            count_launch(ctx);
+        }
+        sg_size2_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, ctx->stream>>>(row_nnz, ub, m, size, wh.on ? wh.saved : nullptr);
         count_launch(ctx);
-        SG_TRY((sg_run_pass<true>(ctx, base, size, m, (int)b->ncols, cls, perm, counters, &scratch)));
+        SG_TRY((sg_run_pass<true>(ctx, base, size, m, (int)b->ncols, cls, perm, counters, &scratch, &wh)));
     }
     int h_err = 0;
     if (p_for_smoothing) {

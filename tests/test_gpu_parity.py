@@ -224,6 +224,82 @@ def test_spgemm_bit_exact_all_size_classes(ctx, F):
     assert c.nnz == 2 and c.to_host()[2].tolist() == [0.0, 1.0]
 
 
+def _banded_csr(rng, nrows, ncols, lens, starts, width):
+    """Random CSR whose row i draws lens[i] sorted unique columns from [starts[i], starts[i] + width)."""
+    rp = np.zeros(nrows + 1, dtype=np.int64)
+    cols, vals = [], []
+    for i in range(nrows):
+        lo = int(min(starts[i], ncols - 1)); hi = int(min(lo + width, ncols))
+        k = int(min(lens[i], hi - lo))
+        cols.append(lo + np.sort(rng.choice(hi - lo, size=k, replace=False)))
+        vals.append(rng.standard_normal(k))
+        rp[i + 1] = rp[i] + k
+    return O.Csr.from_arrays(nrows, ncols, rp, np.concatenate(cols), np.concatenate(vals))
+
+
+def _window_case(seed=17, blens=(60, 140)):
+    """A (220 x 3000) times a wide banded B (3000 x 25500, blens entries per row): thousands of products per row, all candidate columns of a row inside a
+    window of <= 6300 columns that moves with the row (the window class of spgemm.cu), except every 7th row of A, which is
+    spread over all of B (no window: table classes) -- both kinds in one product."""
+    rng = np.random.default_rng(seed)
+    m, inner = 220, 3000
+    starts = np.minimum(np.arange(m) * 10, inner - 600)
+    a = _banded_csr(rng, m, inner, rng.integers(130, 170, m), starts, 600)
+    wide = random_csr(rng, m, inner, rng.integers(130, 170, m))
+    rp, col, val = [0], [], []
+    for i in range(m):
+        src = wide if i % 7 == 3 else a
+        col.append(src.col[src.row_ptr[i]:src.row_ptr[i + 1]]); val.append(src.val[src.row_ptr[i]:src.row_ptr[i + 1]])
+        rp.append(rp[-1] + len(col[-1]))
+    a = O.Csr.from_arrays(m, inner, np.array(rp, dtype=np.int64), np.concatenate(col), np.concatenate(val))
+    lens = rng.integers(blens[0], blens[1], inner)
+    b = _banded_csr(rng, inner, 25500, lens, np.arange(inner) * 8, 1500)
+    return a, b
+
+
+def test_spgemm_window_rows(ctx, F):
+    _check_product(ctx, F, *_window_case())
+    rng = np.random.default_rng(18)
+    # rows of B longer than several staging chunks (pieces of one B_k run one after the other), window = all of B
+    a = random_csr(rng, 4, 64, rng.integers(20, 60, 4))
+    _check_product(ctx, F, a, random_csr(rng, 64, 8000, rng.integers(3000, 7000, 64)))
+    # 1 000 - 2 000 rows of B per output row (dozens of descriptor groups), some of them empty
+    a = random_csr(rng, 6, 4000, rng.integers(1000, 2000, 6))
+    _check_product(ctx, F, a, _banded_csr(rng, 4000, 9000, rng.integers(0, 200, 4000), rng.integers(0, 8000, 4000), 1000))
+
+
+def _run_product_check(env_extra, body):
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import numpy as np, oracle as O, faer_amg_b200 as F\n"
+            "from util import to_dev, same_pattern, random_csr\n"
+            "from test_gpu_parity import _window_case, _banded_csr\n"
+            "ctx = F.Context.default(0)\n"
+            "def check(a, b):\n"
+            "    c = to_dev(ctx, a) @ to_dev(ctx, b); oc = O.spgemm(a, b)\n"
+            "    assert same_pattern(c, oc) and np.array_equal(c.to_host()[2], oc.val)\n"
+            "%s\n"
+            "print('product ok')\n") % (root, os.path.join(root, "tests"), body)
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env_extra), capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "product ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_spgemm_window_rows_deferred_to_fill_pass():
+    """With a scratch buffer of 2 000 entries most window rows do not fit: the fill pass recomputes them in place."""
+    _run_product_check({"FAMG_SG_WIN_CAP": "2000"}, "check(*_window_case())")
+
+
+def test_spgemm_window_rows_short_segments():
+    """The window kernel itself on rows it is normally not given (B rows of 0 - 60 and of 1 - 3 entries)."""
+    _run_product_check({"FAMG_SG_WIN_MIN_SEG": "0"},
+                       "check(*_window_case(19, (0, 60)))\n"
+                       "rng = np.random.default_rng(20)\n"
+                       "a = random_csr(rng, 5, 5000, rng.integers(1800, 4000, 5))\n"
+                       "check(a, _banded_csr(rng, 5000, 700, rng.integers(1, 4, 5000), rng.integers(0, 600, 5000), 100))")
+
+
 def test_transpose_bit_exact(ctx, F):
     rng = np.random.default_rng(8)
     for o in [random_csr(rng, 300, 120, rng.integers(0, 9, 300)), O.gen_g27(6), random_csr(rng, 5, 2000, [900, 0, 1500, 3, 40])]:
