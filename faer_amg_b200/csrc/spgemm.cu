@@ -665,7 +665,7 @@ __global__ void __launch_bounds__(256) sg_dense_kernel(SgArgs s, int ncols_b) {
 // it to its place once row_ptr is known (sg_copy_saved_kernel).  Rows that did not fit are recomputed by the fill pass
 // (!SAVE writes straight into C).
 constexpr unsigned WR_FULL = 0xffffffffu;
-constexpr size_t wn_smem_bytes(int span_max) { return (size_t)9 * span_max + (size_t)24 * WR_SE; }
+constexpr size_t wn_smem_bytes(int span_max, int se) { return (size_t)9 * span_max + (size_t)24 * se; }
 
 struct WrDesc { int b0, len, end; double av; };  // lane l: B-row of the l-th k of the group; end = inclusive scan of len
 
@@ -691,15 +691,15 @@ __device__ __forceinline__ void wr_scan(WrDesc &d, int lane) {
 struct WrChunk { int ks, ke, poff, first_cnt, base; };
 
 // next chunk of the group starting at (ks, poff); advances (ks, poff) past it
-__device__ __forceinline__ WrChunk wr_next_chunk(const WrDesc &d, int lane, int &ks, int &poff) {
+__device__ __forceinline__ WrChunk wr_next_chunk(const WrDesc &d, int lane, int &ks, int &poff, int se) {
     const int len_ks = __shfl_sync(WR_FULL, d.len, ks), end_ks = __shfl_sync(WR_FULL, d.end, ks);
     const int rem = len_ks - poff;
     WrChunk c;
     c.ks = ks; c.poff = poff; c.base = end_ks - rem;
-    if (rem > WR_SE) {  // a piece of one long B_k
-        c.ke = ks + 1; c.first_cnt = WR_SE; poff += WR_SE;
+    if (rem > se) {  // a piece of one long B_k
+        c.ke = ks + 1; c.first_cnt = se; poff += se;
     } else {            // as many whole segments as fit (the scan is monotone: the lanes that fit are a prefix of ks..31)
-        const unsigned fits = __ballot_sync(WR_FULL, lane >= ks && d.end - c.base <= WR_SE);
+        const unsigned fits = __ballot_sync(WR_FULL, lane >= ks && d.end - c.base <= se);
         c.ke = ks + __popc(fits); c.first_cnt = rem; ks = c.ke; poff = 0;
     }
     return c;
@@ -746,12 +746,12 @@ __device__ __forceinline__ void wr_consume(const WrDesc &d, const WrChunk &c, in
 }
 
 template <bool SAVE>
-__global__ void __launch_bounds__(32) sg_window_kernel(SgArgs s, int span_max) {
+__global__ void __launch_bounds__(32) sg_window_kernel(SgArgs s, int span_max, int se) {
     extern __shared__ __align__(16) unsigned char wn_smem[];
     double *acc = reinterpret_cast<double *>(wn_smem);                    // span_max
-    double *sval = acc + span_max;                                        // 2 x WR_SE
-    int *scol = reinterpret_cast<int *>(sval + 2 * WR_SE);                // 2 x WR_SE
-    unsigned *touched_w = reinterpret_cast<unsigned *>(scol + 2 * WR_SE);  // span_max bytes
+    double *sval = acc + span_max;                                     // 2 x se
+    int *scol = reinterpret_cast<int *>(sval + 2 * se);                // 2 x se
+    unsigned *touched_w = reinterpret_cast<unsigned *>(scol + 2 * se);  // span_max bytes
     unsigned char *touched = reinterpret_cast<unsigned char *>(touched_w);
     const int lane = threadIdx.x;
     const int i = s.perm[blockIdx.x];
@@ -766,7 +766,7 @@ __global__ void __launch_bounds__(32) sg_window_kernel(SgArgs s, int span_max) {
         WrDesc dn = wr_load_group(s.a, s.b, qn, a1, lane), dcur = dn;
         wr_scan(dn, lane);
         int ks = 0, poff = 0, buf = 0;
-        WrChunk cur = wr_next_chunk(dn, lane, ks, poff);
+        WrChunk cur = wr_next_chunk(dn, lane, ks, poff, se);
         wr_issue(s.b, dn, cur, lane, scol, sval);
         __pipeline_commit();
         bool cur_in_next = true, n_scanned = true;
@@ -779,20 +779,20 @@ __global__ void __launch_bounds__(32) sg_window_kernel(SgArgs s, int span_max) {
             WrChunk nxt = cur;
             bool have = false, nxt_in_next = false;
             if (ks < 32) {
-                nxt = wr_next_chunk(dcur, lane, ks, poff); have = true;
+                nxt = wr_next_chunk(dcur, lane, ks, poff, se); have = true;
             } else if (qn < a1) {
                 if (!n_scanned) { wr_scan(dn, lane); n_scanned = true; }
                 ks = 0; poff = 0;
-                nxt = wr_next_chunk(dn, lane, ks, poff); have = true; nxt_in_next = true;
+                nxt = wr_next_chunk(dn, lane, ks, poff, se); have = true; nxt_in_next = true;
             }
             if (have) {
-                if (nxt_in_next) wr_issue(s.b, dn, nxt, lane, scol + (buf ^ 1) * WR_SE, sval + (buf ^ 1) * WR_SE);
-                else wr_issue(s.b, dcur, nxt, lane, scol + (buf ^ 1) * WR_SE, sval + (buf ^ 1) * WR_SE);
+                if (nxt_in_next) wr_issue(s.b, dn, nxt, lane, scol + (buf ^ 1) * se, sval + (buf ^ 1) * se);
+                else wr_issue(s.b, dcur, nxt, lane, scol + (buf ^ 1) * se, sval + (buf ^ 1) * se);
             }
             __pipeline_commit();
             __pipeline_wait_prior(1);  // everything but the chunk just issued has landed
             __syncwarp();
-            wr_consume(dcur, cur, lane, scol + buf * WR_SE, sval + buf * WR_SE, acc, touched, jmin);
+            wr_consume(dcur, cur, lane, scol + buf * se, sval + buf * se, acc, touched, jmin);
             if (!have) break;
             cur = nxt; buf ^= 1; cur_in_next = nxt_in_next;
         }
@@ -973,9 +973,13 @@ static famg_status sg_run_pass(famg_ctx *ctx, SgArgs base, const int *d_size, in
                 wh->rows_off = my_off; wh->rows = cnt;
             }
             s.win = SgWin{wh->lo, wh->span, wh->saved, wh->tcol, wh->tval, wh->cursor, wh->cap};
-            const size_t smem = wn_smem_bytes(wh->span_max);
+            // FAMG_SG_WIN_SE: other chunk sizes for measurements (1024-entry chunks where they cost no resident row changed nothing:
+            // the rows are bound by the instruction latency of their one warp, not by the prefetch distance)
+            static const int se_forced = [] { const char *e = getenv("FAMG_SG_WIN_SE"); return e ? atoi(e) : 0; }();
+            const int se = se_forced > 0 ? se_forced : WR_SE;
+            const size_t smem = wn_smem_bytes(wh->span_max, se);
             CUDA_TRY(cudaFuncSetAttribute(sg_window_kernel<!FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            sg_window_kernel<!FILL><<<(unsigned)cnt, 32, smem, ctx->stream>>>(s, wh->span_max);
+            sg_window_kernel<!FILL><<<(unsigned)cnt, 32, smem, ctx->stream>>>(s, wh->span_max, se);
             count_launch(ctx);
             KERNEL_CHECK();
             continue;
