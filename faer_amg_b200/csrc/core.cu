@@ -167,7 +167,7 @@ void csr_release(famg_csr *a) {
     if (!a) return;
     if (a->refs.fetch_sub(1) == 1) {
         // ordered after everything already queued on the context's stream that may read the buffers,
-        // and after the communication stream (NCCL halo path: boundary applies read operators there)
+        // and after the communication stream (halo exchange: boundary applies read operators there)
         cudaStream_t st = a->ctx->stream;
         if (a->ctx->ev_release && a->ctx->comm_used.load(std::memory_order_relaxed)) {
             cudaEventRecord(a->ctx->ev_release, a->ctx->comm_stream);
