@@ -79,6 +79,7 @@ struct famg_ctx {
     int spmv_variant = 2;
     int tma_min_rows = 1 << 17;
     int spmm_cb = 2;  // right-hand sides per row walk for k > 1 (1 | 2); FAMG_SPMM_CB / set_option("spmm_cb")
+    int block_build_host = 0;  // 1: block smoother blocks inverted on the host (set_option("block_build_host"); A/B of the device build)
 };
 
 struct famg_csr {

@@ -376,6 +376,8 @@ famg_status famg_ctx_set_option(famg_ctx *ctx, const char *key, int64_t value) {
     } else if (!strcmp(key, "spmm_cb")) {
         if (value != 1 && value != 2) FAMG_FAIL(FAMG_ERR_INVALID, "spmm_cb must be 1 or 2");
         ctx->spmm_cb = (int)value;
+    } else if (!strcmp(key, "block_build_host")) {
+        ctx->block_build_host = value != 0;
     } else if (!strcmp(key, "trace")) {
         CUDA_TRY(cudaSetDevice(ctx->device));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));

@@ -196,6 +196,180 @@ famg_status famg_smoother_cholesky(const famg_csr *a, famg_smoother **out) {
     return FAMG_OK;
 }
 
+// ---------------------------------------------------------------- block smoother build on the device
+// BlockSmoother::new / diagonally_compensate (block_smoothers.rs:88-123, 293-324) for scalar operators.  One thread per
+// aggregate: compensated principal block, Cholesky, explicit inverse -- the statements of the host routine below in the same
+// order (products and sums are rounded separately on both sides: -fmad=false here, no FMA contraction there), so both builds
+// produce the same bits.  The per-aggregate work arrays are interleaved across aggregates (element e of aggregate g at
+// e * n_aggs + g): the threads of a warp walk the same element of neighbouring aggregates, coalesced.
+constexpr int BS_DEV_MAX_AGG = 64;  // larger aggregates: host build (one thread per block would crawl)
+
+// node -> (aggregate, position inside it); flags: 1 = node out of range or in two aggregates, 2 = nodes not ascending
+__global__ void bs_node_map_kernel(const int *__restrict__ agg_ptr, const int *__restrict__ agg_nodes, int n_aggs, int n,
+                                   int *__restrict__ node_agg, int *__restrict__ node_local, int *__restrict__ flags) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_aggs) return;
+    const int u0 = agg_ptr[g], u1 = agg_ptr[g + 1];
+    for (int u = u0; u < u1; ++u) {
+        const int node = agg_nodes[u];
+        if (node < 0 || node >= n) { atomicOr(flags, 1); continue; }
+        if (u > u0 && agg_nodes[u - 1] >= node) atomicOr(flags, 2);
+        if (atomicExch(&node_agg[node], g) != -1) atomicOr(flags, 1);
+        node_local[node] = u - u0;
+    }
+}
+
+// row i of the block-diagonal M^-1 has one entry per node of i's aggregate
+__global__ void bs_rowlen_kernel(const int *__restrict__ agg_ptr, const int *__restrict__ node_agg, int n, int *__restrict__ len) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int g = node_agg[i];
+    len[i] = g >= 0 ? agg_ptr[g + 1] - agg_ptr[g] : 0;
+}
+
+__global__ void __launch_bounds__(128) bs_build_kernel(const int *__restrict__ rp, const int *__restrict__ col, const double *__restrict__ val,
+                                                       const int *__restrict__ agg_ptr, const int *__restrict__ agg_nodes,
+                                                       const int *__restrict__ node_agg, const int *__restrict__ node_local,
+                                                       const double *__restrict__ diag, int n_aggs, double *__restrict__ wb,
+                                                       double *__restrict__ wl, const int *__restrict__ m_rp, int *__restrict__ m_col,
+                                                       double *__restrict__ m_val, int *__restrict__ bad_agg) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_aggs) return;
+    const size_t S = (size_t)n_aggs;
+    const int u0 = agg_ptr[g], na = agg_ptr[g + 1] - u0;
+    const int *nodes = agg_nodes + u0;
+#define BS_B(r, c) wb[((size_t)(r) + (size_t)(c) * na) * S + g]
+#define BS_L(r, c) wl[((size_t)(r) + (size_t)(c) * na) * S + g]
+    for (int e = 0; e < na * na; ++e) { wb[(size_t)e * S + g] = 0.0; wl[(size_t)e * S + g] = 0.0; }
+    for (int li = 0; li < na; ++li) {
+        const int i = nodes[li];
+        // entries in row order; the diagonal and the lumped off-aggregate couplings are summed in that order
+        bool diag_seen = false;
+        double dsum = 0.0;
+        const double di = diag[i];
+        for (int q = rp[i]; q < rp[i + 1]; ++q) {
+            const int j = col[q];
+            if (node_agg[j] == g) {
+                const int lj = node_local[j];
+                if (lj == li) { dsum = diag_seen ? dsum + val[q] : val[q]; diag_seen = true; }
+                else BS_B(li, lj) = val[q];
+            } else {
+                const double comp = 0.5 * sqrt(di / diag[j]) * fabs(val[q]);
+                dsum = diag_seen ? dsum + comp : comp; diag_seen = true;
+            }
+        }
+        BS_B(li, li) = dsum;
+    }
+    // the reference factorises the upper side of the transpose == lower triangle of the block
+    for (int c = 0; c < na; ++c)
+        for (int r = 0; r < c; ++r) BS_B(r, c) = BS_B(c, r);
+    for (int j = 0; j < na; ++j) {  // Cholesky, column by column
+        double d = BS_B(j, j);
+        for (int k = 0; k < j; ++k) d -= BS_L(j, k) * BS_L(j, k);
+        if (!(d > 0.0)) { atomicMin(bad_agg, g); return; }
+        d = sqrt(d);
+        BS_L(j, j) = d;
+        for (int i = j + 1; i < na; ++i) {
+            double t = BS_B(i, j);
+            for (int k = 0; k < j; ++k) t -= BS_L(i, k) * BS_L(j, k);
+            BS_L(i, j) = t / d;
+        }
+    }
+    for (int c = 0; c < na; ++c) {  // column c of the inverse: L L^T x = e_c
+        for (int i = 0; i < na; ++i) BS_B(i, c) = i == c ? 1.0 : 0.0;
+        for (int i = 0; i < na; ++i) {
+            double t = BS_B(i, c);
+            for (int j = 0; j < i; ++j) t -= BS_L(i, j) * BS_B(j, c);
+            BS_B(i, c) = t / BS_L(i, i);
+        }
+        for (int i = na - 1; i >= 0; --i) {
+            double t = BS_B(i, c);
+            for (int j = i + 1; j < na; ++j) t -= BS_L(j, i) * BS_B(j, c);
+            BS_B(i, c) = t / BS_L(i, i);
+        }
+    }
+    for (int li = 0; li < na; ++li) {
+        const int base = m_rp[nodes[li]];
+        for (int lj = 0; lj < na; ++lj) { m_col[base + lj] = nodes[lj]; m_val[base + lj] = BS_B(li, lj); }
+    }
+#undef BS_B
+#undef BS_L
+}
+
+// returns FAMG_ERR_UNSUPPORTED (without setting an error) when the partition is not one for the device build
+static famg_status block_smoother_build_dev(const famg_csr *a, int64_t n_aggs, const uint64_t *agg_ptr, const uint64_t *agg_nodes,
+                                            famg_smoother **out) {
+    famg_ctx *ctx = a->ctx;
+    const int64_t n = a->nrows;
+    int64_t na_max = 0, total = 0;
+    for (int64_t g = 0; g < n_aggs; ++g) {
+        if (agg_ptr[g + 1] < agg_ptr[g]) FAMG_FAIL(FAMG_ERR_INVALID, "invalid partition");
+        const int64_t na = (int64_t)(agg_ptr[g + 1] - agg_ptr[g]);
+        na_max = std::max(na_max, na); total += na * na;
+    }
+    // interleaved work arrays hold na_max^2 elements for every aggregate: only for partitions of similar, small aggregates
+    if (n == 0 || n_aggs == 0 || na_max > BS_DEV_MAX_AGG || total > 0x7fffffff || na_max * na_max * n_aggs > 2 * total + 4096)
+        return FAMG_ERR_UNSUPPORTED;
+    std::vector<int> h_ptr((size_t)n_aggs + 1), h_nodes((size_t)n);
+    for (int64_t g = 0; g <= n_aggs; ++g) h_ptr[(size_t)g] = (int)agg_ptr[g];
+    for (int64_t u = 0; u < n; ++u) {
+        if (agg_nodes[u] >= (uint64_t)n) FAMG_FAIL(FAMG_ERR_INVALID, "invalid partition");
+        h_nodes[(size_t)u] = (int)agg_nodes[u];
+    }
+    const size_t work = (size_t)(na_max * na_max) * (size_t)n_aggs;
+    int *d_ptr = nullptr, *d_nodes = nullptr, *d_map = nullptr, *d_flags = nullptr;
+    double *d_diag = nullptr, *wb = nullptr, *wl = nullptr;
+    famg_csr *minv = nullptr;
+    auto cleanup = [&]() {
+        pool_free(ctx, d_ptr, 0); pool_free(ctx, d_nodes, 0); pool_free(ctx, d_map, 0); pool_free(ctx, d_flags, 0);
+        pool_free(ctx, d_diag, 0); pool_free(ctx, wb, 0); pool_free(ctx, wl, 0);
+    };
+#define BS_TRY(expr) do { famg_status s__ = (expr); if (s__ != FAMG_OK) { cleanup(); if (minv) csr_release(minv); return s__; } } while (0)
+#define BS_CUDA(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { set_error("block smoother build: %s", cudaGetErrorString(e__)); BS_TRY(FAMG_ERR_CUDA); } } while (0)
+    BS_TRY(pool_alloc(ctx, sizeof(int) * ((size_t)n_aggs + 1), (void **)&d_ptr));
+    BS_TRY(pool_alloc(ctx, sizeof(int) * (size_t)n, (void **)&d_nodes));
+    BS_TRY(pool_alloc(ctx, sizeof(int) * (size_t)3 * (size_t)n, (void **)&d_map));  // node_agg | node_local | row lengths
+    BS_TRY(pool_alloc(ctx, 256, (void **)&d_flags));                               // [0] partition flags, [1] missing diagonals, [2] first non-SPD aggregate
+    BS_TRY(pool_alloc(ctx, sizeof(double) * (size_t)n, (void **)&d_diag));
+    BS_TRY(pool_alloc(ctx, sizeof(double) * work, (void **)&wb));
+    BS_TRY(pool_alloc(ctx, sizeof(double) * work, (void **)&wl));
+    int *node_agg = d_map, *node_local = d_map + n, *row_len = d_map + 2 * n;
+    const int h_init[3] = {0, 0, 0x7fffffff};
+    BS_CUDA(cudaMemcpyAsync(d_ptr, h_ptr.data(), sizeof(int) * ((size_t)n_aggs + 1), cudaMemcpyHostToDevice, ctx->stream));
+    BS_CUDA(cudaMemcpyAsync(d_nodes, h_nodes.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    BS_CUDA(cudaMemcpyAsync(d_flags, h_init, sizeof(h_init), cudaMemcpyHostToDevice, ctx->stream));
+    BS_CUDA(cudaMemsetAsync(node_agg, 0xff, sizeof(int) * (size_t)n, ctx->stream));
+    const unsigned grid_n = (unsigned)ceil_div(n, 256), grid_g = (unsigned)ceil_div(n_aggs, 128);
+    bs_node_map_kernel<<<grid_g, 128, 0, ctx->stream>>>(d_ptr, d_nodes, (int)n_aggs, (int)n, node_agg, node_local, d_flags);
+    bs_rowlen_kernel<<<grid_n, 256, 0, ctx->stream>>>(d_ptr, node_agg, (int)n, row_len);
+    diag_extract_linear_kernel<<<grid_n, 256, 0, ctx->stream>>>(a->row_ptr, a->col, a->val, (int)n, d_diag, d_flags + 1);
+    count_launch(ctx, 3);
+    BS_CUDA(cudaGetLastError());
+    int h_flags[3] = {0, 0, 0};
+    BS_CUDA(cudaMemcpyAsync(h_flags, d_flags, sizeof(h_flags), cudaMemcpyDeviceToHost, ctx->stream));
+    BS_CUDA(cudaStreamSynchronize(ctx->stream));  // also: h_ptr / h_nodes / h_init have been read
+    if (h_flags[0] & 1) { set_error("invalid partition"); BS_TRY(FAMG_ERR_INVALID); }
+    if (h_flags[0] & 2) { set_error("aggregate nodes must ascend"); BS_TRY(FAMG_ERR_INVALID); }
+    if (h_flags[1]) { set_error("%d rows have no diagonal entry", h_flags[1]); BS_TRY(FAMG_ERR_NUMERIC); }
+    BS_TRY(csr_alloc(ctx, n, n, total, &minv));
+    BS_TRY(exclusive_scan_i32(ctx, row_len, minv->row_ptr, n));
+    bs_build_kernel<<<grid_g, 128, 0, ctx->stream>>>(a->row_ptr, a->col, a->val, d_ptr, d_nodes, node_agg, node_local, d_diag, (int)n_aggs, wb, wl,
+                                                     minv->row_ptr, minv->col, minv->val, d_flags + 2);
+    count_launch(ctx);
+    BS_CUDA(cudaGetLastError());
+    BS_CUDA(cudaMemcpyAsync(h_flags, d_flags, sizeof(h_flags), cudaMemcpyDeviceToHost, ctx->stream));
+    BS_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (h_flags[2] != 0x7fffffff) { set_error("aggregate %d block is not positive definite", h_flags[2]); BS_TRY(FAMG_ERR_NUMERIC); }
+    BS_TRY(csr_finalize_plan(minv));
+    cleanup();
+#undef BS_TRY
+#undef BS_CUDA
+    famg_smoother *s = new famg_smoother();
+    s->ctx = ctx; s->kind = SM_SPARSE_INV; s->n = n; s->minv = minv;
+    *out = s;
+    return FAMG_OK;
+}
+
 // Dense SPD inverse of a small block on the host (Cholesky, then solve for the identity).
 static bool host_spd_inverse(int n, std::vector<double> &m /* n x n col-major, in: A, out: A^-1 */) {
     std::vector<double> l((size_t)n * n, 0.0);
@@ -235,6 +409,10 @@ famg_status famg_smoother_block(const famg_csr *a, int64_t n_aggs, const uint64_
     if (a->nrows != a->ncols) FAMG_FAIL(FAMG_ERR_INVALID, "block smoother needs a square matrix");
     if ((int64_t)agg_ptr[n_aggs] != a->nrows) FAMG_FAIL(FAMG_ERR_INVALID, "partition does not cover the matrix");  // block_smoothers.rs:91
     CUDA_TRY(cudaSetDevice(a->ctx->device));
+    if (!a->ctx->block_build_host) {  // aggregates of at most BS_DEV_MAX_AGG nodes: built on the device, same bits
+        const famg_status ds = block_smoother_build_dev(a, n_aggs, agg_ptr, agg_nodes, out);
+        if (ds != FAMG_ERR_UNSUPPORTED) return ds;
+    }
     HostCsr h;
     FAMG_TRY(csr_to_host(a, &h));
     const int64_t n = a->nrows;

@@ -192,6 +192,35 @@ def test_block_smoother(ctx, F):
     assert np.max(np.abs(bs.apply(r) - want)) <= 1e-12 * np.max(np.abs(want))
 
 
+def test_block_smoother_device_build_equals_host_build(ctx, F):
+    """The blocks are assembled, factorised and inverted on the device (one thread per aggregate) with the statements of the
+    host routine in the same order: same bits.  Odd grid sizes give aggregates of 8, 4, 2 and 1 nodes."""
+    dims = (10, 7, 5)
+    o = O.gen_g7(*dims)
+    part, _ = F.geometric_partition(dims)
+    d = to_dev(ctx, o)
+    r = np.random.default_rng(16).standard_normal((o.nrows, 3))
+    dev = F.BlockSmoother.new(F.SparseMatOp(d), part).apply(r)
+    ctx.set_option("block_build_host", 1)
+    try:
+        host = F.BlockSmoother.new(F.SparseMatOp(d), part).apply(r)
+    finally:
+        ctx.set_option("block_build_host", 0)
+    assert np.array_equal(dev, host)
+    want = O.block_smoother_apply(o, part.agg_ptr, part.agg_nodes, r)
+    assert np.max(np.abs(dev - want)) <= 1e-12 * np.max(np.abs(want))
+    # a block that is not positive definite is an error on both paths (block_smoothers.rs: the Cholesky factorisation fails)
+    bad = to_dev(ctx, O.Csr.from_triplets(2, 2, [0, 0, 1, 1], [0, 1, 0, 1], [1.0, 2.0, 2.0, 1.0]))
+    one = F.Partition.from_node_to_agg(np.zeros(2, dtype=np.int64))
+    for host_build in (0, 1):
+        ctx.set_option("block_build_host", host_build)
+        try:
+            with pytest.raises(F.FamgError):
+                F.BlockSmoother.new(F.SparseMatOp(bad), one)
+        finally:
+            ctx.set_option("block_build_host", 0)
+
+
 # ------------------------------------------------------------------ SpGEMM / transpose / RAP
 def _check_product(ctx, F, oa, ob):
     c = to_dev(ctx, oa) @ to_dev(ctx, ob)
