@@ -139,7 +139,9 @@ famg_status famg_smoother_diag_from_host(famg_ctx *ctx, int64_t n, const double 
 famg_status famg_smoother_cholesky(const famg_csr *a, famg_smoother **out);
 /* BlockSmoother::new over aggregates with diagonal compensation (block_smoothers.rs:88-123,
  * 293-324), materialised as the block-diagonal M^-1 of into_sparse_mat (:125-146).
- * agg_ptr[n_aggs+1], agg_nodes ascending inside each aggregate. */
+ * agg_ptr[n_aggs+1], agg_nodes ascending inside each aggregate.  The blocks are assembled, Cholesky-factorised and
+ * inverted on the device (aggregates of at most 64 nodes of similar size; otherwise, or with
+ * famg_ctx_set_option(ctx, "block_build_host", 1), by the host routine -- same statements, same bits). */
 famg_status famg_smoother_block(const famg_csr *a, int64_t n_aggs, const uint64_t *agg_ptr,
                                 const uint64_t *agg_nodes, famg_smoother **out);
 /* the same for vector problems: the partition is over nodes of `vdim` dofs (dof = node * vdim + offset);
@@ -388,7 +390,8 @@ famg_status famg_dist_mg_create_levels(famg_comm *c, int nlevels, famg_dmat *con
 /* ---- instrumentation ---------------------------------------------------------------------- */
 /* tuning knobs for A/B measurements: "spmv_variant" (1 = one staged chunk per CTA, 2 = persistent
  * TMA-fed pipeline), "tma_min_rows" (smallest operator the persistent kernel is used for), "spmm_cb"
- * (right-hand sides per row walk for k > 1: 1 | 2).  Changing an option invalidates captured cycle graphs.
+ * (right-hand sides per row walk for k > 1: 1 | 2), "block_build_host" (1 = famg_smoother_block inverts its blocks on the
+ * host).  Changing an option invalidates captured cycle graphs.
  * One solve at a time per context: PCG work vectors and reduction scratch are context-owned. */
 famg_status famg_ctx_set_option(famg_ctx *ctx, const char *key, int64_t value);
 /* In-kernel timeline: famg_ctx_set_option(ctx, "trace", 1) makes the SpMV-family and halo-exchange kernels launched (or
