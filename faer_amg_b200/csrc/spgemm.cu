@@ -18,8 +18,10 @@
 //           and locate their slot by binary search.  Within one k every j is unique, so there are
 //           no write conflicts and no atomics on values: the result is deterministic and has the
 //           reference's summation order.
-//   classes one warp per row (tables of 64..4096 slots in shared memory), one CTA per row (up to
-//           192 KB of shared memory), and per-CTA tables in global memory for anything larger.
+//   classes one thread per row (<= 32 products), one warp per row (tables of 64..4096 slots in shared memory), one CTA
+//           per row (up to 192 KB of shared memory; one f64 accumulator per column when B is narrow), per-CTA tables in
+//           global memory for anything larger -- and the window class (sg_window_kernel): rows with thousands of products
+//           whose candidate columns fit a window of <= 11 264 columns are computed ONCE, by one warp per row, in the count pass.
 // The prolongator-smoothing epilogue  S_i <- -(w/a_ii) S_i + P_i  is fused into pass 2.
 #include <cuda_pipeline.h>
 
@@ -109,8 +111,6 @@ struct SgStage {
     int nk, partial;
 };
 
-// DENSE: `vals` is indexed by the column itself (ncols(B) accumulators), `touched` records the
-// structural pattern; no search pass.
 // column -> output slot.  slot16 mirrors the key table of the insertion pass: position h holds the rank of the key that
 // landed there among the sorted distinct columns, so a lookup re-walks the key's own probe sequence (1-2 steps at load
 // <= 0.5) and recognises it by list[slot] == j -- two shared-memory reads per step instead of the 7-9 dependent reads of a
@@ -133,6 +133,8 @@ __device__ __forceinline__ int sg_find_slot(int j, const int *__restrict__ list,
     return lo;
 }
 
+// DENSE: `vals` is indexed by the column itself (ncols(B) accumulators), `touched` records the
+// structural pattern; no search pass.
 template <bool DENSE>
 __device__ void sg_accumulate_staged(int tid, const SgMat &a, const SgMat &b, int a0, int a1, const int *list, int n, double *vals,
                                      SgStage &st, unsigned char *touched = nullptr, const unsigned short *slot16 = nullptr, int hmask = 0) {
